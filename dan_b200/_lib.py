@@ -1,0 +1,164 @@
+"""ctypes binding of libdan_b200.so (include/dan_b200.h).
+
+PyTorch is used for tensor hand-off only: every call passes ``tensor.data_ptr()``
+and the current CUDA stream.  There is NO fallback: if the shared library is
+missing, or a tensor is not a contiguous CUDA tensor, the call raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdan_b200.so")
+
+DAN_MAX_LAYERS = 16
+DAN_MAX_DEPTH_TOTAL = 128
+DAN_MATCH_DUAL = 0
+DAN_MATCH_MINING = 1
+
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_f32 = ctypes.c_float
+c_vp = ctypes.c_void_p
+c_sz = ctypes.c_size_t
+
+
+class DanError(RuntimeError):
+    """A libdan_b200 call returned a negative status (mirrors the TF op's InvalidArgument)."""
+
+    def __init__(self, code, msg):
+        super().__init__("libdan_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Pyramid(ctypes.Structure):
+    _fields_ = [
+        ("num_layers", c_i32), ("image_h", c_i32), ("image_w", c_i32),
+        ("layer_h", c_i32 * DAN_MAX_LAYERS), ("layer_w", c_i32 * DAN_MAX_LAYERS),
+        ("depth", c_i32 * DAN_MAX_LAYERS), ("clip", c_i32 * DAN_MAX_LAYERS),
+        ("stride", c_f32 * DAN_MAX_LAYERS),
+        ("offset_h", c_f32 * DAN_MAX_LAYERS), ("offset_w", c_f32 * DAN_MAX_LAYERS),
+        ("border", c_f32 * DAN_MAX_LAYERS),
+        ("anchor_h", c_f32 * DAN_MAX_DEPTH_TOTAL), ("anchor_w", c_f32 * DAN_MAX_DEPTH_TOTAL),
+    ]
+
+
+class EncodeParams(ctypes.Structure):
+    _fields_ = [
+        ("matcher", c_i32), ("ignore_threshold", c_f32), ("positive_threshold", c_f32),
+        ("prior_scaling", c_f32 * 4), ("pa_scale", c_f32), ("debug", c_i32),
+        ("negative_low_thres", c_f32), ("min_match", c_i32), ("stop_positive_thres", c_f32),
+        ("ignore_between", c_i32), ("gt_max_first", c_i32),
+    ]
+
+
+class PostprocessParams(ctypes.Structure):
+    _fields_ = [
+        ("num_classes", c_i32), ("image_h", c_i32), ("image_w", c_i32),
+        ("select_threshold", c_f32), ("min_size", c_f32), ("keep_topk", c_i32),
+        ("nms_topk", c_i32), ("nms_threshold", c_f32), ("prior_scaling", c_f32 * 4),
+    ]
+
+
+_SIGNATURES = {
+    "dan_version": (ctypes.c_int, []),
+    "dan_last_error": (ctypes.c_char_p, []),
+    "dan_device_ok": (ctypes.c_int, []),
+    "dan_anchor_count": (c_i64, [ctypes.POINTER(Pyramid)]),
+    "dan_generate_anchors": (ctypes.c_int, [ctypes.POINTER(Pyramid), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dan_iou_matrix": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "dan_intersection_matrix": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "dan_match_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "dan_small_mining_match": (ctypes.c_int, [c_vp, c_i32, c_i32, c_f32, c_f32, c_f32, c_i32, c_f32, c_vp, c_vp,
+                                              c_vp, c_sz, c_vp]),
+    "dan_dual_max_match": (ctypes.c_int, [c_vp, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_encode_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
+    "dan_encode_batch": (ctypes.c_int, [ctypes.POINTER(EncodeParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp,
+                                        c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_decode_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(c_f32), c_vp, c_vp]),
+    "dan_softmax": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "dan_select_bboxes": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    "dan_clip_bboxes": (ctypes.c_int, [c_vp, c_i64, c_f32, c_f32, c_vp, c_vp]),
+    "dan_filter_bboxes": (ctypes.c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    "dan_bbox_convert": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "dan_sort_workspace_bytes": (c_sz, [c_i64, c_i32]),
+    "dan_sort_bboxes": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_nms_workspace_bytes": (c_sz, [c_i64, c_i32]),
+    "dan_nms_bboxes": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_postprocess_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32, c_i32]),
+    "dan_postprocess_batch": (ctypes.c_int, [ctypes.POINTER(PostprocessParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                             c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """Load libdan_b200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "dan_b200: %s is missing. Build it with `python -m dan_b200.build` "
+                "(nvcc, sm_100a). There is no CPU / PyTorch fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DanError(rc, lib().dan_last_error().decode("utf-8", "replace"))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_device():
+    """The product path is CUDA only: refuse to run without an sm_100 device."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("dan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def dev_ptr(t, dtype=None, name="tensor"):
+    """data_ptr() of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA torch.Tensor (no CPU fallback)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def as_f32(t, device=None):
+    """Hand-off helper: move python lists / numpy arrays / tensors to a contiguous fp32 CUDA tensor."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t, dtype=torch.float32)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class Workspace(object):
+    """Grow-only device scratch buffer owned by the caller side (the library never allocates)."""
+
+    def __init__(self):
+        self._buf = None
+
+    def get(self, nbytes, device):
+        nbytes = int(nbytes)
+        if self._buf is None or self._buf.numel() < nbytes or self._buf.device != device:
+            self._buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        return self._buf

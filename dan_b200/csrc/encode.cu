@@ -1,0 +1,811 @@
+// K2: anchor x GT matching and box encoding.
+//
+//   fused path  (dan_encode_batch):  IoU is evaluated on the fly, tile-culled, and
+//                                    never written to HBM (the reference
+//                                    materialises [N,M] fp32 and makes ~26 passes
+//                                    over it, anchor_manipulator.py:24-105,287).
+//   dense path  (dan_small_mining_match / dan_dual_max_match): the literal custom
+//                                    op boundary, overlaps [N,M] given in HBM.
+//
+// Three launches per batch, all images of the batch in each launch:
+//   pass 1  per-GT column maximum (the only cross-anchor quantity of stage 2 /
+//           of the dual matcher's "GT side") -> atomicMax on fp32 bit patterns
+//   pass 2  per anchor: row max/argmax (stage 1), tie test against the column
+//           maxima (stage 2 / dual claim), labels, encode, all outputs; mining
+//           also histograms matches per GT and buckets compensation candidates
+//   pass 3  (mining only) stage 3 "hard face compensation": one warp per image
+//           walks the GTs in ascending order (the stage is order dependent,
+//           small_mining_match.cc:199-222) and patches the few affected anchors
+//
+// Culling (fused path): a warp owns 32 consecutive anchors; it reduces their
+// bounding box with redux.sync and tests 32 GT boxes per ballot against it.  Only
+// GTs that can intersect some anchor of the warp are evaluated.  A skipped pair
+// has an empty intersection, for which the reference computes exactly 0, so the
+// result is unchanged.  GTs whose column maximum is 0 (dual: `==` claim) or below
+// FLT_EPSILON (mining: tie band) tie with zero-overlap anchors as well and are
+// therefore never culled in pass 2.
+//
+// Precondition shared with the op's own doc string (small_mining_match.cc:42-43):
+// overlaps are in [0, 1], i.e. boxes have non-negative (+1 convention) extents.
+#include <float.h>
+
+#include "common.cuh"
+#include "heap_order.cuh"
+
+namespace dan {
+
+constexpr int kEncThreads = 256;
+constexpr int kGtChunk = 1024;     // GT boxes staged in shared memory at a time
+constexpr int kBucketCap = 64;     // compensation candidates bucketed per GT before spilling
+constexpr int kListCap = 256;      // shared-memory candidate list of pass 3
+
+struct EncArgs {
+  // anchors (fused)
+  const float* ay0;
+  const float* ax0;
+  const float* ay1;
+  const float* ax1;
+  const uint8_t* mask;
+  int n;
+  // ground truth (fused), CSR over the batch
+  const float4* gt;
+  const int32_t* gt_off;
+  // dense
+  const float* overlaps;
+  int m_dense;
+  // parameters
+  float low, high;       // dual: low/high thresholds; mining: negative_high / positive
+  float neg_low, stop;
+  int min_match;
+  int ignore_between, gt_max_first;
+  float ps0, ps1, ps2, ps3;
+  float pa_scale;
+  int debug;
+  // workspace
+  uint32_t* colmax;      // [G] fp32 bit patterns (>= 0)
+  int32_t* cnt;          // [G] anchors matched per GT after stage 2
+  int32_t* haspos;       // [G] GT has a positive anchor-side match (dual, gt_max_first=0)
+  int32_t* fill;         // [G] candidates pushed per GT
+  HeapItem* bucket;      // [G, kBucketCap]
+  HeapItem* spill;       // [B, 2, n]
+  // outputs
+  float4* targets;
+  int64_t* labels;
+  float* scores;
+  float4* matched;
+  int32_t* match32;
+  int64_t* match64;
+};
+
+// image b of the fused path owns per-GT slots [off[b] + b, off[b+1] + b + 1): one
+// extra slot per image holds the dummy box of an empty image (:286).
+struct ImageGt {
+  int off0;     // first GT row in A.gt
+  int m_real;   // GT rows given
+  int m_eff;    // max(m_real, 1)
+  int slot0;    // first per-GT workspace slot
+};
+
+template <bool DENSE>
+DAN_D ImageGt image_gt(const EncArgs& A, int b) {
+  ImageGt g;
+  if (DENSE) {
+    g.off0 = 0;
+    g.m_real = g.m_eff = A.m_dense;
+    g.slot0 = 0;
+  } else {
+    g.off0 = A.gt_off[b];
+    g.m_real = A.gt_off[b + 1] - g.off0;
+    g.m_eff = g.m_real > 0 ? g.m_real : 1;
+    g.slot0 = g.off0 + b;
+  }
+  return g;
+}
+
+DAN_D float4 gt_box(const EncArgs& A, const ImageGt& ig, int j) {
+  return (j < ig.m_real) ? __ldg(A.gt + ig.off0 + j) : make_float4(0.f, 0.f, 1.f, 1.f);
+}
+
+// The box an anchor is MATCHED with: itself (encode_anchors) or shrunk about its
+// centre by pa_scale (encode_pa_anchors, anchor_manipulator.py:337-342).
+struct AnchorBox {
+  float y0, x0, y1, x1;  // original anchor
+  float my0, mx0, my1, mx1, marea;  // matching box and its area
+};
+
+DAN_D AnchorBox load_anchor(const EncArgs& A, int a) {
+  AnchorBox ab;
+  ab.y0 = A.ay0[a];
+  ab.x0 = A.ax0[a];
+  ab.y1 = A.ay1[a];
+  ab.x1 = A.ax1[a];
+  if (A.pa_scale > 0.f) {
+    float cy, cx, h, w;
+    point2center(ab.y0, ab.x0, ab.y1, ab.x1, cy, cx, h, w);
+    center2point(cy, cx, fdiv(h, A.pa_scale), fdiv(w, A.pa_scale), ab.my0, ab.mx0, ab.my1, ab.mx1);
+  } else {
+    ab.my0 = ab.y0;
+    ab.mx0 = ab.x0;
+    ab.my1 = ab.y1;
+    ab.mx1 = ab.x1;
+  }
+  ab.marea = box_area(ab.my0, ab.mx0, ab.my1, ab.mx1);
+  return ab;
+}
+
+// Encode anchor `a` of image `b` against GT box g (anchor_manipulator.py:306-326 /
+// :366-387) and write every output row of a POSITIVE anchor.
+DAN_D void write_positive(const EncArgs& A, int64_t row, const AnchorBox& ab, float4 g, float score, int gt_index) {
+  float4 t;
+  if (A.debug) {
+    t = make_float4(ab.y0, ab.x0, ab.y1, ab.x1);
+  } else {
+    float gcy, gcx, gh, gw, acy, acx, ah, aw;
+    point2center(g.x, g.y, g.z, g.w, gcy, gcx, gh, gw);
+    point2center(ab.y0, ab.x0, ab.y1, ab.x1, acy, acx, ah, aw);
+    t.x = fdiv(fdiv(fsub(gcy, acy), ah), A.ps0);
+    t.y = fdiv(fdiv(fsub(gcx, acx), aw), A.ps1);
+    if (A.pa_scale > 0.f) {
+      t.z = fdiv(cephes_logf(fdiv(fmul(gh, A.pa_scale), ah)), A.ps2);
+      t.w = fdiv(cephes_logf(fdiv(fmul(gw, A.pa_scale), aw)), A.ps3);
+    } else {
+      t.z = fdiv(cephes_logf(fdiv(gh, ah)), A.ps2);
+      t.w = fdiv(cephes_logf(fdiv(gw, aw)), A.ps3);
+    }
+  }
+  A.targets[row] = t;
+  A.labels[row] = 1;
+  A.scores[row] = score;
+  if (A.matched != nullptr) A.matched[row] = g;
+  if (A.match32 != nullptr) A.match32[row] = gt_index;
+}
+
+// ---------------------------------------------------------------------------
+// per-warp GT iteration shared by pass 1 and pass 2 of the FUSED path
+// ---------------------------------------------------------------------------
+struct WarpBox {
+  float y0, x0, y1, x1;
+};
+
+DAN_D WarpBox warp_bbox(bool active, const AnchorBox& ab) {
+  const float inf = __int_as_float(0x7f800000);
+  WarpBox wb;
+  wb.y0 = warp_min_f(active ? ab.my0 : inf);
+  wb.x0 = warp_min_f(active ? ab.mx0 : inf);
+  wb.y1 = warp_max_f(active ? ab.my1 : -inf);
+  wb.x1 = warp_max_f(active ? ab.mx1 : -inf);
+  return wb;
+}
+
+// conservative "may intersect some anchor of the warp" test (see file header):
+// a pair intersects only if fl(min(ymax) - max(ymin)) > -1, and the warp box
+// dominates every anchor of the warp, so >= -1 on the warp box never misses.
+DAN_D bool may_hit(const WarpBox& wb, float4 g) {
+  const float dy = fsub(fminf(wb.y1, g.z), fmaxf(wb.y0, g.x));
+  const float dx = fsub(fminf(wb.x1, g.w), fmaxf(wb.x0, g.y));
+  return (dy >= -1.f) && (dx >= -1.f);
+}
+
+// ---------------------------------------------------------------------------
+// pass 1: per-GT column maxima
+// ---------------------------------------------------------------------------
+template <bool DENSE, bool NEED_ROW>
+__global__ void __launch_bounds__(kEncThreads) enc_pass1_kernel(const EncArgs A) {
+  __shared__ float4 s_box[DENSE ? 1 : kGtChunk];
+  __shared__ float s_area[DENSE ? 1 : kGtChunk];
+  __shared__ uint32_t s_cm[DENSE ? 1 : kGtChunk];
+  __shared__ float s_tile[DENSE ? (kEncThreads / 32) * 32 * 33 : 1];
+
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int a = blockIdx.x * kEncThreads + threadIdx.x;
+  const bool valid = a < A.n;
+  const ImageGt ig = image_gt<DENSE>(A, b);
+
+  float best = 0.f;
+  int best_gt = 0;
+
+  if (DENSE) {
+    float* tile = s_tile + warp * 32 * 33;
+    const int row0 = blockIdx.x * kEncThreads + warp * 32;
+    if (row0 >= A.n) return;
+    for (int j0 = 0; j0 < ig.m_eff; j0 += 32) {
+      const int jc = j0 + lane;
+      for (int r = 0; r < 32; ++r) {
+        const int row = row0 + r;
+        tile[r * 33 + lane] = (row < A.n && jc < ig.m_eff) ? A.overlaps[(int64_t)row * ig.m_eff + jc] : 0.f;
+      }
+      __syncwarp();
+      // column maximum of the 32x32 tile: lane == column
+      float cmx = 0.f;
+      for (int r = 0; r < 32; ++r) cmx = fmaxf(cmx, tile[r * 33 + lane]);
+      if (jc < ig.m_eff && cmx > 0.f) atomicMax(A.colmax + ig.slot0 + jc, __float_as_uint(cmx));
+      if (NEED_ROW) {
+        const int lim = min(32, ig.m_eff - j0);
+        for (int jj = 0; jj < lim; ++jj) {
+          const float ov = tile[lane * 33 + jj];
+          if (ov > best) { best = ov; best_gt = j0 + jj; }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    AnchorBox ab = {};
+    bool active = false;
+    if (valid) {
+      ab = load_anchor(A, a);
+      active = (A.mask == nullptr) || (A.mask[a] != 0);
+    }
+    const WarpBox wb = warp_bbox(active, ab);
+    for (int c0 = 0; c0 < ig.m_eff; c0 += kGtChunk) {
+      const int mc = min(kGtChunk, ig.m_eff - c0);
+      __syncthreads();
+      for (int k = threadIdx.x; k < mc; k += kEncThreads) {
+        const float4 g = gt_box(A, ig, c0 + k);
+        s_box[k] = g;
+        s_area[k] = box_area(g.x, g.y, g.z, g.w);
+        s_cm[k] = 0u;
+      }
+      __syncthreads();
+      for (int k0 = 0; k0 < mc; k0 += 32) {
+        const int k = k0 + lane;
+        const bool test = (k < mc) && may_hit(wb, s_box[k]);
+        unsigned hits = __ballot_sync(0xffffffffu, test);
+        while (hits) {
+          const int kk = k0 + __ffs(hits) - 1;
+          hits &= hits - 1;
+          const float4 g = s_box[kk];
+          bool hit = false;
+          float ov = 0.f;
+          if (active) ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, g.x, g.y, g.z, g.w, s_area[kk], hit);
+          const uint32_t key = (ov > 0.f) ? __float_as_uint(ov) : 0u;
+          const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
+          if (lane == 0 && wmax != 0u) atomicMax(&s_cm[kk], wmax);
+          if (NEED_ROW && ov > best) { best = ov; best_gt = c0 + kk; }
+        }
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < mc; k += kEncThreads)
+        if (s_cm[k] != 0u) atomicMax(A.colmax + ig.slot0 + c0 + k, s_cm[k]);
+    }
+  }
+
+  if (NEED_ROW && valid) {
+    // anchor-side positive (match_indices >= 0 in anchor_manipulator.py:67-76)
+    const bool less = best < A.low;
+    const bool between = (best < A.high) && (best >= A.low);
+    if (!less && !between) A.haspos[ig.slot0 + best_gt] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pass 2: per-anchor resolution + outputs
+// ---------------------------------------------------------------------------
+struct RowState {
+  float best;      // row maximum, first strictly-greatest GT wins
+  int best_gt;
+  float ov0;       // overlap with GT 0
+  // dual
+  bool claimed;
+  float cbest;
+  int cbest_gt;
+  // mining
+  int owner;
+  float owner_ov;
+};
+
+template <bool MINING>
+DAN_D void row_update(RowState& s, int j, float ov, float cm, bool claimable) {
+  if (ov > s.best) { s.best = ov; s.best_gt = j; }
+  if (j == 0) s.ov0 = ov;
+  if (MINING) {
+    // stage 2 tie band, small_mining_match.cc:171,179; ascending j => last GT wins
+    if (fabsf(fsub(ov, cm)) < FLT_EPSILON) { s.owner = j; s.owner_ov = ov; }
+  } else {
+    // anchor_manipulator.py:88 exact equality with the column maximum
+    if (claimable && ov == cm) {
+      s.claimed = true;
+      if (ov > s.cbest) { s.cbest = ov; s.cbest_gt = j; }
+    }
+  }
+}
+
+template <bool DENSE, bool MINING>
+__global__ void __launch_bounds__(kEncThreads) enc_pass2_kernel(const EncArgs A) {
+  __shared__ float4 s_box[DENSE ? 1 : kGtChunk];
+  __shared__ float s_area[DENSE ? 1 : kGtChunk];
+  __shared__ float s_cm[DENSE ? 1 : kGtChunk];
+  __shared__ uint8_t s_claimable[DENSE ? 1 : kGtChunk];
+  __shared__ float s_tile[DENSE ? (kEncThreads / 32) * 32 * 33 : 1];
+
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int a = blockIdx.x * kEncThreads + threadIdx.x;
+  const bool valid = a < A.n;
+  const ImageGt ig = image_gt<DENSE>(A, b);
+  const bool need_haspos = !MINING && !A.gt_max_first;
+
+  RowState s;
+  s.best = 0.f; s.best_gt = 0; s.ov0 = 0.f;
+  s.claimed = false; s.cbest = 0.f; s.cbest_gt = 0;
+  s.owner = -1; s.owner_ov = 0.f;
+
+  AnchorBox ab = {};
+  bool active = false;
+  WarpBox wb = {};
+  if (!DENSE) {
+    if (valid) {
+      ab = load_anchor(A, a);
+      active = (A.mask == nullptr) || (A.mask[a] != 0);
+    }
+    wb = warp_bbox(active, ab);
+  }
+
+  // ---- sweep the GTs: two rounds only when compensation candidates must be pushed
+  bool push_round = false;
+  bool warp_push = false;
+  int match = -1;
+  float score = 0.f;
+  for (int round = 0; round < 2; ++round) {
+    if (DENSE) {
+      float* tile = s_tile + warp * 32 * 33;
+      const int row0 = blockIdx.x * kEncThreads + warp * 32;
+      if (row0 < A.n && (round == 0 || warp_push)) {
+        for (int j0 = 0; j0 < ig.m_eff; j0 += 32) {
+          const int jc = j0 + lane;
+          for (int r = 0; r < 32; ++r) {
+            const int row = row0 + r;
+            tile[r * 33 + lane] = (row < A.n && jc < ig.m_eff) ? A.overlaps[(int64_t)row * ig.m_eff + jc] : 0.f;
+          }
+          __syncwarp();
+          const int lim = min(32, ig.m_eff - j0);
+          for (int jj = 0; jj < lim; ++jj) {
+            const int j = j0 + jj;
+            const float ov = tile[lane * 33 + jj];
+            if (round == 0) {
+              const float cm = __uint_as_float(A.colmax[ig.slot0 + j]);
+              const bool claimable = !need_haspos || A.haspos[ig.slot0 + j] == 0;
+              row_update<MINING>(s, j, ov, cm, claimable);
+            } else if (MINING && push_round && ov > A.stop) {
+              const int pos = atomicAdd(A.fill + ig.slot0 + j, 1);
+              if (pos < kBucketCap) A.bucket[(int64_t)(ig.slot0 + j) * kBucketCap + pos] = HeapItem{ov, a};
+            }
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      for (int c0 = 0; c0 < ig.m_eff; c0 += kGtChunk) {
+        const int mc = min(kGtChunk, ig.m_eff - c0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < mc; k += kEncThreads) {
+          const float4 g = gt_box(A, ig, c0 + k);
+          s_box[k] = g;
+          s_area[k] = box_area(g.x, g.y, g.z, g.w);
+          s_cm[k] = __uint_as_float(A.colmax[ig.slot0 + c0 + k]);
+          s_claimable[k] = (!need_haspos || A.haspos[ig.slot0 + c0 + k] == 0) ? 1 : 0;
+        }
+        __syncthreads();
+        if (round == 1 && !warp_push) continue;
+        for (int k0 = 0; k0 < mc; k0 += 32) {
+          const int k = k0 + lane;
+          bool test = false;
+          if (k < mc) {
+            const float cm = s_cm[k];
+            const bool wide = MINING ? (cm < FLT_EPSILON) : (cm == 0.f);
+            test = may_hit(wb, s_box[k]) || (round == 0 && wide);
+          }
+          unsigned hits = __ballot_sync(0xffffffffu, test);
+          while (hits) {
+            const int kk = k0 + __ffs(hits) - 1;
+            hits &= hits - 1;
+            const float4 g = s_box[kk];
+            bool hit = false;
+            float ov = 0.f;
+            if (active) ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, g.x, g.y, g.z, g.w, s_area[kk], hit);
+            if (round == 0) {
+              row_update<MINING>(s, c0 + kk, ov, s_cm[kk], s_claimable[kk] != 0);
+            } else if (MINING && push_round && ov > A.stop) {
+              const int pos = atomicAdd(A.fill + ig.slot0 + c0 + kk, 1);
+              if (pos < kBucketCap) A.bucket[(int64_t)(ig.slot0 + c0 + kk) * kBucketCap + pos] = HeapItem{ov, a};
+            }
+          }
+        }
+      }
+    }
+
+    if (round == 1) break;
+
+    // ---- resolve this anchor (end of round 0)
+    if (MINING) {
+      // stage 1, small_mining_match.cc:85-93
+      if (s.best >= A.neg_low && s.best < A.low) match = -1;
+      else if (s.best >= A.high) match = s.best_gt;
+      else match = -2;
+      score = s.best;
+      // stage 2, :178-186
+      if (s.owner >= 0) { match = s.owner; score = s.owner_ov; }
+      if (valid && match >= 0) atomicAdd(A.cnt + ig.slot0 + match, 1);
+      push_round = valid && match < 0 && s.best > A.stop;
+    } else {
+      // anchor_manipulator.py:67-76
+      const bool less = s.best < A.low;
+      const bool between = (s.best < A.high) && (s.best >= A.low);
+      const bool neg = A.ignore_between ? less : between;
+      const bool ign = A.ignore_between ? between : less;
+      match = s.best_gt;
+      if (neg) match = -1;
+      if (ign) match = -2;
+      score = s.best;
+      // :95-104 GT-side claim has priority; argmax over (overlap * claim mask)
+      if (s.claimed) {
+        if (s.cbest > 0.f) { match = s.cbest_gt; score = s.cbest; }
+        else { match = 0; score = s.ov0; }
+      }
+    }
+    // the push round re-stages GT chunks with __syncthreads, so the decision to run
+    // it must be CTA-uniform; warps without a pushing lane skip the inner loops
+    if (!MINING || !__syncthreads_or(push_round ? 1 : 0)) break;
+    warp_push = __any_sync(0xffffffffu, push_round);
+  }
+
+  if (!valid) return;
+  const int64_t row = (int64_t)b * A.n + a;
+  if (DENSE) {
+    if (A.match32 != nullptr) A.match32[row] = match;
+    if (A.match64 != nullptr) A.match64[row] = match;
+    A.scores[row] = score;
+    return;
+  }
+  if (match >= 0) {
+    write_positive(A, row, ab, gt_box(A, ig, match), score, match);
+  } else {
+    A.targets[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+    A.labels[row] = (match < -1) ? -1 : 0;   // anchor_manipulator.py:300-302
+    A.scores[row] = score;
+    if (A.matched != nullptr) A.matched[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (A.match32 != nullptr) A.match32[row] = match;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pass 3: stage 3 "hard face compensation", small_mining_match.cc:199-222.
+// One warp per image, GTs in ascending order.
+// ---------------------------------------------------------------------------
+template <bool DENSE>
+DAN_D bool still_unmatched(const EncArgs& A, int64_t row) {
+  if (DENSE) return reinterpret_cast<const volatile int32_t*>(A.match32)[row] < 0;
+  return reinterpret_cast<const volatile int64_t*>(A.labels)[row] < 1;
+}
+
+template <bool DENSE>
+DAN_D void apply_compensation(const EncArgs& A, const ImageGt& ig, int b, int a, int j, float ov) {
+  const int64_t row = (int64_t)b * A.n + a;
+  if (DENSE) {
+    A.match32[row] = j;
+    A.scores[row] = ov;
+  } else {
+    write_positive(A, row, load_anchor(A, a), gt_box(A, ig, j), ov, j);
+  }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(32) enc_pass3_kernel(const EncArgs A) {
+  __shared__ HeapItem s_list[kListCap];
+  __shared__ HeapItem s_heap[kListCap];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const ImageGt ig = image_gt<DENSE>(A, b);
+
+  for (int j0 = 0; j0 < ig.m_eff; j0 += 32) {
+    int my_need = 0;
+    if (j0 + lane < ig.m_eff) my_need = A.min_match - A.cnt[ig.slot0 + j0 + lane];
+    unsigned todo = __ballot_sync(0xffffffffu, my_need > 0);
+    while (todo) {
+      const int jj = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int j = j0 + jj;
+      const int need = __shfl_sync(0xffffffffu, my_need, jj);
+      const int filled = A.fill[ig.slot0 + j];
+
+      HeapItem* list = s_list;
+      HeapItem* heap = s_heap;
+      bool ordered = false;
+      int c = 0;
+      if (filled <= kBucketCap) {
+        const HeapItem* bk = A.bucket + (int64_t)(ig.slot0 + j) * kBucketCap;
+        for (int e0 = 0; e0 < filled; e0 += 32) {
+          const int e = e0 + lane;
+          bool ok = false;
+          HeapItem it;
+          if (e < filled) {
+            it = bk[e];
+            ok = still_unmatched<DENSE>(A, (int64_t)b * A.n + it.id);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (ok) s_list[c + __popc(m & lt_mask)] = it;
+          c += __popc(m);
+        }
+      } else {
+        // bucket overflowed: rescan every anchor of the image in index order
+        list = A.spill + (int64_t)b * 2 * A.n;
+        heap = list + A.n;
+        ordered = true;
+        const float4 g = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : gt_box(A, ig, j);
+        const float garea = box_area(g.x, g.y, g.z, g.w);
+        for (int a0 = 0; a0 < A.n; a0 += 32) {
+          const int a = a0 + lane;
+          bool ok = false;
+          float ov = 0.f;
+          if (a < A.n) {
+            if (DENSE) {
+              ov = A.overlaps[(int64_t)a * ig.m_eff + j];
+            } else if (A.mask == nullptr || A.mask[a] != 0) {
+              const AnchorBox ab = load_anchor(A, a);
+              bool hit;
+              ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, g.x, g.y, g.z, g.w, garea, hit);
+            }
+            ok = (ov > A.stop) && still_unmatched<DENSE>(A, (int64_t)b * A.n + a);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (ok) list[c + __popc(m & lt_mask)] = HeapItem{ov, a};
+          c += __popc(m);
+        }
+        __threadfence_block();
+      }
+      __syncwarp();
+
+      if (c <= need) {
+        for (int e = lane; e < c; e += 32) apply_compensation<DENSE>(A, ig, b, list[e].id, j, list[e].key);
+      } else {
+        // pop order of a max-heap == descending key; only a tie that straddles the
+        // cut depends on libstdc++'s heap layout -> exact transcription below.
+        int taken = 0;
+        bool straddle = false;
+        while (taken < need) {
+          float lmax = 0.f;
+          for (int e = lane; e < c; e += 32) lmax = fmaxf(lmax, list[e].key);
+          const uint32_t wbits = __reduce_max_sync(0xffffffffu, __float_as_uint(lmax));
+          if (wbits == 0u) break;
+          const float wmax = __uint_as_float(wbits);
+          int eq = 0;
+          for (int e = lane; e < c; e += 32) eq += (list[e].key == wmax) ? 1 : 0;
+          const int total = __reduce_add_sync(0xffffffffu, eq);
+          if (taken + total > need) { straddle = true; break; }
+          for (int e = lane; e < c; e += 32) {
+            if (list[e].key == wmax) {
+              apply_compensation<DENSE>(A, ig, b, list[e].id, j, wmax);
+              list[e].key = -wmax;   // mark as taken, value kept for the exact path
+            }
+          }
+          taken += total;
+          __syncwarp();
+        }
+        if (straddle) {
+          __syncwarp();
+          if (lane == 0) {
+            for (int e = 0; e < c; ++e) list[e].key = fabsf(list[e].key);
+            if (!ordered) {  // reference pushes candidates in ascending anchor index (:204-209)
+              for (int e = 1; e < c; ++e) {
+                const HeapItem v = list[e];
+                int p = e - 1;
+                while (p >= 0 && list[p].id > v.id) { list[p + 1] = list[p]; --p; }
+                list[p + 1] = v;
+              }
+            }
+            int len = 0;
+            for (int e = 0; e < c; ++e) heap_push(heap, len, list[e]);
+            for (int p = 0; p < need && len > 0; ++p) {
+              const HeapItem it = heap_pop(heap, len);
+              apply_compensation<DENSE>(A, ig, b, it.id, j, it.key);
+            }
+          }
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+    }
+  }
+}
+
+// M == 0 on the dense mining op: stage 1 leaves every anchor at (-2, lowest())
+__global__ void fill_empty_match_kernel(int32_t* match, float* scores, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    match[i] = -2;
+    scores[i] = -FLT_MAX;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct WsLayout {
+  size_t colmax, cnt, haspos, fill, zero_bytes, bucket, spill, total;
+};
+
+static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
+  WsLayout w;
+  size_t off = 0;
+  w.colmax = off; off += align_up(slots * 4, 256);
+  w.cnt = off;    off += align_up(slots * 4, 256);
+  w.haspos = off; off += align_up(slots * 4, 256);
+  w.fill = off;   off += align_up(slots * 4, 256);
+  w.zero_bytes = off;
+  w.bucket = off; off += align_up(slots * kBucketCap * sizeof(HeapItem), 256);
+  w.spill = off;  off += align_up(batch * 2 * n * sizeof(HeapItem), 256);
+  w.total = off;
+  return w;
+}
+
+static int check_mining_attrs(float neg_low, float neg_high, float pos, int min_match, float stop) {
+  // small_mining_match.cc:292-305
+  DAN_REQUIRE(neg_low >= 0.f && neg_low < 1.f, DAN_ERR_INVALID_ARGUMENT, "Need Attr 1 > negative_low_thres >= 0, got %g", neg_low);
+  DAN_REQUIRE(neg_high > neg_low && neg_high < 1.f, DAN_ERR_INVALID_ARGUMENT,
+              "Need Attr 1 > negative_high_thres > negative_low_thres, got %g", neg_high);
+  DAN_REQUIRE(pos >= neg_high && pos < 1.f, DAN_ERR_INVALID_ARGUMENT, "Need Attr 1 > positive_thres >= negative_high_thres, got %g", pos);
+  DAN_REQUIRE(stop >= 0.f && stop < 1.f, DAN_ERR_INVALID_ARGUMENT, "Need Attr 1 > stop_positive_thres >= 0., got %g", stop);
+  DAN_REQUIRE(min_match >= 1, DAN_ERR_INVALID_ARGUMENT, "Need Attr min_match >= 1, got %d", min_match);
+  return DAN_OK;
+}
+
+static void bind_workspace(EncArgs& A, void* workspace, const WsLayout& w) {
+  char* base = static_cast<char*>(workspace);
+  A.colmax = reinterpret_cast<uint32_t*>(base + w.colmax);
+  A.cnt = reinterpret_cast<int32_t*>(base + w.cnt);
+  A.haspos = reinterpret_cast<int32_t*>(base + w.haspos);
+  A.fill = reinterpret_cast<int32_t*>(base + w.fill);
+  A.bucket = reinterpret_cast<HeapItem*>(base + w.bucket);
+  A.spill = reinterpret_cast<HeapItem*>(base + w.spill);
+}
+
+template <bool DENSE>
+static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, cudaStream_t st) {
+  const dim3 grid((A.n + kEncThreads - 1) / kEncThreads, batch);
+  if (need_row) enc_pass1_kernel<DENSE, true><<<grid, kEncThreads, 0, st>>>(A);
+  else enc_pass1_kernel<DENSE, false><<<grid, kEncThreads, 0, st>>>(A);
+  DAN_LAUNCH_CHECK("enc_pass1_kernel");
+  if (mining) enc_pass2_kernel<DENSE, true><<<grid, kEncThreads, 0, st>>>(A);
+  else enc_pass2_kernel<DENSE, false><<<grid, kEncThreads, 0, st>>>(A);
+  DAN_LAUNCH_CHECK("enc_pass2_kernel");
+  if (mining) {
+    enc_pass3_kernel<DENSE><<<batch, 32, 0, st>>>(A);
+    DAN_LAUNCH_CHECK("enc_pass3_kernel");
+  }
+  return DAN_OK;
+}
+
+}  // namespace dan
+
+using namespace dan;
+
+extern "C" {
+
+size_t dan_match_workspace_bytes(int32_t num_anchors, int32_t num_gt) {
+  if (num_anchors < 0 || num_gt < 0) return 0;
+  return ws_layout(num_anchors, 1, (int64_t)num_gt + 1).total;
+}
+
+size_t dan_encode_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t total_gt) {
+  if (num_anchors < 0 || batch < 0 || total_gt < 0) return 0;
+  return ws_layout(num_anchors, batch, (int64_t)total_gt + batch).total;
+}
+
+int dan_small_mining_match(const float* overlaps, int32_t num_anchors, int32_t num_gt, float negative_low_thres,
+                           float negative_high_thres, float positive_thres, int32_t min_match, float stop_positive_thres,
+                           int32_t* out_match_indices, float* out_match_scores, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  int rc = check_mining_attrs(negative_low_thres, negative_high_thres, positive_thres, min_match, stop_positive_thres);
+  if (rc != DAN_OK) return rc;
+  DAN_REQUIRE(num_anchors >= 0 && num_gt >= 0, DAN_ERR_INVALID_ARGUMENT, "inputs must be in 'num_anchors x num_ground_truth' format.");
+  if (num_anchors == 0) return DAN_OK;
+  DAN_REQUIRE(out_match_indices && out_match_scores, DAN_ERR_INVALID_ARGUMENT, "NULL output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (num_gt == 0) {
+    fill_empty_match_kernel<<<(num_anchors + 255) / 256, 256, 0, st>>>(out_match_indices, out_match_scores, num_anchors);
+    DAN_LAUNCH_CHECK("fill_empty_match_kernel");
+    return DAN_OK;
+  }
+  DAN_REQUIRE(overlaps != nullptr, DAN_ERR_INVALID_ARGUMENT, "NULL overlaps");
+  const WsLayout w = ws_layout(num_anchors, 1, (int64_t)num_gt + 1);
+  DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
+              w.total, workspace_bytes);
+  EncArgs A = {};
+  A.n = num_anchors;
+  A.overlaps = overlaps;
+  A.m_dense = num_gt;
+  A.low = negative_high_thres;
+  A.high = positive_thres;
+  A.neg_low = negative_low_thres;
+  A.stop = stop_positive_thres;
+  A.min_match = min_match;
+  A.gt_max_first = 1;
+  A.ignore_between = 1;
+  A.match32 = out_match_indices;
+  A.scores = out_match_scores;
+  bind_workspace(A, workspace, w);
+  DAN_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));
+  return run_passes<true>(A, true, false, 1, st);
+}
+
+int dan_dual_max_match(const float* overlaps, int32_t num_anchors, int32_t num_gt, float low_thres, float high_thres,
+                       int32_t ignore_between, int32_t gt_max_first, int64_t* out_match_indices, float* out_match_scores,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  DAN_REQUIRE(num_anchors >= 0 && num_gt >= 1, DAN_ERR_INVALID_ARGUMENT,
+              "do_dual_max_match needs overlap_matrix [num_anchors, num_gt>=1] (tf.argmax over an empty axis is an error)");
+  if (num_anchors == 0) return DAN_OK;
+  DAN_REQUIRE(overlaps && out_match_indices && out_match_scores, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
+  const WsLayout w = ws_layout(num_anchors, 1, (int64_t)num_gt + 1);
+  DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
+              w.total, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  EncArgs A = {};
+  A.n = num_anchors;
+  A.overlaps = overlaps;
+  A.m_dense = num_gt;
+  A.low = low_thres;
+  A.high = high_thres;
+  A.ignore_between = ignore_between ? 1 : 0;
+  A.gt_max_first = gt_max_first ? 1 : 0;
+  A.match64 = out_match_indices;
+  A.scores = out_match_scores;
+  bind_workspace(A, workspace, w);
+  DAN_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));
+  return run_passes<true>(A, false, !gt_max_first, 1, st);
+}
+
+int dan_encode_batch(const dan_encode_params* p, const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                     const float* a_xmax, const uint8_t* inside_mask, int32_t num_anchors, const float* gt_boxes,
+                     const int32_t* gt_offsets, int32_t batch, int32_t total_gt, float* out_targets, int64_t* out_labels,
+                     float* out_scores, float* out_matched_gt, int32_t* out_match, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  DAN_REQUIRE(p != nullptr, DAN_ERR_INVALID_ARGUMENT, "params is NULL");
+  DAN_REQUIRE(p->matcher == DAN_MATCH_DUAL || p->matcher == DAN_MATCH_MINING, DAN_ERR_INVALID_ARGUMENT, "unknown matcher %d", p->matcher);
+  DAN_REQUIRE(num_anchors >= 0 && batch >= 0 && total_gt >= 0, DAN_ERR_INVALID_ARGUMENT, "negative size");
+  DAN_REQUIRE(batch <= 65535, DAN_ERR_UNSUPPORTED, "batch > 65535");
+  const bool mining = p->matcher == DAN_MATCH_MINING;
+  if (mining) {
+    int rc = check_mining_attrs(p->negative_low_thres, p->ignore_threshold, p->positive_threshold, p->min_match, p->stop_positive_thres);
+    if (rc != DAN_OK) return rc;
+  }
+  DAN_REQUIRE(p->pa_scale >= 0.f, DAN_ERR_INVALID_ARGUMENT, "pa_scale must be >= 0");
+  if (num_anchors == 0 || batch == 0) return DAN_OK;
+  DAN_REQUIRE(a_ymin && a_xmin && a_ymax && a_xmax && gt_offsets && out_targets && out_labels && out_scores, DAN_ERR_INVALID_ARGUMENT,
+              "NULL pointer");
+  DAN_REQUIRE(total_gt == 0 || gt_boxes != nullptr, DAN_ERR_INVALID_ARGUMENT, "gt_boxes is NULL");
+  DAN_REQUIRE(aligned16(gt_boxes) && aligned16(out_targets) && aligned16(out_matched_gt), DAN_ERR_INVALID_ARGUMENT,
+              "gt_boxes / out_targets / out_matched_gt must be 16-byte aligned");
+  const WsLayout w = ws_layout(num_anchors, batch, (int64_t)total_gt + batch);
+  DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu",
+              w.total, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  EncArgs A = {};
+  A.ay0 = a_ymin; A.ax0 = a_xmin; A.ay1 = a_ymax; A.ax1 = a_xmax;
+  A.mask = inside_mask;
+  A.n = num_anchors;
+  A.gt = reinterpret_cast<const float4*>(gt_boxes);
+  A.gt_off = gt_offsets;
+  A.low = p->ignore_threshold;
+  A.high = p->positive_threshold;
+  A.neg_low = p->negative_low_thres;
+  A.stop = p->stop_positive_thres;
+  A.min_match = p->min_match;
+  A.ignore_between = mining ? 1 : (p->ignore_between ? 1 : 0);
+  A.gt_max_first = mining ? 1 : (p->gt_max_first ? 1 : 0);
+  A.ps0 = p->prior_scaling[0]; A.ps1 = p->prior_scaling[1]; A.ps2 = p->prior_scaling[2]; A.ps3 = p->prior_scaling[3];
+  A.pa_scale = p->pa_scale;
+  A.debug = p->debug;
+  A.targets = reinterpret_cast<float4*>(out_targets);
+  A.labels = out_labels;
+  A.scores = out_scores;
+  A.matched = reinterpret_cast<float4*>(out_matched_gt);
+  A.match32 = out_match;
+  bind_workspace(A, workspace, w);
+  DAN_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));
+  return run_passes<false>(A, mining, !mining && !A.gt_max_first, batch, st);
+}
+
+}  // extern "C"

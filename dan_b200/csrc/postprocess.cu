@@ -1,0 +1,588 @@
+// K3-K5: the evaluation half of the path -- utility/bbox_util.py:103-119
+// parse_by_class and its pieces, batched over images and classes.
+//
+//   pp_filter_kernel   softmax -> select(threshold) -> decode -> clip -> min-size;
+//                      survivors are COMPACTED as 64-bit keys
+//                      (ordered score bits << 32 | ~anchor index).  The reference
+//                      instead multiplies by 0/1 masks and keeps all N rows
+//                      (bbox_util.py:24-59); rows it zeroes can never precede a
+//                      positive score in tf.nn.top_k, so dropping them is exact.
+//   topk_sort_kernel   per (image, class): block radix select of the keep_topk
+//                      largest keys when more survive, then an in-shared-memory
+//                      bitonic sort.  Keys are unique, descending key order ==
+//                      descending score with ties broken by LOWER index, which is
+//                      tf.nn.top_k's documented order (bbox_util.py:64).
+//   nms_mask_kernel    64x64 tiles of the upper-triangular suppression bit matrix
+//                      with tf.image.non_max_suppression's IoU (no +1, strict >,
+//                      area<=0 never suppresses).
+//   nms_sweep_kernel   one warp per (image, class): 64-wide chunks; the serial
+//                      part is a register-resident shuffle sweep over the diagonal
+//                      word, the kept rows are OR-ed into the removed set by all
+//                      lanes; writes the zero padded outputs (bbox_util.py:80-90).
+#include "common.cuh"
+
+namespace dan {
+
+constexpr int kSortCap = 8192;      // keys sorted in shared memory (64 KB)
+constexpr int kSortThreads = 1024;
+constexpr int kMaskTilesPerList = 64;
+
+DAN_D uint32_t score_to_key(float s) { return (uint32_t)float_to_ordered(s) ^ 0x80000000u; }
+DAN_D float key_to_score(uint32_t k) { return ordered_to_float((int)(k ^ 0x80000000u)); }
+
+struct PpArgs {
+  // inputs
+  const float* cls;       // [B, N, C] logits
+  const float4* loc;      // [B, N, 4] offsets (or NULL)
+  const float4* boxes;    // [B, N, 4] decoded boxes (or NULL)
+  const float* ay0;
+  const float* ax0;
+  const float* ay1;
+  const float* ax1;
+  int n, batch, num_classes;
+  float img_h, img_w;
+  float select_thr, min_size_p1;
+  float ps0, ps1, ps2, ps3;
+  int keep_topk, nms_topk;
+  float nms_thr;
+  // workspace
+  unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
+  int32_t* key_count;         // [L]
+  float* s_scores;            // [L, keep_topk] sorted
+  float4* s_boxes;            // [L, keep_topk]
+  int32_t* s_index;           // [L, keep_topk]
+  int32_t* s_len;             // [L] number of sorted (real) rows
+  unsigned long long* mask;   // [L, keep_topk, words]
+  int words;
+  // outputs
+  float4* out_boxes;
+  float* out_scores;
+  int32_t* out_counts;
+  int32_t* out_index;
+  int32_t* out_keep;
+  int filler;                 // fused parse_by_class: zero-score rows fill up the NMS selection
+};
+
+// clip_bboxes, bbox_util.py:38-48
+DAN_D float4 pp_clip(float4 b, float height, float width) {
+  float ymin = fmaxf(b.x, 0.f);
+  float xmin = fmaxf(b.y, 0.f);
+  const float ymax = fminf(b.z, fsub(height, 1.f));
+  const float xmax = fminf(b.w, fsub(width, 1.f));
+  ymin = fminf(ymin, ymax);
+  xmin = fminf(xmin, xmax);
+  return make_float4(ymin, xmin, ymax, xmax);
+}
+
+// decode (when offsets are given) + clip for anchor `a` of image `b`
+DAN_D float4 pp_box(const PpArgs& A, int b, int a) {
+  const int64_t row = (int64_t)b * A.n + a;
+  float4 bx;
+  if (A.loc != nullptr) bx = decode_box(A.loc[row], A.ay0[a], A.ax0[a], A.ay1[a], A.ax1[a], A.ps0, A.ps1, A.ps2, A.ps3);
+  else bx = A.boxes[row];
+  return pp_clip(bx, A.img_h, A.img_w);
+}
+
+// ---------------------------------------------------------------------------
+// K3: filter + compaction.  grid (ceil(N/256), B)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
+  const int b = blockIdx.y;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = a < A.n;
+  const int C = A.num_classes;
+  const float* x = A.cls + ((int64_t)b * A.n + (valid ? a : 0)) * C;
+
+  // tf.nn.softmax: exp(x - max) * (1 / sum(exp(x - max))), sum in class order
+  float mx = 0.f, inv = 0.f;
+  if (valid) {
+    mx = x[0];
+    for (int k = 1; k < C; ++k) mx = fmaxf(mx, x[k]);
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) {
+      const float e = cephes_expf(fsub(x[k], mx));
+      s = (k == 0) ? e : fadd(s, e);
+    }
+    inv = fdiv(1.f, s);
+  }
+  float4 box;
+  bool have_box = false;
+  for (int c = 1; c < C; ++c) {
+    bool pass = false;
+    float p = 0.f;
+    if (valid) {
+      p = fmul(cephes_expf(fsub(x[c], mx)), inv);
+      if (p > A.select_thr) {                       // select_bboxes :24-36
+        if (!have_box) { box = pp_box(A, b, a); have_box = true; }
+        const float w = fadd(fsub(box.w, box.y), 1.f);   // filter_bboxes :50-59
+        const float h = fadd(fsub(box.z, box.x), 1.f);
+        pass = (w > A.min_size_p1) && (h > A.min_size_p1);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m != 0u) {
+      const int list = b * (C - 1) + (c - 1);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(A.key_count + list, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pass) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        A.keys[(int64_t)list * A.n + pos] = ((unsigned long long)score_to_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+      }
+    }
+  }
+}
+
+// standalone sort_bboxes / nms_bboxes: one key per input row, nothing filtered
+__global__ void __launch_bounds__(256) key_build_kernel(const float* __restrict__ scores, int64_t n, unsigned long long* __restrict__ keys,
+                                                        int32_t* __restrict__ key_count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    keys[i] = ((unsigned long long)score_to_key(scores[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+  if (blockIdx.x == 0 && threadIdx.x == 0) key_count[0] = (int32_t)n;
+}
+
+// ---------------------------------------------------------------------------
+// K4: per-list top-k (radix select when needed) + bitonic sort + gather
+// ---------------------------------------------------------------------------
+template <bool DECODE>
+__global__ void __launch_bounds__(kSortThreads) topk_sort_kernel(const PpArgs A, const float* __restrict__ src_scores,
+                                                                 const float4* __restrict__ src_boxes, int pad_outputs) {
+  extern __shared__ unsigned long long s_keys[];
+  __shared__ int s_hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining;
+  __shared__ int s_fill;
+
+  const int list = blockIdx.x;
+  const int tid = threadIdx.x;
+  const unsigned long long* keys = A.keys + (int64_t)list * A.n;
+  const int cnt = min(A.key_count[list], A.n);
+  const int k = min(A.keep_topk, cnt);
+
+  int m = cnt;   // keys to sort
+  if (cnt <= kSortCap) {
+    for (int i = tid; i < cnt; i += kSortThreads) s_keys[i] = keys[i];
+  } else {
+    // block radix select, MSB first, 8 bits per pass: find the k-th largest key
+    if (tid == 0) { s_prefix = 0ull; s_remaining = k; }
+    unsigned long long prefix_mask = 0ull;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += kSortThreads) s_hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < cnt; i += kSortThreads) {
+        const unsigned long long key = keys[i];
+        if ((key & prefix_mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 255ull)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, bin = 255;
+        for (; bin > 0; --bin) {
+          if (cum + s_hist[bin] >= s_remaining) break;
+          cum += s_hist[bin];
+        }
+        s_remaining -= cum;
+        s_prefix = prefix | ((unsigned long long)bin << shift);
+      }
+      prefix_mask |= 255ull << shift;
+      __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;
+    if (tid == 0) s_fill = 0;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += kSortThreads) {
+      const unsigned long long key = keys[i];
+      if (key >= kth) s_keys[atomicAdd(&s_fill, 1)] = key;   // exactly k keys (keys are unique)
+    }
+    m = k;
+  }
+  // pad to a power of two with 0 (smaller than any real key: the low word of a
+  // real key is ~index != 0 for index < 2^32-1) and sort descending
+  int p2 = 1;
+  while (p2 < m) p2 <<= 1;
+  for (int i = m + tid; i < p2; i += kSortThreads) s_keys[i] = 0ull;
+  __syncthreads();
+  for (int size = 2; size <= p2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (p2 >> 1); t += kSortThreads) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long x = s_keys[lo], y = s_keys[hi];
+        if ((x < y) == desc) { s_keys[lo] = y; s_keys[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  // gather the k best rows (recompute the box from the anchor index: same bits)
+  const int b = list / max(A.num_classes - 1, 1);
+  const int rows = pad_outputs ? A.keep_topk : k;
+  for (int r = tid; r < rows; r += kSortThreads) {
+    const int64_t o = (int64_t)list * A.keep_topk + r;
+    if (r < k) {
+      const unsigned long long key = s_keys[r];
+      const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+      A.s_scores[o] = DECODE ? key_to_score((uint32_t)(key >> 32)) : src_scores[idx];
+      A.s_boxes[o] = DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx];
+      if (A.s_index != nullptr) A.s_index[o] = (int32_t)idx;
+    } else {
+      A.s_scores[o] = 0.f;
+      A.s_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A.s_index != nullptr) A.s_index[o] = -1;
+    }
+  }
+  if (tid == 0 && A.s_len != nullptr) A.s_len[list] = k;
+}
+
+// ---------------------------------------------------------------------------
+// K5a: suppression bit matrix.  grid (kMaskTilesPerList, L), 64 threads.
+// bit c of mask[list][row][w] is set iff col = 64*w + c > row and
+// IOUGreaterThanThreshold(row, col) of TF's non_max_suppression_op.cc.
+// ---------------------------------------------------------------------------
+struct NmsBox {
+  float y0, x0, y1, x1, area;
+};
+
+DAN_D NmsBox nms_norm(float4 b) {
+  NmsBox r;
+  r.y0 = fminf(b.x, b.z);
+  r.x0 = fminf(b.y, b.w);
+  r.y1 = fmaxf(b.x, b.z);
+  r.x1 = fmaxf(b.y, b.w);
+  r.area = fmul(fsub(r.y1, r.y0), fsub(r.x1, r.x0));
+  return r;
+}
+
+DAN_D bool nms_suppresses(const NmsBox& i, const NmsBox& j, float thr) {
+  if (i.area <= 0.f || j.area <= 0.f) return false;
+  const float iy0 = fmaxf(i.y0, j.y0);
+  const float ix0 = fmaxf(i.x0, j.x0);
+  const float iy1 = fminf(i.y1, j.y1);
+  const float ix1 = fminf(i.x1, j.x1);
+  const float h = fmaxf(fsub(iy1, iy0), 0.f);
+  const float w = fmaxf(fsub(ix1, ix0), 0.f);
+  const float inter = fmul(h, w);
+  if (inter == 0.f) return 0.f > thr;     // 0 / (area_i + area_j) == 0 exactly
+  return fdiv(inter, fsub(fadd(i.area, j.area), inter)) > thr;
+}
+
+__global__ void __launch_bounds__(64) nms_mask_kernel(const PpArgs A) {
+  __shared__ NmsBox s_col[64];
+  const int list = blockIdx.y;
+  const int K = A.s_len[list];
+  const int nb = (K + 63) >> 6;
+  const int tiles = nb * (nb + 1) / 2;
+  const float4* boxes = A.s_boxes + (int64_t)list * A.keep_topk;
+  unsigned long long* mask = A.mask + (int64_t)list * A.keep_topk * A.words;
+  const int t = threadIdx.x;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // upper triangle, row-block major: row block rb owns nb - rb tiles
+    int rb = 0, rem = tile;
+    while (rem >= nb - rb) { rem -= nb - rb; ++rb; }
+    const int cb = rb + rem;
+    __syncthreads();
+    const int col = cb * 64 + t;
+    if (col < K) s_col[t] = nms_norm(boxes[col]);
+    __syncthreads();
+    const int row = rb * 64 + t;
+    if (row < K) {
+      const NmsBox me = nms_norm(boxes[row]);
+      const int lim = min(64, K - cb * 64);
+      unsigned long long bits = 0ull;
+      for (int c = 0; c < lim; ++c) {
+        if (cb * 64 + c > row && nms_suppresses(me, s_col[c], A.nms_thr)) bits |= 1ull << c;
+      }
+      mask[(int64_t)row * A.words + cb] = bits;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5b: greedy sweep + outputs.  grid L, one warp per list.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) nms_sweep_kernel(const PpArgs A) {
+  extern __shared__ int32_t s_keep[];            // [nms_topk]
+  __shared__ unsigned long long s_removed[kSortCap / 64];
+  const int list = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int K = A.s_len[list];
+  const int nb = (K + 63) >> 6;
+  const unsigned long long* mask = A.mask + (int64_t)list * A.keep_topk * A.words;
+
+  for (int w = lane; w < nb; w += 32) s_removed[w] = 0ull;
+  __syncwarp();
+
+  int kept_total = 0;
+  for (int c = 0; c < nb && kept_total < A.nms_topk; ++c) {
+    const int base = c << 6;
+    const int r0 = base + lane, r1 = base + 32 + lane;
+    const unsigned long long d0 = (r0 < K) ? mask[(int64_t)r0 * A.words + c] : 0ull;
+    const unsigned long long d1 = (r1 < K) ? mask[(int64_t)r1 * A.words + c] : 0ull;
+    const int nvalid = min(64, K - base);
+    const unsigned long long valid_bits = (nvalid >= 64) ? ~0ull : ((1ull << nvalid) - 1ull);
+    unsigned long long cur = s_removed[c] | ~valid_bits;
+    // serial greedy resolve inside the chunk; the shuffles do not depend on `cur`
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const unsigned long long row = __shfl_sync(0xffffffffu, d0, i);
+      if (!((cur >> i) & 1ull)) cur |= row;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const unsigned long long row = __shfl_sync(0xffffffffu, d1, i);
+      if (!((cur >> (32 + i)) & 1ull)) cur |= row;
+    }
+    unsigned long long kept = ~cur & valid_bits;
+    int nk = __popcll(kept);
+    if (kept_total + nk > A.nms_topk) {          // max_output_size reached inside the chunk
+      int drop = kept_total + nk - A.nms_topk;
+      while (drop-- > 0) kept &= ~(1ull << (63 - __clzll(kept)));
+      nk = A.nms_topk - kept_total;
+    }
+    // record kept positions (ascending) -- lane i handles bits i and i+32
+    {
+      const unsigned long long below0 = kept & ((1ull << lane) - 1ull);
+      if ((kept >> lane) & 1ull) s_keep[kept_total + __popcll(below0)] = base + lane;
+      const unsigned long long below1 = kept & ((1ull << (lane + 32)) - 1ull);
+      if ((kept >> (lane + 32)) & 1ull) s_keep[kept_total + __popcll(below1)] = base + 32 + lane;
+    }
+    kept_total += nk;
+    // OR the kept rows into the removed set of the later chunks
+    for (int w = c + 1 + lane; w < nb; w += 32) {
+      unsigned long long acc = s_removed[w];
+      unsigned long long kk = kept;
+      while (kk) {
+        const int i = __ffsll((long long)kk) - 1;
+        kk &= kk - 1ull;
+        acc |= mask[(int64_t)(base + i) * A.words + w];
+      }
+      s_removed[w] = acc;
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+
+  // outputs, zero padded to nms_topk (bbox_util.py:80-90)
+  const float* sc = A.s_scores + (int64_t)list * A.keep_topk;
+  const float4* bx = A.s_boxes + (int64_t)list * A.keep_topk;
+  const int32_t* ix = A.s_index + (int64_t)list * A.keep_topk;
+  for (int t = lane; t < A.nms_topk; t += 32) {
+    const int64_t o = (int64_t)list * A.nms_topk + t;
+    if (t < kept_total) {
+      const int pos = s_keep[t];
+      A.out_scores[o] = sc[pos];
+      A.out_boxes[o] = bx[pos];
+      if (A.out_index != nullptr) A.out_index[o] = ix[pos];
+      if (A.out_keep != nullptr) A.out_keep[o] = A.filler ? pos : ix[pos];
+    } else {
+      A.out_scores[o] = 0.f;
+      A.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A.out_index != nullptr) A.out_index[o] = -1;
+      if (A.out_keep != nullptr) {
+        // parse_by_class runs NMS on the zero padded top-k list: zero-area filler
+        // rows are never suppressed and get selected until nms_topk is reached
+        const int fpos = K + (t - kept_total);
+        A.out_keep[o] = (A.filler && fpos < A.keep_topk) ? fpos : -1;
+      }
+    }
+  }
+  if (lane == 0 && A.out_counts != nullptr) A.out_counts[list] = kept_total;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct PpLayout {
+  size_t key_count, s_len, keys, s_scores, s_boxes, s_index, mask, total;
+  int words;
+};
+
+static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk) {
+  PpLayout w;
+  size_t off = 0;
+  w.words = (int)((keep_topk + 63) / 64);
+  w.key_count = off; off += align_up(lists * 4, 256);
+  w.s_len = off;     off += align_up(lists * 4, 256);
+  w.keys = off;      off += align_up(lists * n * 8, 256);
+  w.s_scores = off;  off += align_up(lists * keep_topk * 4, 256);
+  w.s_boxes = off;   off += align_up(lists * keep_topk * 16, 256);
+  w.s_index = off;   off += align_up(lists * keep_topk * 4, 256);
+  w.mask = off;      off += align_up(lists * keep_topk * (size_t)w.words * 8, 256);
+  w.total = off;
+  return w;
+}
+
+static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
+  char* base = static_cast<char*>(ws);
+  A.key_count = reinterpret_cast<int32_t*>(base + w.key_count);
+  A.s_len = reinterpret_cast<int32_t*>(base + w.s_len);
+  A.keys = reinterpret_cast<unsigned long long*>(base + w.keys);
+  A.s_scores = reinterpret_cast<float*>(base + w.s_scores);
+  A.s_boxes = reinterpret_cast<float4*>(base + w.s_boxes);
+  A.s_index = reinterpret_cast<int32_t*>(base + w.s_index);
+  A.mask = reinterpret_cast<unsigned long long*>(base + w.mask);
+  A.words = w.words;
+}
+
+static int enable_big_smem() {
+  static bool done = false;
+  if (!done) {
+    DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
+    DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
+    DAN_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 4));
+    done = true;
+  }
+  return DAN_OK;
+}
+
+static int run_nms(const PpArgs& A, int lists, cudaStream_t st) {
+  nms_mask_kernel<<<dim3(kMaskTilesPerList, lists), 64, 0, st>>>(A);
+  DAN_LAUNCH_CHECK("nms_mask_kernel");
+  nms_sweep_kernel<<<lists, 32, (size_t)A.nms_topk * 4, st>>>(A);
+  DAN_LAUNCH_CHECK("nms_sweep_kernel");
+  return DAN_OK;
+}
+
+}  // namespace dan
+
+using namespace dan;
+
+extern "C" {
+
+size_t dan_postprocess_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t num_classes, int32_t keep_topk) {
+  if (num_anchors < 0 || batch < 0 || num_classes < 2 || keep_topk < 1) return 0;
+  return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1), keep_topk).total;
+}
+
+size_t dan_sort_workspace_bytes(int64_t n, int32_t keep_topk) {
+  if (n < 0 || keep_topk < 1) return 0;
+  return pp_layout(n, 1, keep_topk).total;
+}
+
+size_t dan_nms_workspace_bytes(int64_t n, int32_t nms_topk) {
+  if (n < 0 || nms_topk < 0) return 0;
+  return pp_layout(n, 1, n > 0 ? n : 1).total;
+}
+
+int dan_postprocess_batch(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
+                          const float* a_ymin, const float* a_xmin, const float* a_ymax, const float* a_xmax, int32_t num_anchors,
+                          int32_t batch, float* out_boxes, float* out_scores, int32_t* out_counts, int32_t* out_anchor_index,
+                          int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, void* stream) {
+  DAN_REQUIRE(p != nullptr, DAN_ERR_INVALID_ARGUMENT, "params is NULL");
+  DAN_REQUIRE(p->num_classes >= 2, DAN_ERR_INVALID_ARGUMENT, "num_classes must be >= 2 (class 0 is background), got %d", p->num_classes);
+  DAN_REQUIRE(num_anchors >= 0 && batch >= 0, DAN_ERR_INVALID_ARGUMENT, "negative size");
+  DAN_REQUIRE(batch <= 65535, DAN_ERR_UNSUPPORTED, "batch > 65535");
+  DAN_REQUIRE(p->select_threshold >= 0.f, DAN_ERR_INVALID_ARGUMENT,
+              "select_threshold must be >= 0 (a negative threshold would let zero-score rows carry boxes), got %g", p->select_threshold);
+  DAN_REQUIRE(p->keep_topk >= 1 && p->nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "keep_topk and nms_topk must be >= 1");
+  DAN_REQUIRE(p->keep_topk <= kSortCap, DAN_ERR_UNSUPPORTED, "keep_topk %d exceeds the in-shared-memory sort capacity %d", p->keep_topk, kSortCap);
+  DAN_REQUIRE(p->nms_topk <= kSortCap, DAN_ERR_UNSUPPORTED, "nms_topk %d exceeds %d", p->nms_topk, kSortCap);
+  DAN_REQUIRE((loc_pred != nullptr) != (boxes_pred != nullptr), DAN_ERR_INVALID_ARGUMENT, "exactly one of loc_pred / boxes_pred must be given");
+  if (batch == 0) return DAN_OK;
+  DAN_REQUIRE(cls_pred && out_boxes && out_scores, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
+  DAN_REQUIRE(loc_pred == nullptr || (a_ymin && a_xmin && a_ymax && a_xmax), DAN_ERR_INVALID_ARGUMENT, "anchors needed to decode loc_pred");
+  DAN_REQUIRE(aligned16(loc_pred) && aligned16(boxes_pred) && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "box tensors must be 16-byte aligned");
+  const int lists = batch * (p->num_classes - 1);
+  const PpLayout w = pp_layout(num_anchors, lists, p->keep_topk);
+  DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
+              workspace_bytes);
+  int rc = enable_big_smem();
+  if (rc != DAN_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PpArgs A = {};
+  A.cls = cls_pred;
+  A.loc = reinterpret_cast<const float4*>(loc_pred);
+  A.boxes = reinterpret_cast<const float4*>(boxes_pred);
+  A.ay0 = a_ymin; A.ax0 = a_xmin; A.ay1 = a_ymax; A.ax1 = a_xmax;
+  A.n = num_anchors;
+  A.batch = batch;
+  A.num_classes = p->num_classes;
+  A.img_h = (float)p->image_h;
+  A.img_w = (float)p->image_w;
+  A.select_thr = p->select_threshold;
+  A.min_size_p1 = (float)((double)p->min_size + 1.0);   // python: min_size + 1. then fp32
+  A.ps0 = p->prior_scaling[0]; A.ps1 = p->prior_scaling[1]; A.ps2 = p->prior_scaling[2]; A.ps3 = p->prior_scaling[3];
+  A.keep_topk = p->keep_topk;
+  A.nms_topk = p->nms_topk;
+  A.nms_thr = p->nms_threshold;
+  A.out_boxes = reinterpret_cast<float4*>(out_boxes);
+  A.out_scores = out_scores;
+  A.out_counts = out_counts;
+  A.out_index = out_anchor_index;
+  A.out_keep = out_keep_pos;
+  A.filler = 1;
+  pp_bind(A, workspace, w);
+  DAN_CUDA(cudaMemsetAsync(A.key_count, 0, (size_t)lists * 4, st));
+  if (num_anchors > 0) {
+    pp_filter_kernel<<<dim3((num_anchors + 255) / 256, batch), 256, 0, st>>>(A);
+    DAN_LAUNCH_CHECK("pp_filter_kernel");
+  }
+  topk_sort_kernel<true><<<lists, kSortThreads, kSortCap * 8, st>>>(A, nullptr, nullptr, 0);
+  DAN_LAUNCH_CHECK("topk_sort_kernel");
+  return run_nms(A, lists, st);
+}
+
+int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t keep_topk, float* out_scores, float* out_boxes,
+                    int32_t* out_index, void* workspace, size_t workspace_bytes, void* stream) {
+  DAN_REQUIRE(n >= 0 && n < 0x7fffffff && keep_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "bad size");
+  DAN_REQUIRE(keep_topk <= kSortCap || n <= kSortCap, DAN_ERR_UNSUPPORTED, "min(keep_topk, n) exceeds the sort capacity %d", kSortCap);
+  DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
+  DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
+  const PpLayout w = pp_layout(n, 1, keep_topk);
+  DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
+              workspace_bytes);
+  int rc = enable_big_smem();
+  if (rc != DAN_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PpArgs A = {};
+  A.n = (int)n;
+  A.num_classes = 2;
+  A.keep_topk = keep_topk;
+  pp_bind(A, workspace, w);
+  // outputs ARE the sorted arrays
+  A.s_scores = out_scores;
+  A.s_boxes = reinterpret_cast<float4*>(out_boxes);
+  A.s_index = out_index;
+  A.s_len = nullptr;
+  key_build_kernel<<<grid_for(n), 256, 0, st>>>(scores, n, A.keys, A.key_count);
+  DAN_LAUNCH_CHECK("key_build_kernel");
+  topk_sort_kernel<false><<<1, kSortThreads, kSortCap * 8, st>>>(A, scores, reinterpret_cast<const float4*>(boxes), 1);
+  DAN_LAUNCH_CHECK("topk_sort_kernel");
+  return DAN_OK;
+}
+
+int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t nms_topk, float nms_threshold, float* out_scores,
+                   float* out_boxes, int32_t* out_keep, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  DAN_REQUIRE(n >= 0 && nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "bad size");
+  DAN_REQUIRE(n <= kSortCap && nms_topk <= kSortCap, DAN_ERR_UNSUPPORTED, "n / nms_topk exceed the NMS capacity %d", kSortCap);
+  DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
+  DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
+  const int64_t cap = n > 0 ? n : 1;
+  const PpLayout w = pp_layout(n, 1, cap);
+  DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
+              workspace_bytes);
+  int rc = enable_big_smem();
+  if (rc != DAN_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PpArgs A = {};
+  A.n = (int)n;
+  A.num_classes = 2;
+  A.keep_topk = (int)cap;
+  A.nms_topk = nms_topk;
+  A.nms_thr = nms_threshold;
+  A.out_boxes = reinterpret_cast<float4*>(out_boxes);
+  A.out_scores = out_scores;
+  A.out_counts = out_count;
+  A.out_index = nullptr;
+  A.out_keep = out_keep;
+  A.filler = 0;
+  pp_bind(A, workspace, w);
+  key_build_kernel<<<grid_for(n), 256, 0, st>>>(scores, n, A.keys, A.key_count);
+  DAN_LAUNCH_CHECK("key_build_kernel");
+  topk_sort_kernel<false><<<1, kSortThreads, kSortCap * 8, st>>>(A, scores, reinterpret_cast<const float4*>(boxes), 0);
+  DAN_LAUNCH_CHECK("topk_sort_kernel");
+  return run_nms(A, 1, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+"""Tensor-level entry points: one python function per C-ABI call of include/dan_b200.h.
+
+Every function takes / returns CUDA ``torch.Tensor`` objects, allocates only the
+outputs (and a caller-owned workspace) with torch, and enqueues the kernels on
+torch's current stream.  No arithmetic of the hot path is done in PyTorch."""
+from __future__ import annotations
+
+import ctypes
+from collections import namedtuple
+
+import torch
+
+from . import _lib as L
+
+_ws = L.Workspace()
+
+EncodeResult = namedtuple("EncodeResult", ["targets", "labels", "scores", "matched_gt", "match"])
+Detections = namedtuple("Detections", ["boxes", "scores", "counts", "anchor_index", "keep_pos"])
+
+
+def _dev(t):
+    return t.device
+
+
+# ----------------------------------------------------------------------------------
+# anchors
+# ----------------------------------------------------------------------------------
+def make_pyramid(image_shape, anchors_height, anchors_width, anchors_depth, anchors_offsets, layer_shapes,
+                 feat_strides, allowed_borders, should_clips):
+    """Pack the arguments of AnchorEncoder.get_all_anchors (anchor_manipulator.py:213) into the
+    dan_pyramid POD.  Heights / widths are rounded to fp32 once, like tf.constant(float32)."""
+    p = L.Pyramid()
+    nl = len(anchors_depth)
+    if nl < 1 or nl > L.DAN_MAX_LAYERS:
+        raise L.DanError(-1, "num_layers must be in [1, %d], got %d" % (L.DAN_MAX_LAYERS, nl))
+    p.num_layers = nl
+    p.image_h, p.image_w = int(image_shape[0]), int(image_shape[1])
+    dpos = 0
+    for i in range(nl):
+        p.layer_h[i], p.layer_w[i] = int(layer_shapes[i][0]), int(layer_shapes[i][1])
+        p.depth[i] = int(anchors_depth[i])
+        p.clip[i] = 1 if should_clips[i] else 0
+        p.stride[i] = float(feat_strides[i])
+        off = anchors_offsets[i]
+        if isinstance(off, (list, tuple)):
+            p.offset_h[i], p.offset_w[i] = float(off[0]), float(off[1])
+        else:
+            p.offset_h[i] = p.offset_w[i] = float(off)
+        p.border[i] = float(allowed_borders[i])
+        hs = [float(v) for v in (anchors_height[i].tolist() if hasattr(anchors_height[i], "tolist") else anchors_height[i])]
+        ws = [float(v) for v in (anchors_width[i].tolist() if hasattr(anchors_width[i], "tolist") else anchors_width[i])]
+        if len(hs) != p.depth[i] or len(ws) != p.depth[i]:
+            raise L.DanError(-1, "layer %d: %d heights / %d widths for depth %d" % (i, len(hs), len(ws), p.depth[i]))
+        if dpos + p.depth[i] > L.DAN_MAX_DEPTH_TOTAL:
+            raise L.DanError(-4, "sum of anchor depths exceeds %d" % L.DAN_MAX_DEPTH_TOTAL)
+        for d in range(p.depth[i]):
+            p.anchor_h[dpos + d] = hs[d]
+            p.anchor_w[dpos + d] = ws[d]
+        dpos += p.depth[i]
+    return p
+
+
+def anchor_count(pyramid):
+    n = L.lib().dan_anchor_count(ctypes.byref(pyramid))
+    if n < 0:
+        L.check(-1)
+    return int(n)
+
+
+def generate_anchors(pyramid, device=None):
+    """-> (ymin, xmin, ymax, xmax) fp32 [N] and inside_mask bool [N]."""
+    L.require_device()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n = anchor_count(pyramid)
+    out = [torch.empty(n, dtype=torch.float32, device=device) for _ in range(4)]
+    mask = torch.empty(n, dtype=torch.bool, device=device)
+    with torch.cuda.device(device):
+        L.check(L.lib().dan_generate_anchors(ctypes.byref(pyramid), *[L.dev_ptr(t) for t in out], L.dev_ptr(mask),
+                                             L.stream_ptr()))
+    return out[0], out[1], out[2], out[3], mask
+
+
+def _anchor_ptrs(ymin, xmin, ymax, xmax):
+    n = ymin.numel()
+    for name, t in (("anchors_ymin", ymin), ("anchors_xmin", xmin), ("anchors_ymax", ymax), ("anchors_xmax", xmax)):
+        if t.numel() != n:
+            raise ValueError("anchor vectors differ in length")
+    return [L.dev_ptr(t, torch.float32, name) for name, t in
+            (("anchors_ymin", ymin), ("anchors_xmin", xmin), ("anchors_ymax", ymax), ("anchors_xmax", xmax))]
+
+
+def _mask_u8(inside_mask):
+    if inside_mask is None:
+        return None
+    if inside_mask.dtype not in (torch.bool, torch.uint8):
+        raise TypeError("inside_mask must be bool or uint8")
+    return inside_mask.contiguous()
+
+
+# ----------------------------------------------------------------------------------
+# matching on a dense overlaps matrix (the custom-op boundary)
+# ----------------------------------------------------------------------------------
+def iou_matrix(ymin, xmin, ymax, xmax, gt_boxes, inside_mask=None):
+    L.require_device()
+    gt_boxes = gt_boxes.contiguous()
+    n, m = ymin.numel(), gt_boxes.shape[0]
+    out = torch.empty((n, m), dtype=torch.float32, device=_dev(ymin))
+    mask = _mask_u8(inside_mask)
+    with torch.cuda.device(_dev(ymin)):
+        L.check(L.lib().dan_iou_matrix(*_anchor_ptrs(ymin, xmin, ymax, xmax), L.dev_ptr(mask), n,
+                                       L.dev_ptr(gt_boxes, torch.float32, "gt_boxes"), m, L.dev_ptr(out), L.stream_ptr()))
+    return out
+
+
+def intersection_matrix(ymin, xmin, ymax, xmax, gt_boxes):
+    L.require_device()
+    gt_boxes = gt_boxes.contiguous()
+    n, m = ymin.numel(), gt_boxes.shape[0]
+    out = torch.empty((n, m), dtype=torch.float32, device=_dev(ymin))
+    with torch.cuda.device(_dev(ymin)):
+        L.check(L.lib().dan_intersection_matrix(*_anchor_ptrs(ymin, xmin, ymax, xmax), n,
+                                                L.dev_ptr(gt_boxes, torch.float32, "gt_boxes"), m, L.dev_ptr(out),
+                                                L.stream_ptr()))
+    return out
+
+
+def small_mining_match(overlaps, negative_low_thres, negative_high_thres, positive_thres, min_match,
+                       stop_positive_thres):
+    """SmallMiningMatch op (cpp/ExtraLib/small_mining_match.cc:31-54) -> (int32 [N], fp32 [N])."""
+    L.require_device()
+    if overlaps.dim() != 2:
+        raise L.DanError(-1, "inputs must be in 'num_anchors x num_ground_truth' format.")
+    overlaps = overlaps.contiguous()
+    n, m = overlaps.shape
+    match = torch.empty(n, dtype=torch.int32, device=_dev(overlaps))
+    scores = torch.empty(n, dtype=torch.float32, device=_dev(overlaps))
+    nbytes = L.lib().dan_match_workspace_bytes(n, m)
+    ws = _ws.get(nbytes, _dev(overlaps))
+    with torch.cuda.device(_dev(overlaps)):
+        L.check(L.lib().dan_small_mining_match(L.dev_ptr(overlaps, torch.float32, "overlaps"), n, m, negative_low_thres,
+                                               negative_high_thres, positive_thres, int(min_match), stop_positive_thres,
+                                               L.dev_ptr(match), L.dev_ptr(scores), L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return match, scores
+
+
+def dual_max_match(overlaps, low_thres, high_thres, ignore_between=True, gt_max_first=True):
+    """do_dual_max_match (anchor_manipulator.py:54-105) -> (int64 [N], fp32 [N])."""
+    L.require_device()
+    if overlaps.dim() != 2:
+        raise L.DanError(-1, "overlap_matrix must be num_anchors x num_gt")
+    overlaps = overlaps.contiguous()
+    n, m = overlaps.shape
+    match = torch.empty(n, dtype=torch.int64, device=_dev(overlaps))
+    scores = torch.empty(n, dtype=torch.float32, device=_dev(overlaps))
+    nbytes = L.lib().dan_match_workspace_bytes(n, m)
+    ws = _ws.get(nbytes, _dev(overlaps))
+    with torch.cuda.device(_dev(overlaps)):
+        L.check(L.lib().dan_dual_max_match(L.dev_ptr(overlaps, torch.float32, "overlaps"), n, m, low_thres, high_thres,
+                                           1 if ignore_between else 0, 1 if gt_max_first else 0, L.dev_ptr(match),
+                                           L.dev_ptr(scores), L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return match, scores
+
+
+# ----------------------------------------------------------------------------------
+# fused batched encode
+# ----------------------------------------------------------------------------------
+def encode_params(positive_threshold, ignore_threshold, prior_scaling, match_mining, pa_scale=0.0, debug=False,
+                  negative_low_thres=0.0, min_match=6, stop_positive_thres=0.3, ignore_between=True,
+                  gt_max_first=True):
+    p = L.EncodeParams()
+    p.matcher = L.DAN_MATCH_MINING if match_mining else L.DAN_MATCH_DUAL
+    p.ignore_threshold = float(ignore_threshold)
+    p.positive_threshold = float(positive_threshold)
+    for i in range(4):
+        p.prior_scaling[i] = float(prior_scaling[i])
+    p.pa_scale = float(pa_scale)
+    p.debug = 1 if debug else 0
+    p.negative_low_thres = float(negative_low_thres)
+    p.min_match = int(min_match)
+    p.stop_positive_thres = float(stop_positive_thres)
+    p.ignore_between = 1 if ignore_between else 0
+    p.gt_max_first = 1 if gt_max_first else 0
+    return p
+
+
+def encode_batch(params, ymin, xmin, ymax, xmax, inside_mask, gt_boxes, gt_offsets, out=None, want_match=False,
+                 want_matched_gt=True, workspace=None):
+    """Fused IoU + match + encode for a batch (anchor_manipulator.py:275-387 per image).
+
+    gt_boxes [sum M, 4] fp32, gt_offsets [B+1] int32 (CSR).  Returns EncodeResult with
+    targets [B,N,4] f32, labels [B,N] int64, scores [B,N] f32, matched_gt [B,N,4] f32."""
+    L.require_device()
+    dev = _dev(ymin)
+    n = ymin.numel()
+    if gt_offsets.dtype != torch.int32:
+        raise TypeError("gt_offsets must be int32")
+    batch = gt_offsets.numel() - 1
+    gt_boxes = gt_boxes.contiguous().view(-1, 4)
+    total_gt = gt_boxes.shape[0]
+    if out is None:
+        targets = torch.empty((batch, n, 4), dtype=torch.float32, device=dev)
+        labels = torch.empty((batch, n), dtype=torch.int64, device=dev)
+        scores = torch.empty((batch, n), dtype=torch.float32, device=dev)
+        matched = torch.empty((batch, n, 4), dtype=torch.float32, device=dev) if want_matched_gt else None
+        match = torch.empty((batch, n), dtype=torch.int32, device=dev) if want_match else None
+    else:
+        targets, labels, scores, matched, match = out
+    mask = _mask_u8(inside_mask)
+    nbytes = L.lib().dan_encode_workspace_bytes(n, batch, total_gt)
+    ws = (workspace or _ws).get(nbytes, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_encode_batch(ctypes.byref(params), *_anchor_ptrs(ymin, xmin, ymax, xmax), L.dev_ptr(mask), n,
+                                         L.dev_ptr(gt_boxes, torch.float32, "gt_boxes") if total_gt else ctypes.c_void_p(0),
+                                         L.dev_ptr(gt_offsets, torch.int32, "gt_offsets"), batch, total_gt,
+                                         L.dev_ptr(targets, torch.float32), L.dev_ptr(labels, torch.int64),
+                                         L.dev_ptr(scores, torch.float32), L.dev_ptr(matched), L.dev_ptr(match),
+                                         L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return EncodeResult(targets, labels, scores, matched, match)
+
+
+# ----------------------------------------------------------------------------------
+# decode
+# ----------------------------------------------------------------------------------
+def decode_batch(pred_location, ymin, xmin, ymax, xmax, prior_scaling):
+    L.require_device()
+    pred = pred_location.contiguous()
+    if pred.dtype != torch.float32 or pred.dim() != 3 or pred.shape[-1] != 4:
+        raise TypeError("pred_location must be fp32 [batch, num_preds, 4]")
+    batch, n = pred.shape[0], pred.shape[1]
+    if n != ymin.numel():
+        raise ValueError("pred_location has %d rows but there are %d anchors" % (n, ymin.numel()))
+    out = torch.empty_like(pred)
+    ps = (ctypes.c_float * 4)(*[float(v) for v in prior_scaling])
+    with torch.cuda.device(_dev(pred)):
+        L.check(L.lib().dan_decode_batch(L.dev_ptr(pred), *_anchor_ptrs(ymin, xmin, ymax, xmax), n, batch, ps,
+                                         L.dev_ptr(out), L.stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------------
+# bbox_util pieces
+# ----------------------------------------------------------------------------------
+def softmax(logits):
+    L.require_device()
+    x = logits.contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // max(c, 1)
+    out = torch.empty_like(x)
+    with torch.cuda.device(_dev(x)):
+        L.check(L.lib().dan_softmax(L.dev_ptr(x, torch.float32, "logits"), rows, c, L.dev_ptr(out), L.stream_ptr()))
+    return out
+
+
+def select_bboxes_class(scores_pred, bboxes_pred, class_ind, select_threshold):
+    L.require_device()
+    s = scores_pred.contiguous()
+    b = bboxes_pred.contiguous()
+    n, c = s.shape
+    ob = torch.empty_like(b)
+    osc = torch.empty(n, dtype=torch.float32, device=_dev(s))
+    with torch.cuda.device(_dev(s)):
+        L.check(L.lib().dan_select_bboxes(L.dev_ptr(s, torch.float32, "scores_pred"), c, class_ind,
+                                          L.dev_ptr(b, torch.float32, "bboxes_pred"), n, float(select_threshold),
+                                          L.dev_ptr(ob), L.dev_ptr(osc), L.stream_ptr()))
+    return ob, osc
+
+
+def clip_boxes(boxes, height, width):
+    L.require_device()
+    b = boxes.contiguous()
+    out = torch.empty_like(b)
+    with torch.cuda.device(_dev(b)):
+        L.check(L.lib().dan_clip_bboxes(L.dev_ptr(b, torch.float32, "boxes"), b.numel() // 4, float(height), float(width),
+                                        L.dev_ptr(out), L.stream_ptr()))
+    return out
+
+
+def filter_boxes(scores, boxes, min_size):
+    L.require_device()
+    s = scores.contiguous()
+    b = boxes.contiguous()
+    os_, ob = torch.empty_like(s), torch.empty_like(b)
+    import numpy as np
+    thr = float(np.float32(float(min_size) + 1.0))
+    with torch.cuda.device(_dev(b)):
+        L.check(L.lib().dan_filter_bboxes(L.dev_ptr(s, torch.float32, "scores"), L.dev_ptr(b, torch.float32, "boxes"),
+                                          s.numel(), thr, L.dev_ptr(os_), L.dev_ptr(ob), L.stream_ptr()))
+    return os_, ob
+
+
+def bbox_convert(boxes, mode):
+    L.require_device()
+    b = boxes.contiguous()
+    out = torch.empty_like(b)
+    with torch.cuda.device(_dev(b)):
+        L.check(L.lib().dan_bbox_convert(L.dev_ptr(b, torch.float32, "boxes"), b.numel() // 4, int(mode), L.dev_ptr(out),
+                                         L.stream_ptr()))
+    return out
+
+
+def sort_boxes(scores, boxes, keep_topk):
+    """tf.nn.top_k + gather + zero pad -> (scores [keep_topk], boxes [keep_topk,4], index int32 [keep_topk])."""
+    L.require_device()
+    s = scores.contiguous()
+    b = boxes.contiguous()
+    n = s.numel()
+    dev = _dev(s)
+    os_ = torch.empty(keep_topk, dtype=torch.float32, device=dev)
+    ob = torch.empty((keep_topk, 4), dtype=torch.float32, device=dev)
+    oi = torch.empty(keep_topk, dtype=torch.int32, device=dev)
+    nbytes = L.lib().dan_sort_workspace_bytes(n, keep_topk)
+    ws = _ws.get(nbytes, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_sort_bboxes(L.dev_ptr(s, torch.float32, "scores"), L.dev_ptr(b, torch.float32, "boxes"), n,
+                                        int(keep_topk), L.dev_ptr(os_), L.dev_ptr(ob), L.dev_ptr(oi), L.dev_ptr(ws), nbytes,
+                                        L.stream_ptr()))
+    return os_, ob, oi
+
+
+def nms_boxes(scores, boxes, nms_topk, nms_threshold):
+    """tf.image.non_max_suppression + gather + zero pad.
+    -> (scores [nms_topk], boxes [nms_topk,4], keep int32 [nms_topk] (-1 padded), count int32 [1])."""
+    L.require_device()
+    s = scores.contiguous()
+    b = boxes.contiguous()
+    n = s.numel()
+    dev = _dev(s)
+    os_ = torch.empty(nms_topk, dtype=torch.float32, device=dev)
+    ob = torch.empty((nms_topk, 4), dtype=torch.float32, device=dev)
+    keep = torch.empty(nms_topk, dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = L.lib().dan_nms_workspace_bytes(n, nms_topk)
+    ws = _ws.get(nbytes, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_nms_bboxes(L.dev_ptr(s, torch.float32, "scores"), L.dev_ptr(b, torch.float32, "boxes"), n,
+                                       int(nms_topk), float(nms_threshold), L.dev_ptr(os_), L.dev_ptr(ob), L.dev_ptr(keep),
+                                       L.dev_ptr(cnt), L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return os_, ob, keep, cnt
+
+
+def postprocess_params(num_classes, image_shape, select_threshold, min_size, keep_topk, nms_topk, nms_threshold,
+                       prior_scaling=(0.1, 0.1, 0.2, 0.2)):
+    p = L.PostprocessParams()
+    p.num_classes = int(num_classes)
+    p.image_h, p.image_w = int(image_shape[0]), int(image_shape[1])
+    p.select_threshold = float(select_threshold)
+    p.min_size = float(min_size)
+    p.keep_topk = int(keep_topk)
+    p.nms_topk = int(nms_topk)
+    p.nms_threshold = float(nms_threshold)
+    for i in range(4):
+        p.prior_scaling[i] = float(prior_scaling[i])
+    return p
+
+
+def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=None, out=None, want_index=True,
+                      workspace=None):
+    """Batched fused parse_by_class (bbox_util.py:103-119).  cls_pred [B,N,C]; give loc_pred [B,N,4]
+    (+ anchors = (ymin,xmin,ymax,xmax)) or boxes_pred [B,N,4].  Returns Detections indexed [b, c-1]."""
+    L.require_device()
+    cls_pred = cls_pred.contiguous()
+    if cls_pred.dim() != 3:
+        raise TypeError("cls_pred must be [batch, num_anchors, num_classes]")
+    batch, n, c = cls_pred.shape
+    if c != params.num_classes:
+        raise ValueError("cls_pred has %d classes, params say %d" % (c, params.num_classes))
+    dev = _dev(cls_pred)
+    lists = c - 1
+    if out is None:
+        boxes = torch.empty((batch, lists, params.nms_topk, 4), dtype=torch.float32, device=dev)
+        scores = torch.empty((batch, lists, params.nms_topk), dtype=torch.float32, device=dev)
+        counts = torch.empty((batch, lists), dtype=torch.int32, device=dev)
+        aidx = torch.empty((batch, lists, params.nms_topk), dtype=torch.int32, device=dev) if want_index else None
+        kpos = torch.empty((batch, lists, params.nms_topk), dtype=torch.int32, device=dev) if want_index else None
+    else:
+        boxes, scores, counts, aidx, kpos = out
+    if loc_pred is not None:
+        loc_pred = loc_pred.contiguous()
+        if anchors is None:
+            raise ValueError("anchors are needed to decode loc_pred")
+        aptr = _anchor_ptrs(*anchors)
+    else:
+        boxes_pred = boxes_pred.contiguous()
+        aptr = [ctypes.c_void_p(0)] * 4
+    nbytes = L.lib().dan_postprocess_workspace_bytes(n, batch, c, params.keep_topk)
+    ws = (workspace or _ws).get(nbytes, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_postprocess_batch(ctypes.byref(params), L.dev_ptr(cls_pred, torch.float32, "cls_pred"),
+                                              L.dev_ptr(loc_pred, torch.float32, "loc_pred"),
+                                              L.dev_ptr(boxes_pred, torch.float32, "boxes_pred"), *aptr, n, batch,
+                                              L.dev_ptr(boxes), L.dev_ptr(scores), L.dev_ptr(counts), L.dev_ptr(aidx),
+                                              L.dev_ptr(kpos), L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return Detections(boxes, scores, counts, aidx, kpos)

@@ -1,0 +1,142 @@
+"""Batched hot path = training encode + evaluation postprocess, sharded per image.
+
+Images are independent (the reference itself handles one image at a time:
+dataset/dataset_common.py:150, eval_sfd.py:311-327), so a batch is split into
+contiguous blocks, one per rank, with NO data-path collective.  The only exchange
+is the variable-length detections at the end: every rank's NMS kernel writes its
+zero padded keep lists and per-image counts straight into ONE fixed-capacity slab,
+and one ``all_gather_into_tensor`` (NCCL on GPUs, gloo in the CPU tests) moves
+all slabs -- the counts travel inside the slab, so there is no size exchange.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import torch
+
+from . import functional as F
+
+Shard = namedtuple("Shard", ["lo", "hi"])
+
+
+def shard_range(batch, rank, world_size):
+    """Contiguous block [lo, hi) of a batch owned by `rank` (first `batch % world` ranks get one more)."""
+    base, rem = divmod(int(batch), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return Shard(lo, lo + base + (1 if rank < rem else 0))
+
+
+def shard_csr(gt_boxes, gt_offsets, shard):
+    """Slice a CSR ground-truth batch to the images [lo, hi) (offsets rebased to 0)."""
+    offs = gt_offsets[shard.lo:shard.hi + 1]
+    start, end = int(offs[0]), int(offs[-1])
+    return gt_boxes[start:end], (offs - offs[0]).to(gt_offsets.dtype)
+
+
+class DetectionSlab(object):
+    """One rank's detections as a single contiguous buffer.
+
+    layout (all 4-byte words): counts int32 [B, L] (padded to 16 B) | boxes f32 [B, L, K, 4] | scores f32 [B, L, K]
+    with L = num_classes - 1 and K = nms_topk.  ``views()`` returns typed views that the NMS kernel
+    writes in place, so the slab needs no packing step before the collective."""
+
+    def __init__(self, images, lists, nms_topk, device):
+        self.images, self.lists, self.k = int(images), int(lists), int(nms_topk)
+        self.n_counts = self.images * self.lists
+        self.n_scores = self.n_counts * self.k
+        self.n_boxes = self.n_scores * 4
+        # counts region padded to 4 words so that the box region stays 16-byte aligned
+        self.counts_words = (self.n_counts + 3) // 4 * 4
+        self.words = self.counts_words + self.n_scores + self.n_boxes
+        self.buf = torch.zeros(self.words, dtype=torch.float32, device=device)
+
+    @staticmethod
+    def words_for(images, lists, nms_topk):
+        nc = images * lists
+        return (nc + 3) // 4 * 4 + nc * nms_topk * 5
+
+    def views(self, buf=None):
+        buf = self.buf if buf is None else buf
+        o = 0
+        counts = buf[o:o + self.n_counts].view(torch.int32).view(self.images, self.lists)
+        # boxes first after the counts (16-byte alignment for float4 stores), then scores
+        o = self.counts_words
+        boxes = buf[o:o + self.n_boxes].view(self.images, self.lists, self.k, 4)
+        o += self.n_boxes
+        scores = buf[o:o + self.n_scores].view(self.images, self.lists, self.k)
+        return counts, scores, boxes
+
+
+def gather_detections(slab, world_size, group=None):
+    """ONE collective for the variable-length detections.  Returns a list (rank order) of
+    (counts, scores, boxes) views; every rank must pass a slab of identical capacity."""
+    import torch.distributed as dist
+    if world_size == 1 or not dist.is_initialized():
+        return [slab.views()]
+    out = torch.empty(world_size * slab.words, dtype=slab.buf.dtype, device=slab.buf.device)
+    dist.all_gather_into_tensor(out, slab.buf, group=group)
+    return [slab.views(out[r * slab.words:(r + 1) * slab.words]) for r in range(world_size)]
+
+
+def flatten_detections(gathered, image_counts=None):
+    """Ragged result for the host: list over images (global order) of dict(class -> (boxes [n,4], scores [n])).
+    `image_counts[r]` = number of real images of rank r (ranks may own fewer images than the slab capacity)."""
+    result = []
+    for r, (counts, scores, boxes) in enumerate(gathered):
+        n_img = counts.shape[0] if image_counts is None else image_counts[r]
+        c = counts.cpu()
+        for i in range(n_img):
+            per_class = {}
+            for l in range(counts.shape[1]):
+                n = int(c[i, l])
+                per_class[l + 1] = (boxes[i, l, :n], scores[i, l, :n])
+            result.append(per_class)
+    return result
+
+
+class HotPath(object):
+    """The whole path for one rank: encode (training side) + postprocess (evaluation side)."""
+
+    def __init__(self, anchors_train, inside_mask, encode_params, postprocess_params, anchors_eval=None,
+                 images_per_rank=None):
+        self.anchors_train = anchors_train          # (ymin, xmin, ymax, xmax)
+        self.inside_mask = inside_mask
+        self.anchors_eval = anchors_eval if anchors_eval is not None else anchors_train
+        self.enc_params = encode_params
+        self.pp_params = postprocess_params
+        self.device = anchors_train[0].device
+        self.images_per_rank = images_per_rank
+        self._slab = None
+        self._enc_out = None
+        self._aux = None
+
+    def _buffers(self, images):
+        n = self.anchors_train[0].numel()
+        k, lists = self.pp_params.nms_topk, self.pp_params.num_classes - 1
+        cap = images if self.images_per_rank is None else self.images_per_rank
+        if self._slab is None or self._slab.images != cap:
+            self._slab = DetectionSlab(cap, lists, k, self.device)
+            self._aux = (torch.empty((cap, lists, k), dtype=torch.int32, device=self.device),
+                         torch.empty((cap, lists, k), dtype=torch.int32, device=self.device))
+        if self._enc_out is None or self._enc_out[0].shape[0] != images:
+            d = self.device
+            self._enc_out = (torch.empty((images, n, 4), dtype=torch.float32, device=d),
+                             torch.empty((images, n), dtype=torch.int64, device=d),
+                             torch.empty((images, n), dtype=torch.float32, device=d),
+                             torch.empty((images, n, 4), dtype=torch.float32, device=d),
+                             None)
+
+    def step(self, gt_boxes, gt_offsets, cls_pred, loc_pred):
+        """One pass over this rank's images.  Everything is enqueued on the current stream."""
+        images = gt_offsets.numel() - 1
+        self._buffers(images)
+        enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
+                             out=self._enc_out)
+        counts, scores, boxes = self._slab.views()
+        det = F.postprocess_batch(self.pp_params, cls_pred, loc_pred=loc_pred, anchors=self.anchors_eval,
+                                  out=(boxes[:images], scores[:images], counts[:images], self._aux[0][:images],
+                                       self._aux[1][:images]))
+        return enc, det
+
+    def gather(self, world_size, group=None):
+        return gather_detections(self._slab, world_size, group)

@@ -1,0 +1,185 @@
+"""Seeded synthetic inputs for the anchor hot path (SURVEY.md 8(d) generators) and the
+reference's hard-coded stride pyramids.  numpy only; used by tests/ and bench.py to
+produce the SAME inputs for the CUDA path and for the CPU oracle.  Nothing here is
+part of the measured path."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+BASE_SEED = 20180817   # the reference's tf_random_seed (train_sfd.py:92-93)
+f32 = np.float32
+
+
+# ---------------------------------------------------------------------------------
+# pyramids hard-coded in the reference scripts
+# ---------------------------------------------------------------------------------
+def layer_shapes_for(image_size, strides=(4, 8, 16, 32, 64, 128)):
+    """'same'-padded feature map sides: ceil(S / stride) (net/sfd_net.py:127-156)."""
+    h, w = image_size
+    return [(int(math.ceil(h / s)), int(math.ceil(w / s))) for s in strides]
+
+
+def pyramid_config(kind="s3fd", image_size=(640, 640), border=None, clip=False):
+    """kind 's3fd' (train_sfd.py:179-184, ratio 1) | 'dan' (train_dan.py:181-186, ratio 0.8).
+    border=None -> the training setting (border = image size => mask all true);
+    eval scripts use border 0 (eval_sfd.py:266-269)."""
+    strides = [4, 8, 16, 32, 64, 128]
+    ratio = {"s3fd": 1.0, "pyramidbox": 1.0, "dan": 0.8}[kind]
+    cfg = dict(
+        image_shape=list(image_size),
+        anchor_scales=[(16.,), (32.,), (64.,), (128.,), (256.,), (512.,)],
+        extra_scales=[(), (), (), (), (), ()],
+        anchor_ratios=[(ratio,)] * 6,
+        layer_shapes=layer_shapes_for(image_size, strides),
+        layer_strides=strides,
+        offsets=[0.5] * 6,
+        allowed_borders=[float(image_size[0]) if border is None else float(border)] * 6,
+        should_clips=[bool(clip)] * 6,
+    )
+    return cfg
+
+
+def build_anchors(encoder, cfg):
+    """Run get_anchors_width_height + get_all_anchors of ANY AnchorEncoder implementation
+    (dan_b200's or the oracle's) on a pyramid config.  -> (ymin, xmin, ymax, xmax, inside_mask)."""
+    hs, ws, ds = [], [], []
+    for i in range(len(cfg["layer_shapes"])):
+        h, w, d = encoder.get_anchors_width_height(cfg["anchor_scales"][i], cfg["extra_scales"][i],
+                                                   cfg["anchor_ratios"][i])
+        hs.append(h)
+        ws.append(w)
+        ds.append(d)
+    return encoder.get_all_anchors(cfg["image_shape"], hs, ws, ds, cfg["offsets"], cfg["layer_shapes"],
+                                   cfg["layer_strides"], cfg["allowed_borders"], cfg["should_clips"])
+
+
+def anchors_numpy(cfg):
+    """Plain numpy anchors for the GENERATORS only (float64 math, not a parity path)."""
+    out = []
+    for i, (lh, lw) in enumerate(cfg["layer_shapes"]):
+        s = cfg["layer_strides"][i]
+        hw = []
+        for sc in cfg["extra_scales"][i]:
+            hw.append((sc, sc))
+        for sc in cfg["anchor_scales"][i]:
+            for r in cfg["anchor_ratios"][i]:
+                hw.append((sc / math.sqrt(r), sc * math.sqrt(r)))
+        ys, xs = np.meshgrid(np.arange(lh), np.arange(lw), indexing="ij")
+        cy = (ys + 0.5) * s
+        cx = (xs + 0.5) * s
+        for_layer = []
+        for (h, w) in hw:
+            for_layer.append(np.stack([cy - (h - 1) / 2, cx - (w - 1) / 2, cy + (h - 1) / 2, cx + (w - 1) / 2], -1))
+        out.append(np.stack(for_layer, axis=2).reshape(-1, 4))
+    return np.concatenate(out, 0)
+
+
+# ---------------------------------------------------------------------------------
+# ground truth generators
+# ---------------------------------------------------------------------------------
+def _faces(rng, m, smin, smax, size, snap):
+    s = np.exp(rng.uniform(np.log(smin), np.log(smax), m))
+    h = s * rng.uniform(1.0, 1.4, m)
+    w = s
+    h = np.minimum(h, size[0] - 1.0)
+    w = np.minimum(w, size[1] - 1.0)
+    ymin = rng.uniform(0, (size[0] - 1.0) - h + 1e-6)
+    xmin = rng.uniform(0, (size[1] - 1.0) - w + 1e-6)
+    boxes = np.stack([ymin, xmin, ymin + h - 1.0, xmin + w - 1.0], axis=1)
+    if snap:
+        boxes = np.round(boxes / snap) * snap
+    boxes = boxes.astype(f32)
+    # the reference's small-face filter (preprocessing/sfd_preprocessing.py:544-551): h > 6 & w > 3
+    hh = boxes[:, 2] - boxes[:, 0] + 1
+    ww = boxes[:, 3] - boxes[:, 1] + 1
+    return boxes[(hh > 6) & (ww > 3)]
+
+
+def gen_faces(image_index, max_faces=50, size=(640, 640), snap=0.0, min_faces=1, smin=8.0, smax=400.0):
+    """G1 faces (snap=0) / G1-snap (snap=1 or 4: corners on a grid -> exact IoU ties)."""
+    rng = np.random.default_rng(BASE_SEED + image_index)
+    m = int(rng.integers(min_faces, max_faces + 1))
+    return _faces(rng, m, smin, min(smax, min(size) * 0.625), size, snap)
+
+
+def gen_dense_tiny(image_index, size=(640, 640), lo=200, hi=1000, snap=0.0):
+    """G2 dense tiny faces: M ~ U{200..1000}, side exp(U(ln 7, ln 40))."""
+    rng = np.random.default_rng(BASE_SEED + 100000 + image_index)
+    m = int(rng.integers(lo, hi + 1))
+    return _faces(rng, m, 7.0, 40.0, size, snap)
+
+
+def gen_adversarial(kind, size=(640, 640)):
+    """G-adv: degenerate ground truth sets."""
+    h, w = size
+    if kind == "empty":
+        return np.zeros((0, 4), f32)
+    if kind == "outside":      # all-zero IoU column
+        return np.asarray([[100, 100, 180, 170], [-500, -500, -400, -420]], f32)
+    if kind == "duplicate":
+        return np.asarray([[50, 60, 120, 130], [50, 60, 120, 130], [300, 310, 420, 400]], f32)
+    if kind == "anchor_identical":   # IoU == 1 with an S3FD stride-8 anchor
+        return np.asarray([[4 - 15.5, 4 - 15.5, 4 + 15.5, 4 + 15.5], [100 - 15.5, 204 - 15.5, 100 + 15.5, 204 + 15.5]], f32)
+    if kind == "tiny":
+        return np.asarray([[10, 10, 17, 14], [300.2, 300.7, 309.1, 306.3], [630, 630, 639, 639]], f32)
+    if kind == "huge":
+        return np.asarray([[0, 0, h - 1, w - 1]], f32)
+    raise ValueError(kind)
+
+
+def to_csr(list_of_boxes):
+    """list of [M_i,4] -> (concat [sum M,4] fp32, offsets int32 [B+1])."""
+    offs = np.zeros(len(list_of_boxes) + 1, np.int32)
+    for i, b in enumerate(list_of_boxes):
+        offs[i + 1] = offs[i] + len(b)
+    cat = np.concatenate([np.asarray(b, f32).reshape(-1, 4) for b in list_of_boxes], 0) if list_of_boxes else \
+        np.zeros((0, 4), f32)
+    return np.ascontiguousarray(cat, f32), offs
+
+
+# ---------------------------------------------------------------------------------
+# G3: predictions of a "trained detector"
+# ---------------------------------------------------------------------------------
+def _iou_chunked(anchors, faces):
+    a = anchors[:, None, :].astype(np.float64)
+    g = faces[None, :, :].astype(np.float64)
+    ih = np.maximum(np.minimum(a[..., 2], g[..., 2]) - np.maximum(a[..., 0], g[..., 0]) + 1, 0)
+    iw = np.maximum(np.minimum(a[..., 3], g[..., 3]) - np.maximum(a[..., 1], g[..., 1]) + 1, 0)
+    inter = ih * iw
+    aa = (a[..., 2] - a[..., 0] + 1) * (a[..., 3] - a[..., 1] + 1)
+    ag = (g[..., 2] - g[..., 0] + 1) * (g[..., 3] - g[..., 1] + 1)
+    return inter / (aa + ag - inter)
+
+
+def gen_predictions(image_index, anchors, size=(640, 640), max_faces=300, prior_scaling=(0.1, 0.1, 0.2, 0.2)):
+    """G3: K_true ~ U{1..max_faces} planted faces; anchors with IoU > 0.35 to a face get foreground
+    logits (N(0,1), N(5,1)) and loc = encode(face) + N(0, 0.3); all others (N(8,1), N(0,1)) and N(0,0.5).
+    -> (cls_pred [N,2] fp32, loc_pred [N,4] fp32, faces [K,4])"""
+    rng = np.random.default_rng(BASE_SEED + 200000 + image_index)
+    k_true = int(rng.integers(1, max_faces + 1))
+    faces = _faces(rng, k_true, 8.0, min(400.0, min(size) * 0.625), size, 0.0)
+    n = anchors.shape[0]
+    cls = np.stack([rng.normal(8.0, 1.0, n), rng.normal(0.0, 1.0, n)], axis=1)
+    loc = rng.normal(0.0, 0.5, (n, 4))
+    best_iou = np.zeros(n)
+    best_face = np.zeros(n, np.int64)
+    for c0 in range(0, n, 16384):
+        iou = _iou_chunked(anchors[c0:c0 + 16384], faces)
+        best_iou[c0:c0 + 16384] = iou.max(1)
+        best_face[c0:c0 + 16384] = iou.argmax(1)
+    fg = best_iou > 0.35
+    nf = int(fg.sum())
+    if nf:
+        a = anchors[fg].astype(np.float64)
+        g = faces[best_face[fg]].astype(np.float64)
+        ah, aw = a[:, 2] - a[:, 0] + 1, a[:, 3] - a[:, 1] + 1
+        acy, acx = (a[:, 0] + a[:, 2]) / 2, (a[:, 1] + a[:, 3]) / 2
+        gh, gw = g[:, 2] - g[:, 0] + 1, g[:, 3] - g[:, 1] + 1
+        gcy, gcx = (g[:, 0] + g[:, 2]) / 2, (g[:, 1] + g[:, 3]) / 2
+        enc = np.stack([(gcy - acy) / ah / prior_scaling[0], (gcx - acx) / aw / prior_scaling[1],
+                        np.log(gh / ah) / prior_scaling[2], np.log(gw / aw) / prior_scaling[3]], 1)
+        loc[fg] = enc + rng.normal(0.0, 0.3, (nf, 4))
+        cls[fg] = np.stack([rng.normal(0.0, 1.0, nf), rng.normal(5.0, 1.0, nf)], axis=1)
+    return cls.astype(f32), loc.astype(f32), faces

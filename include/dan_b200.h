@@ -1,0 +1,238 @@
+/*
+ * dan_b200 -- C ABI of the Blackwell-native (sm_100a) anchor hot path of HiKapok/DAN.
+ *
+ * This is the drop-in boundary.  Everything the reference reaches for this path
+ * through TensorFlow graph ops and the `SmallMiningMatch` custom op
+ * (cpp/ExtraLib/build/libextra_lib.so, loaded by utility/custom_op.py:33-48) is
+ * exposed here as plain `extern "C"` functions taking device pointers, sizes and
+ * a cudaStream_t (passed as void*).  No C++ types, no exceptions, no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative DAN_ERR_* code; the
+ *     message is available from dan_last_error() (thread local);
+ *   - the caller owns every buffer; the library only touches the caller-provided
+ *     workspace (size from the matching dan_*_workspace_bytes());
+ *   - all pointers are DEVICE pointers unless the name starts with `h_`;
+ *   - `stream` is a cudaStream_t; work is enqueued, never synchronised, so every
+ *     call is CUDA-graph capturable;
+ *   - boxes are fp32 [ymin, xmin, ymax, xmax]; the +1 (inclusive pixel) convention
+ *     of utility/anchor_manipulator.py is used everywhere except inside NMS
+ *     (tf.image.non_max_suppression has no +1);
+ *   - the library is stateless and re-entrant across host threads / streams
+ *     (the reference op is called concurrently from 36-48 queue threads,
+ *     train_sfd.py:37-39); two concurrent calls must not share a workspace.
+ *
+ * Reference citations are relative to /root/reference.
+ */
+#ifndef DAN_B200_H_
+#define DAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAN_B200_VERSION 100
+
+#define DAN_OK 0
+#define DAN_ERR_INVALID_ARGUMENT (-1) /* mirrors errors::InvalidArgument of the TF op */
+#define DAN_ERR_WORKSPACE (-2)        /* workspace missing or too small                */
+#define DAN_ERR_CUDA (-3)             /* a CUDA runtime call / launch failed           */
+#define DAN_ERR_UNSUPPORTED (-4)      /* size beyond what the kernels were built for   */
+
+#define DAN_MAX_LAYERS 16
+#define DAN_MAX_DEPTH_TOTAL 128
+
+/* matcher selection for dan_encode_batch */
+#define DAN_MATCH_DUAL 0   /* do_dual_max_match, utility/anchor_manipulator.py:54-105 */
+#define DAN_MATCH_MINING 1 /* SmallMiningMatch,  cpp/ExtraLib/small_mining_match.cc   */
+
+int dan_version(void);
+const char* dan_last_error(void);
+/* 1 when a CUDA device of compute capability 10.x is visible, else 0 (no error set). */
+int dan_device_ok(void);
+
+/* ------------------------------------------------------------------------- *
+ * (a2-a5) anchors: AnchorEncoder.get_all_anchors
+ *         utility/anchor_manipulator.py:163-198 (per layer), :213-273 (all)
+ * ------------------------------------------------------------------------- */
+typedef struct dan_pyramid {
+  int32_t num_layers;
+  int32_t image_h, image_w;
+  int32_t layer_h[DAN_MAX_LAYERS], layer_w[DAN_MAX_LAYERS];
+  int32_t depth[DAN_MAX_LAYERS];        /* anchors per cell (get_anchors_width_height) */
+  int32_t clip[DAN_MAX_LAYERS];         /* should_clips                                */
+  float stride[DAN_MAX_LAYERS];         /* feat_strides                                */
+  float offset_h[DAN_MAX_LAYERS], offset_w[DAN_MAX_LAYERS];
+  float border[DAN_MAX_LAYERS];         /* allowed_borders                             */
+  /* per-layer anchor heights / widths, concatenated in layer order (sum depth)        */
+  float anchor_h[DAN_MAX_DEPTH_TOTAL], anchor_w[DAN_MAX_DEPTH_TOTAL];
+} dan_pyramid;
+
+/* total anchors; <0 on invalid pyramid */
+int64_t dan_anchor_count(const dan_pyramid* h_pyr);
+
+/* out_*: fp32 [N]; out_inside_mask: uint8 [N] (may be NULL). */
+int dan_generate_anchors(const dan_pyramid* h_pyr, float* out_ymin, float* out_xmin, float* out_ymax,
+                         float* out_xmax, uint8_t* out_inside_mask, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a6) iou_matrix: utility/anchor_manipulator.py:24-52, materialised [N, M].
+ *      inside_mask may be NULL (then no mask multiply, like iou_matrix itself).
+ * ------------------------------------------------------------------------- */
+int dan_iou_matrix(const float* a_ymin, const float* a_xmin, const float* a_ymax, const float* a_xmax,
+                   const uint8_t* inside_mask, int32_t num_anchors, const float* gt_boxes,
+                   int32_t num_gt, float* out_overlaps, void* stream);
+
+/* intersection(), anchor_manipulator.py:29-43, materialised [N, M] (no mask). */
+int dan_intersection_matrix(const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                            const float* a_xmax, int32_t num_anchors, const float* gt_boxes,
+                            int32_t num_gt, float* out_inter, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a8) the SmallMiningMatch op on a dense overlaps matrix -- the literal
+ *      replacement of REGISTER_OP("SmallMiningMatch") small_mining_match.cc:31-54.
+ *      overlaps: fp32 [N, M] row major, every element in [0, 1] (op doc :42-43).
+ *      Attribute checks are those of the op constructor (:292-305).
+ * ------------------------------------------------------------------------- */
+size_t dan_match_workspace_bytes(int32_t num_anchors, int32_t num_gt);
+int dan_small_mining_match(const float* overlaps, int32_t num_anchors, int32_t num_gt,
+                           float negative_low_thres, float negative_high_thres, float positive_thres,
+                           int32_t min_match, float stop_positive_thres, int32_t* out_match_indices,
+                           float* out_match_scores, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* (a7) do_dual_max_match on a dense overlaps matrix, anchor_manipulator.py:54-105.
+ *      out_match_indices is int64 like tf.argmax. */
+int dan_dual_max_match(const float* overlaps, int32_t num_anchors, int32_t num_gt, float low_thres,
+                       float high_thres, int32_t ignore_between, int32_t gt_max_first,
+                       int64_t* out_match_indices, float* out_match_scores, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a9/a10) batched fused encode: IoU + match + encode, no [N,M] matrix in HBM.
+ *   encode_anchors    anchor_manipulator.py:275-326  (pa_scale = 0)
+ *   encode_pa_anchors anchor_manipulator.py:328-387  (pa_scale = scale > 0)
+ * One call encodes `batch` images that share one anchor set; image b owns GT rows
+ * [gt_offsets[b], gt_offsets[b+1]) of gt_boxes (CSR).  An image with no GT gets
+ * the reference's dummy box [0,0,1,1] (:286).
+ * ------------------------------------------------------------------------- */
+typedef struct dan_encode_params {
+  int32_t matcher;          /* DAN_MATCH_DUAL | DAN_MATCH_MINING                         */
+  float ignore_threshold;   /* dual: low_thres; mining: negative_high_thres              */
+  float positive_threshold; /* dual: high_thres; mining: positive_thres                  */
+  float prior_scaling[4];
+  float pa_scale;           /* 0: encode_anchors; >0: encode_pa_anchors with this scale  */
+  int32_t debug;            /* debug=True: targets carry the raw anchors (:319-320)      */
+  /* mining attributes (small_mining_match.cc:33-37); the reference call site
+   * anchor_manipulator.py:291 uses (0., ignore, positive, 6, 0.3) */
+  float negative_low_thres;
+  int32_t min_match;
+  float stop_positive_thres;
+  /* dual options (anchor_manipulator.py:54) */
+  int32_t ignore_between;
+  int32_t gt_max_first;
+} dan_encode_params;
+
+size_t dan_encode_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t total_gt);
+
+/* out_targets [B,N,4] f32; out_labels [B,N] int64 (1 pos, 0 neg, -1 ignore);
+ * out_scores [B,N] f32; out_matched_gt [B,N,4] f32 (may be NULL);
+ * out_match [B,N] int32 (may be NULL): >=0 GT index within the image, -1, -2.  */
+int dan_encode_batch(const dan_encode_params* h_params, const float* a_ymin, const float* a_xmin,
+                     const float* a_ymax, const float* a_xmax, const uint8_t* inside_mask,
+                     int32_t num_anchors, const float* gt_boxes, const int32_t* gt_offsets,
+                     int32_t batch, int32_t total_gt, float* out_targets, int64_t* out_labels,
+                     float* out_scores, float* out_matched_gt, int32_t* out_match, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a11) decode_anchors / batch_decode_anchors, anchor_manipulator.py:389-424.
+ *       pred [B,N,4] (cy,cx,h,w offsets) -> out [B,N,4] boxes.
+ * ------------------------------------------------------------------------- */
+int dan_decode_batch(const float* pred, const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                     const float* a_xmax, int32_t num_anchors, int32_t batch,
+                     const float* h_prior_scaling, float* out_boxes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a12-a18) utility/bbox_util.py helpers, one kernel each (elementwise).
+ * ------------------------------------------------------------------------- */
+/* tf.nn.softmax over the last axis (bbox_util.py:105), rows x classes. */
+int dan_softmax(const float* logits, int64_t rows, int32_t num_classes, float* out, void* stream);
+/* select_bboxes :24-36 for one class column: out_boxes = boxes*m, out_scores = s*m. */
+int dan_select_bboxes(const float* scores, int32_t num_classes, int32_t class_ind, const float* boxes,
+                      int64_t n, float select_threshold, float* out_boxes, float* out_scores,
+                      void* stream);
+/* clip_bboxes :38-48 on an AoS [n,4] tensor (in place allowed). */
+int dan_clip_bboxes(const float* boxes, int64_t n, float height, float width, float* out_boxes,
+                    void* stream);
+/* filter_bboxes :50-59 ; min_size_plus_1 = fp32(min_size + 1.) */
+int dan_filter_bboxes(const float* scores, const float* boxes, int64_t n, float min_size_plus_1,
+                      float* out_scores, float* out_boxes, void* stream);
+/* bbox_point2center :92-96 (mode 0) / bbox_center2point :98-101 (mode 1) /
+ * areas() anchor_manipulator.py:24-27 (mode 2: area written to column 0, rest 0) */
+int dan_bbox_convert(const float* boxes, int64_t n, int32_t mode, float* out_boxes, void* stream);
+
+/* sort_bboxes :61-72 = tf.nn.top_k(sorted) + gather + zero pad to keep_topk.
+ * Descending score, equal scores -> lower index first.  out_* have keep_topk rows;
+ * out_index (int32, may be NULL) is -1 in the padding. */
+size_t dan_sort_workspace_bytes(int64_t n, int32_t keep_topk);
+int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t keep_topk,
+                    float* out_scores, float* out_boxes, int32_t* out_index, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* nms_bboxes :75-78 / nms_bboxes_with_padding :80-90 = tf.image.non_max_suppression
+ * (greedy, IoU without +1, strict >, area<=0 never suppresses) + gather + zero pad
+ * to nms_topk.  Input need not be sorted; equal scores keep input order (documented
+ * tie policy).  out_count: int32 [1] number of selected boxes; out_keep int32
+ * [nms_topk] selected input indices (-1 padded; may be NULL). */
+size_t dan_nms_workspace_bytes(int64_t n, int32_t nms_topk);
+int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t nms_topk,
+                   float nms_threshold, float* out_scores, float* out_boxes, int32_t* out_keep,
+                   int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a17) batched fused parse_by_class, bbox_util.py:103-119:
+ *   softmax -> select(threshold) -> [decode] -> clip -> min-size filter ->
+ *   per-class top-k (block radix select + sort) -> bitmask NMS -> zero pad.
+ * cls_pred [B,N,C] logits.  Exactly one of `loc_pred` ([B,N,4] offsets, decoded
+ * in-kernel against the anchors like decode_anchors) or `boxes_pred` ([B,N,4]
+ * already decoded boxes, what parse_by_class literally takes) must be non-NULL.
+ * ------------------------------------------------------------------------- */
+typedef struct dan_postprocess_params {
+  int32_t num_classes;
+  int32_t image_h, image_w;
+  float select_threshold; /* must be >= 0 */
+  float min_size;
+  int32_t keep_topk;
+  int32_t nms_topk;
+  float nms_threshold;
+  float prior_scaling[4];
+} dan_postprocess_params;
+
+size_t dan_postprocess_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t num_classes,
+                                       int32_t keep_topk);
+
+/* Outputs are indexed [b][c-1] for classes c = 1..C-1:
+ *   out_boxes  [B, C-1, nms_topk, 4] f32, zero padded
+ *   out_scores [B, C-1, nms_topk]    f32, zero padded
+ *   out_counts [B, C-1]              int32  number of REAL (score>0) detections kept
+ *   out_anchor_index [B, C-1, nms_topk] int32 (may be NULL): anchor index of each
+ *       kept detection, -1 in the padding
+ *   out_keep_pos [B, C-1, nms_topk] int32 (may be NULL): what
+ *       tf.image.non_max_suppression returns inside nms_bboxes_with_padding, i.e.
+ *       positions in the top-k sorted list (zero-score filler rows included),
+ *       -1 beyond the number selected. */
+int dan_postprocess_batch(const dan_postprocess_params* h_params, const float* cls_pred,
+                          const float* loc_pred, const float* boxes_pred, const float* a_ymin,
+                          const float* a_xmin, const float* a_ymax, const float* a_xmax,
+                          int32_t num_anchors, int32_t batch, float* out_boxes, float* out_scores,
+                          int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAN_B200_H_ */

@@ -1,0 +1,130 @@
+"""Generates tests/golden/*.npz.  Run HERE (the build container), where /root/reference
+exists: the mining matcher outputs come from the reference's OWN functor compiled verbatim
+(oracle/_ref/libsmm_ref.so, `make -C oracle`), everything else from the numpy restatement
+oracle/reference_np.py.  The fixtures pin (a) the restatement against the real reference
+and (b) the CUDA kernels on the GPU box, where /root/reference does not exist.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from dan_b200 import synthetic  # noqa: E402
+from oracle import native, reference_np as R  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def pack_encode(res):
+    targets, labels, scores, matched, match = res
+    nz = np.nonzero(labels != 0)[0].astype(np.int32)
+    pos = np.nonzero(labels == 1)[0].astype(np.int32)
+    return dict(nonzero_rows=nz, nonzero_labels=labels[nz].astype(np.int8), pos_rows=pos,
+                pos_match=match[pos].astype(np.int32), pos_targets=targets[pos], pos_matched=matched[pos],
+                scores=scores, match=match.astype(np.int32))
+
+
+def main():
+    native.build()
+    assert native.have_reference(), "oracle/_ref/libsmm_ref.so missing: run `make -C oracle` where /root/reference exists"
+
+    # ---- known-answer vectors for the custom op (cpp/ExtraLib/test_op.py:41,56) -------------
+    ov = np.array([[0.1, 0.4, 0.6, 0.2, 0.7], [0.5, 0.14, 0.76, 0.32, 0.47], [0.21, 0.94, 0.66, 0.22, 0.57],
+                   [0.91, 0.14, 0.26, 0.42, 0.67], [0.11, 0.84, 0.26, 0.42, 0.57]], np.float32)
+    m, s = native.small_mining_match(ov, 0., 0.6, 0.6, 5, 0.1, impl="reference")
+    tie = np.array([[.4]] * 7 + [[.45]], np.float32)
+    mt, st = native.small_mining_match(tie, 0., .5, .5, 3, .3, impl="reference")
+    np.savez(os.path.join(OUT, "smm_known_answers.npz"), test_op_overlaps=ov, test_op_match=m, test_op_scores=s,
+             test_op_attrs=np.array([0., 0.6, 0.6, 5, 0.1]), tie_overlaps=tie, tie_match=mt, tie_scores=st,
+             tie_attrs=np.array([0., .5, .5, 3, .3]))
+
+    # ---- random dense matrices through the reference functor --------------------------------
+    rng = np.random.default_rng(synthetic.BASE_SEED)
+    dense = {}
+    for i, (n, mm, levels) in enumerate([(64, 5, 0), (300, 17, 12), (1000, 40, 30), (33, 70, 8)]):
+        x = rng.uniform(0, 1, (n, mm)).astype(np.float32)
+        x[x < 0.55] = 0
+        if levels:
+            x = (np.round(x * levels) / levels).astype(np.float32)    # heavy exact ties
+        for attrs in [(0., 0.4, 0.4, 6, 0.3), (0., 0.5, 0.7, 3, 0.1)]:
+            mi, sc = native.small_mining_match(x, *attrs[:3], int(attrs[3]), attrs[4], impl="reference")
+            key = "d%d_%d" % (i, int(attrs[3]))
+            dense[key + "_x"] = x
+            dense[key + "_attrs"] = np.array(attrs)
+            dense[key + "_match"] = mi
+            dense[key + "_scores"] = sc
+    np.savez_compressed(os.path.join(OUT, "smm_dense_reference.npz"), **dense)
+
+    # ---- anchors: closed-form facts of SURVEY 8(c)(3) ----------------------------------------
+    enc = R.AnchorEncoder(0.4, 0.4, [0.1, 0.1, 0.2, 0.2])
+    facts = {}
+    for kind, size, border in [("s3fd", (640, 640), None), ("dan", (640, 640), None), ("s3fd", (1600, 1600), 0.),
+                               ("s3fd", (640, 640), 0.)]:
+        a = synthetic.build_anchors(enc, synthetic.pyramid_config(kind, size, border=border))
+        key = "%s_%d_%s" % (kind, size[0], "train" if border is None else "eval")
+        facts[key + "_n"] = np.int64(a[0].shape[0])
+        facts[key + "_first"] = np.array([v[0] for v in a[:4]], np.float32)
+        facts[key + "_last"] = np.array([v[-1] for v in a[:4]], np.float32)
+        facts[key + "_inside"] = np.int64(a[4].sum())
+        facts[key + "_sum"] = np.array([np.float64(v.astype(np.float64).sum()) for v in a[:4]])
+    np.savez(os.path.join(OUT, "anchor_facts.npz"), **facts)
+
+    # ---- encode goldens: BASELINE config 1 (S3FD 640, batch 1) + DAN + adversarial -----------
+    s3fd = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd"))
+    dan = synthetic.build_anchors(enc, synthetic.pyramid_config("dan"))
+    cases = {}
+
+    def add(name, anchors, gt, pos, ign, mining, pa=None):
+        e = R.AnchorEncoder(pos, ign, [0.1, 0.1, 0.2, 0.2])
+        if pa is None:
+            res = e.encode_anchors(gt, *anchors, match_mining=mining, mining_impl="reference", return_match=True)
+        else:
+            res = e.encode_pa_anchors(gt, *anchors, ign, pos, match_mining=mining, scale=pa, mining_impl="reference",
+                                      return_match=True)
+        cases[name + "__gt"] = gt
+        cases[name + "__cfg"] = np.array([pos, ign, 1.0 if mining else 0.0, -1.0 if pa is None else pa])
+        for k, v in pack_encode(res).items():
+            cases[name + "__" + k] = v
+
+    add("s3fd_mining_m12", s3fd, synthetic.gen_faces(3, 12, min_faces=12), 0.4, 0.4, True)
+    add("s3fd_mining_m50", s3fd, synthetic.gen_faces(7, 50, min_faces=50), 0.4, 0.4, True)
+    add("s3fd_mining_snap", s3fd, synthetic.gen_faces(11, 30, snap=4.0, min_faces=30), 0.4, 0.4, True)
+    add("s3fd_dual_m12_unittest", s3fd, synthetic.gen_faces(3, 12, min_faces=12), 0.5, 0.5, False)
+    add("s3fd_mining_empty", s3fd, synthetic.gen_adversarial("empty"), 0.4, 0.4, True)
+    add("dan_dual_m50", dan, synthetic.gen_faces(5, 50, min_faces=50), 0.35, 0.35, False)
+    add("dan_dual_snap", dan, synthetic.gen_faces(13, 30, snap=1.0, min_faces=30), 0.35, 0.35, False)
+    add("pb_head_dual_scale2", s3fd, synthetic.gen_faces(17, 20, min_faces=20), 0.35, 0.35, False, pa=2.0)
+    np.savez_compressed(os.path.join(OUT, "encode_goldens.npz"), **cases)
+
+    # ---- decode round trip of SURVEY 8(c)(4) ----------------------------------------------------
+    e = R.AnchorEncoder(0.5, 0.5, [0.1, 0.1, 0.2, 0.2])
+    a0 = [v[:1] for v in s3fd[:4]]
+    gt = np.array([[3, 2, 20, 17]], np.float32)
+    acy, acx, ah, aw = e.point2center(*a0)
+    gcy, gcx, gh, gw = e.point2center(*[gt[:, i] for i in range(4)])
+    t = np.stack([(gcy - acy) / ah / np.float32(.1), (gcx - acx) / aw / np.float32(.1),
+                  R.logf(gh / ah) / np.float32(.2), R.logf(gw / aw) / np.float32(.2)], -1).astype(np.float32)
+    np.savez(os.path.join(OUT, "decode_roundtrip.npz"), gt=gt, targets=t, decoded=e.decode_anchors(t, *a0))
+
+    # ---- postprocess golden (640, C=2) -----------------------------------------------------------
+    eval_anchors = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", border=0.))
+    an = np.stack(eval_anchors[:4], -1)
+    cls, loc, faces = synthetic.gen_predictions(1, an, max_faces=40)
+    boxes = e.decode_anchors(loc, *eval_anchors[:4])
+    sb, ss, idx = R.parse_by_class([640, 640], cls, boxes, 2, 0.01, 0, 5000, 750, 0.3, return_indices=True)
+    np.savez_compressed(os.path.join(OUT, "postprocess_golden.npz"), image_index=np.int64(1), max_faces=np.int64(40),
+                        boxes=sb[1], scores=ss[1], topk_index=idx[1][0][:int((ss[1] > 0).sum()) + 2000],
+                        keep=idx[1][1])
+    print("golden fixtures written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print("  %-32s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,551 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every test calls the CUDA path through the
+python mirror of the reference API -> ctypes -> C ABI (libdan_b200.so) and compares with the CPU oracle on
+the same seeded inputs and with the committed golden fixtures.
+
+Bar: bit-exact (assert_array_equal) for match indices, labels, scores-as-bits, keep-lists and indices;
+encoded/decoded fp32 offsets are ALSO compared bit-exact against the oracle (both sides evaluate the same
+Cephes exp/log sequence without fma), which is stricter than the 1e-5 relative tolerance of BASELINE.json."""
+import os
+
+import numpy as np
+import pytest
+
+from dan_b200 import synthetic
+
+from conftest import to_dev
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PS = [0.1, 0.1, 0.2, 0.2]
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _gpu_anchors(cfg, device):
+    from dan_b200.utility import anchor_manipulator as am
+    enc = am.AnchorEncoder(0.4, 0.4, PS)
+    return synthetic.build_anchors(enc, cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 anchors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,size,border,clip", [("s3fd", (640, 640), None, False), ("dan", (640, 640), None, False),
+                                                   ("s3fd", (1600, 1600), 0., False), ("dan", (800, 1024), 0., True),
+                                                   ("s3fd", (333, 517), 8., True)])
+def test_anchors_bit_exact(cuda, oracle, kind, size, border, clip):
+    cfg = synthetic.pyramid_config(kind, size, border=border, clip=clip)
+    ref = synthetic.build_anchors(oracle.AnchorEncoder(0.4, 0.4, PS), cfg)
+    got = _gpu_anchors(cfg, cuda)
+    for r, g in zip(ref[:4], got[:4]):
+        np.testing.assert_array_equal(_np(g), r)
+    np.testing.assert_array_equal(_np(got[4]), ref[4])
+
+
+def test_anchors_multi_depth_and_offsets(cuda, oracle):
+    from dan_b200.utility import anchor_manipulator as am
+    args = dict(scales=[(16., 24.), (64.,)], extra=[(20.,), ()], ratios=[(1., 2., 0.5), (0.8, 1.3)])
+    outs = []
+    for enc in (oracle.AnchorEncoder(0.5, 0.5, PS), am.AnchorEncoder(0.5, 0.5, PS)):
+        hs, ws, ds = [], [], []
+        for i in range(2):
+            h, w, d = enc.get_anchors_width_height(args["scales"][i], args["extra"][i], args["ratios"][i])
+            hs.append(h), ws.append(w), ds.append(d)
+        assert ds == [7, 2]
+        outs.append(enc.get_all_anchors([120, 200], hs, ws, ds, [(0.5, 0.25), 0.5], [(30, 50), (8, 13)], [4, 16],
+                                        [4., 0.], [False, True]))
+    for r, g in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(_np(g), r)
+    # generate_anchors_by_offset of one layer, [H*W, depth]
+    e_ref, e_gpu = oracle.AnchorEncoder(0.5, 0.5, PS), am.AnchorEncoder(0.5, 0.5, PS)
+    h, w, d = e_ref.get_anchors_width_height((32.,), (40.,), (1., 2.))
+    r = e_ref.generate_anchors_by_offset(h, w, d, [100, 100], (7, 9), 8, offset=0.5)
+    g = e_gpu.generate_anchors_by_offset(h, w, d, [100, 100], (7, 9), 8, offset=0.5)
+    for a, b in zip(r, g):
+        assert tuple(b.shape) == a.shape == (63, 3)
+        np.testing.assert_array_equal(_np(b), a)
+    assert e_gpu.get_anchors_count(3, (7, 9)) == (63, 189)
+
+
+# ------------------------------------------------------------------------------------------------
+# a6 IoU matrix
+# ------------------------------------------------------------------------------------------------
+def test_iou_matrix_bit_exact(cuda, oracle, s3fd_anchors_np):
+    from dan_b200.utility import anchor_manipulator as am
+    a = np.stack(s3fd_anchors_np[:4], -1)
+    for gt in (synthetic.gen_faces(2, 50, min_faces=50), synthetic.gen_faces(4, 30, snap=1.0, min_faces=30),
+               synthetic.gen_adversarial("outside"), synthetic.gen_adversarial("anchor_identical")):
+        ref = oracle.iou_matrix(a, gt)
+        got = am.iou_matrix(to_dev(a, cuda), to_dev(gt, cuda))
+        np.testing.assert_array_equal(_np(got), ref)
+        np.testing.assert_array_equal(_np(am.intersection(to_dev(a, cuda), to_dev(gt, cuda))), oracle.intersection(a, gt))
+    np.testing.assert_array_equal(_np(am.areas(to_dev(a, cuda))), oracle.areas(a))
+
+
+# ------------------------------------------------------------------------------------------------
+# a8 SmallMiningMatch on a dense matrix (the custom-op boundary)
+# ------------------------------------------------------------------------------------------------
+def test_small_mining_match_known_answers(cuda):
+    from dan_b200.utility import custom_op
+    g = np.load(os.path.join(GOLD, "smm_known_answers.npz"))
+    m, s = custom_op.small_mining_match(to_dev(g["test_op_overlaps"], cuda), 0., 0.6, 0.6, 5, 0.1)
+    assert _np(m).tolist() == [4, 2, 1, 3, 3] and m.dtype.is_floating_point is False
+    np.testing.assert_array_equal(_np(s), g["test_op_scores"])
+    m, s = custom_op.small_mining_match(to_dev(g["tie_overlaps"], cuda), 0., .5, .5, 3, .3)
+    np.testing.assert_array_equal(_np(m), g["tie_match"])        # libstdc++ heap order on a straddling tie
+    np.testing.assert_array_equal(_np(s), g["tie_scores"])
+
+
+def test_small_mining_match_reference_goldens(cuda):
+    from dan_b200.utility import custom_op
+    g = np.load(os.path.join(GOLD, "smm_dense_reference.npz"))
+    for k in sorted(k[:-2] for k in g.files if k.endswith("_x")):
+        a = g[k + "_attrs"]
+        m, s = custom_op.small_mining_match(to_dev(g[k + "_x"], cuda), float(a[0]), float(a[1]), float(a[2]), int(a[3]), float(a[4]))
+        np.testing.assert_array_equal(_np(m), g[k + "_match"], err_msg=k)
+        np.testing.assert_array_equal(_np(s), g[k + "_scores"], err_msg=k)
+
+
+def test_small_mining_match_random_vs_oracle(cuda, oracle):
+    from dan_b200.utility import custom_op
+    rng = np.random.default_rng(11)
+    for case in range(40):
+        n, m = int(rng.integers(1, 3000)), int(rng.integers(1, 90))
+        x = rng.uniform(0, 1, (n, m)).astype(np.float32)
+        x[x < rng.uniform(0.2, 0.95)] = 0
+        if case % 2:
+            lv = int(rng.integers(2, 40))
+            x = (np.round(x * lv) / lv).astype(np.float32)
+        if case % 7 == 0:
+            x[:, int(rng.integers(0, m))] = 0            # all-zero column: ties with every anchor (T7)
+        attrs = (0., 0.4, float(rng.choice([0.4, 0.6])), int(rng.integers(1, 9)), float(rng.choice([0.0, 0.05, 0.3])))
+        rm, rs = oracle.small_mining_match(x, *attrs)
+        gm, gs = custom_op.small_mining_match(to_dev(x, cuda), *attrs)
+        np.testing.assert_array_equal(_np(gm), rm, err_msg="case %d" % case)
+        np.testing.assert_array_equal(_np(gs), rs, err_msg="case %d" % case)
+
+
+def test_small_mining_match_bucket_overflow(cuda, oracle):
+    """> 64 compensation candidates for one GT: the spill path must agree too (incl. a straddling tie)."""
+    from dan_b200.utility import custom_op
+    rng = np.random.default_rng(5)
+    n = 1000
+    x = np.zeros((n, 3), np.float32)
+    x[:, 0] = rng.uniform(0.31, 0.39, n)          # nobody reaches pos=0.4, everybody is a candidate of GT 0
+    x[:, 1] = np.round(rng.uniform(0.31, 0.39, n) * 50) / 50
+    x[5, 2] = 0.9
+    for attrs in [(0., 0.4, 0.4, 6, 0.3), (0., 0.4, 0.4, 200, 0.3)]:
+        rm, rs = oracle.small_mining_match(x, *attrs)
+        gm, gs = custom_op.small_mining_match(to_dev(x, cuda), *attrs)
+        np.testing.assert_array_equal(_np(gm), rm)
+        np.testing.assert_array_equal(_np(gs), rs)
+
+
+def test_small_mining_match_errors(cuda):
+    import torch
+    from dan_b200 import _lib
+    from dan_b200.utility import custom_op
+    x = torch.zeros((8, 3), device=cuda)
+    for bad in [(-0.1, .4, .4, 6, .3), (0., 0., .4, 6, .3), (0., .5, .4, 6, .3), (0., .4, 1., 6, .3), (0., .4, .4, 0, .3),
+                (0., .4, .4, 6, 1.)]:
+        with pytest.raises(_lib.DanError) as e:
+            custom_op.small_mining_match(x, *bad)
+        assert e.value.code == -1 and "Need Attr" in str(e.value)
+    with pytest.raises(_lib.DanError):
+        custom_op.small_mining_match(torch.zeros(8, device=cuda), 0., .4, .4, 6, .3)     # rank != 2 (:311)
+    m, s = custom_op.small_mining_match(torch.zeros((5, 0), device=cuda), 0., .4, .4, 6, .3)
+    assert _np(m).tolist() == [-2] * 5
+
+
+# ------------------------------------------------------------------------------------------------
+# a7 do_dual_max_match on a dense matrix
+# ------------------------------------------------------------------------------------------------
+def test_dual_max_match_vs_oracle(cuda, oracle):
+    from dan_b200.utility import anchor_manipulator as am
+    rng = np.random.default_rng(13)
+    for case in range(40):
+        n, m = int(rng.integers(1, 3000)), int(rng.integers(1, 90))
+        x = rng.uniform(0, 1, (n, m)).astype(np.float32)
+        x[x < rng.uniform(0.2, 0.95)] = 0
+        if case % 2:
+            lv = int(rng.integers(2, 40))
+            x = (np.round(x * lv) / lv).astype(np.float32)
+        if case % 5 == 0:
+            x[:, int(rng.integers(0, m))] = 0
+        kw = dict(ignore_between=bool(case % 3), gt_max_first=bool(case % 4))
+        low, high = (0.35, 0.35) if case % 2 else (0.3, 0.5)
+        rm, rs = oracle.do_dual_max_match(x, low, high, **kw)
+        gm, gs = am.do_dual_max_match(to_dev(x, cuda), low, high, **kw)
+        assert gm.dtype.itemsize == 8
+        np.testing.assert_array_equal(_np(gm), rm, err_msg="case %d %s" % (case, kw))
+        np.testing.assert_array_equal(_np(gs), rs, err_msg="case %d %s" % (case, kw))
+
+
+# ------------------------------------------------------------------------------------------------
+# a9 / a10 fused encode
+# ------------------------------------------------------------------------------------------------
+def _check_encode(ref, got, name=""):
+    targets, labels, scores, matched = [_np(t) for t in got[:4]]
+    np.testing.assert_array_equal(labels, ref[1], err_msg=name + " labels")
+    np.testing.assert_array_equal(scores, ref[2], err_msg=name + " scores")
+    np.testing.assert_array_equal(targets, ref[0], err_msg=name + " targets")
+    np.testing.assert_array_equal(matched, ref[3], err_msg=name + " matched_gt")
+    assert labels.dtype == np.int64 and targets.dtype == np.float32
+
+
+def test_encode_goldens(cuda, s3fd_anchors_np, dan_anchors_np):
+    """fixtures produced with the REFERENCE's own matcher functor (tests/golden/make_golden.py)."""
+    from dan_b200.utility import anchor_manipulator as am
+    g = np.load(os.path.join(GOLD, "encode_goldens.npz"))
+    for name in sorted(k[:-4] for k in g.files if k.endswith("__gt")):
+        pos, ign, mining, pa = g[name + "__cfg"]
+        anchors_np = dan_anchors_np if name.startswith("dan") else s3fd_anchors_np
+        anchors = [to_dev(v, cuda) for v in anchors_np]
+        e = am.AnchorEncoder(float(pos), float(ign), PS)
+        gt = to_dev(g[name + "__gt"], cuda)
+        if pa < 0:
+            t, l, s, mg = e.encode_anchors(gt, *anchors, match_mining=bool(mining))
+        else:
+            t, l, s, mg = e.encode_pa_anchors(gt, *anchors, float(ign), float(pos), match_mining=bool(mining), scale=float(pa))
+        labels = np.zeros(l.shape[0], np.int64)
+        labels[g[name + "__nonzero_rows"]] = g[name + "__nonzero_labels"]
+        np.testing.assert_array_equal(_np(l), labels, err_msg=name)
+        np.testing.assert_array_equal(_np(s), g[name + "__scores"], err_msg=name)
+        rows = g[name + "__pos_rows"]
+        np.testing.assert_array_equal(_np(t)[rows], g[name + "__pos_targets"], err_msg=name)
+        np.testing.assert_array_equal(_np(mg)[rows], g[name + "__pos_matched"], err_msg=name)
+        assert not _np(t)[labels != 1].any() and not _np(mg)[labels != 1].any()
+
+
+@pytest.mark.parametrize("mining", [True, False])
+def test_encode_per_image_vs_oracle(cuda, oracle, s3fd_anchors_np, mining):
+    from dan_b200.utility import anchor_manipulator as am
+    thr = 0.4 if mining else 0.5
+    e_ref, e_gpu = oracle.AnchorEncoder(thr, thr, PS), am.AnchorEncoder(thr, thr, PS)
+    anchors = [to_dev(v, cuda) for v in s3fd_anchors_np]
+    gts = [synthetic.gen_faces(i, 50) for i in range(20, 26)]
+    gts += [synthetic.gen_faces(i, 50, snap=s) for i, s in ((30, 1.0), (31, 4.0), (32, 4.0), (33, 8.0))]
+    gts += [synthetic.gen_adversarial(k) for k in ("empty", "outside", "duplicate", "anchor_identical", "tiny", "huge")]
+    for i, gt in enumerate(gts):
+        ref = e_ref.encode_anchors(gt, *s3fd_anchors_np, match_mining=mining)
+        got = e_gpu.encode_anchors(to_dev(gt, cuda), *anchors, match_mining=mining)
+        _check_encode(ref, got, "gt set %d" % i)
+
+
+def test_encode_inside_mask_and_debug(cuda, oracle):
+    """eval-style border 0 -> 2424 anchors masked out; debug=True returns raw anchors."""
+    from dan_b200.utility import anchor_manipulator as am
+    cfg = synthetic.pyramid_config("s3fd", border=0.)
+    a_np = synthetic.build_anchors(oracle.AnchorEncoder(0.4, 0.4, PS), cfg)
+    assert int(a_np[4].sum()) == 31701
+    a = [to_dev(v, cuda) for v in a_np]
+    for mining in (True, False):
+        for gt in (synthetic.gen_faces(41, 50), synthetic.gen_adversarial("outside"), synthetic.gen_adversarial("huge")):
+            for debug in (False, True):
+                ref = oracle.AnchorEncoder(0.4, 0.4, PS).encode_anchors(gt, *a_np, match_mining=mining, debug=debug)
+                got = am.AnchorEncoder(0.4, 0.4, PS).encode_anchors(to_dev(gt, cuda), *a, match_mining=mining, debug=debug)
+                _check_encode(ref, got)
+
+
+def test_encode_pa_anchors_vs_oracle(cuda, oracle, s3fd_anchors_np):
+    """PyramidBox: face (mining, scale 1), head (dual, scale 2, anchors[N0:]), body (dual, scale 4, anchors[N0+N1:])
+    train_pb.py:205-225."""
+    from dan_b200.utility import anchor_manipulator as am
+    e_ref, e_gpu = oracle.AnchorEncoder(0.4, 0.4, PS), am.AnchorEncoder(0.4, 0.4, PS)
+    n0, n1 = 160 * 160, 80 * 80
+    for seed in (50, 51):
+        gt = synthetic.gen_faces(seed, 40)
+        for start, ign, pos, mining, scale in [(0, 0.4, 0.4, True, 1.), (n0, 0.35, 0.35, False, 2.), (n0 + n1, 0.35, 0.35, False, 4.)]:
+            sl_np = [v[start:] for v in s3fd_anchors_np]
+            sl = [to_dev(v, cuda) for v in sl_np]
+            ref = e_ref.encode_pa_anchors(gt, *sl_np, ign, pos, match_mining=mining, scale=scale)
+            got = e_gpu.encode_pa_anchors(to_dev(gt, cuda), *sl, ign, pos, match_mining=mining, scale=scale)
+            _check_encode(ref, got, "start %d scale %g" % (start, scale))
+
+
+def test_encode_batch_matches_per_image(cuda, oracle, dan_anchors_np):
+    """config-3 style: DAN anchors, dual matcher 0.35, dense tiny faces (up to 1000 / image), CSR batch with an
+    empty image in the middle; also checks the int32 match output."""
+    from dan_b200.utility import anchor_manipulator as am
+    e_ref, e_gpu = oracle.AnchorEncoder(0.35, 0.35, PS), am.AnchorEncoder(0.35, 0.35, PS)
+    anchors = [to_dev(v, cuda) for v in dan_anchors_np]
+    gts = [synthetic.gen_dense_tiny(0, lo=990, hi=1000), synthetic.gen_adversarial("empty"), synthetic.gen_faces(60, 50),
+           synthetic.gen_dense_tiny(1, lo=200, hi=260), synthetic.gen_faces(61, 3, snap=4.0)]
+    cat, offs = synthetic.to_csr(gts)
+    res = e_gpu.encode_anchors_batch(to_dev(cat, cuda), to_dev(offs, cuda), *anchors, match_mining=False, want_match=True)
+    assert tuple(res.targets.shape) == (5, 34125, 4) and tuple(res.labels.shape) == (5, 34125)
+    for b, gt in enumerate(gts):
+        ref = e_ref.encode_anchors(gt, *dan_anchors_np, match_mining=False, return_match=True)
+        _check_encode(ref, [res.targets[b], res.labels[b], res.scores[b], res.matched_gt[b]], "image %d" % b)
+        np.testing.assert_array_equal(_np(res.match[b]), ref[4].astype(np.int32))
+
+
+def test_encode_batch_mining_config2(cuda, oracle, s3fd_anchors_np):
+    """config 2: S3FD 640, mining, thresholds 0.4/0.4, batch 32, <= 50 faces / image."""
+    from dan_b200.utility import anchor_manipulator as am
+    e_ref, e_gpu = oracle.AnchorEncoder(0.4, 0.4, PS), am.AnchorEncoder(0.4, 0.4, PS)
+    anchors = [to_dev(v, cuda) for v in s3fd_anchors_np]
+    gts = [synthetic.gen_faces(100 + i, 50, snap=(2.0 if i % 8 == 7 else 0.0)) for i in range(32)]
+    cat, offs = synthetic.to_csr(gts)
+    res = e_gpu.encode_all_anchors(to_dev(cat, cuda), to_dev(offs, cuda), *anchors, match_mining=True, want_match=True)
+    n_comp = 0
+    for b, gt in enumerate(gts):
+        ref = e_ref.encode_anchors(gt, *s3fd_anchors_np, match_mining=True, return_match=True)
+        _check_encode(ref, [res.targets[b], res.labels[b], res.scores[b], res.matched_gt[b]], "image %d" % b)
+        np.testing.assert_array_equal(_np(res.match[b]), ref[4].astype(np.int32))
+        n_comp += int(((ref[1] == 1) & (ref[2] < 0.4)).sum())
+    assert n_comp > 0     # the compensation stage really fired in this batch
+
+
+def test_encode_roundtrip_property_full_size(cuda, s3fd_anchors_np):
+    """size-independent property at BASELINE config-3 scale (batch 64): decoding the encoded targets of every
+    positive anchor returns its matched GT box; labels/targets/matched are consistent."""
+    import torch
+    from dan_b200.utility import anchor_manipulator as am
+    e = am.AnchorEncoder(0.35, 0.35, PS)
+    anchors = [to_dev(v, cuda) for v in s3fd_anchors_np]
+    gts = [synthetic.gen_dense_tiny(200 + i) if i % 2 else synthetic.gen_faces(200 + i, 50) for i in range(64)]
+    cat, offs = synthetic.to_csr(gts)
+    res = e.encode_anchors_batch(to_dev(cat, cuda), to_dev(offs, cuda), *anchors, match_mining=False, want_match=True)
+    dec = e.batch_decode_anchors(res.targets, *anchors[:4])
+    pos = res.labels == 1
+    assert int(pos.sum()) > 64
+    assert torch.equal(pos, res.match >= 0) and torch.equal(res.labels == -1, res.match == -2)
+    torch.testing.assert_close(dec[pos], res.matched_gt[pos], rtol=1e-5, atol=2e-3)
+    assert not res.targets[~pos].any() and not res.matched_gt[~pos].any()
+    # matched GT indices stay inside the image's own CSR segment
+    offs_l = offs.tolist()
+    for b in (0, 1, 63):
+        m = res.match[b]
+        assert int(m.max()) < offs_l[b + 1] - offs_l[b] and int(m.min()) >= -2
+    # gathered matched_gt equals gt[match]
+    b = 5
+    gt_b = to_dev(gts[b], cuda)
+    m = res.match[b]
+    assert torch.equal(res.matched_gt[b][m >= 0], gt_b[m[m >= 0].long()])
+
+
+# ------------------------------------------------------------------------------------------------
+# a11 decode
+# ------------------------------------------------------------------------------------------------
+def test_decode_bit_exact(cuda, oracle, s3fd_anchors_np):
+    from dan_b200.utility import anchor_manipulator as am
+    rng = np.random.default_rng(17)
+    pred = rng.normal(0, 1.5, (3, 34125, 4)).astype(np.float32)
+    pred[0, :100] = 0
+    pred[1, :50, 2:] = 30.0          # large exp arguments
+    e_ref, e_gpu = oracle.AnchorEncoder(None, None, PS), am.AnchorEncoder(None, None, PS)
+    anchors = [to_dev(v, cuda) for v in s3fd_anchors_np[:4]]
+    np.testing.assert_array_equal(_np(e_gpu.batch_decode_anchors(to_dev(pred, cuda), *anchors)),
+                                  e_ref.batch_decode_anchors(pred, *s3fd_anchors_np[:4]))
+    np.testing.assert_array_equal(_np(e_gpu.decode_anchors(to_dev(pred[2], cuda), *anchors)),
+                                  e_ref.decode_anchors(pred[2], *s3fd_anchors_np[:4]))
+    g = np.load(os.path.join(GOLD, "decode_roundtrip.npz"))
+    np.testing.assert_array_equal(_np(e_gpu.decode_anchors(to_dev(g["targets"], cuda), *[a[:1] for a in anchors])), g["decoded"])
+
+
+# ------------------------------------------------------------------------------------------------
+# a12-a18 bbox_util
+# ------------------------------------------------------------------------------------------------
+def test_bbox_util_elementwise(cuda, oracle):
+    from dan_b200 import functional as F
+    from dan_b200.utility import bbox_util as bu
+    rng = np.random.default_rng(19)
+    n = 5000
+    logits = rng.normal(0, 4, (n, 3)).astype(np.float32)
+    boxes = (rng.uniform(-50, 700, (n, 4))).astype(np.float32)
+    sm_ref = oracle.softmax(logits)
+    sm = F.softmax(to_dev(logits, cuda))
+    np.testing.assert_array_equal(_np(sm), sm_ref)
+    sb_ref, ss_ref = oracle.select_bboxes(sm_ref, boxes, 3, 0.3)
+    sb, ss = bu.select_bboxes(sm, to_dev(boxes, cuda), 3, 0.3)
+    for c in (1, 2):
+        np.testing.assert_array_equal(_np(sb[c]), sb_ref[c])
+        np.testing.assert_array_equal(_np(ss[c]), ss_ref[c])
+    cols = [boxes[:, i] for i in range(4)]
+    dcols = [to_dev(c, cuda) for c in cols]
+    ref = oracle.clip_bboxes(*cols, 640, 480)
+    got = bu.clip_bboxes(*dcols, 640, 480)
+    for r, g in zip(ref, got):
+        np.testing.assert_array_equal(_np(g), r)
+    ref = oracle.filter_bboxes(ss_ref[1], *ref, 12.5)
+    got = bu.filter_bboxes(ss[1], *got, 12.5)
+    for r, g in zip(ref, got):
+        np.testing.assert_array_equal(_np(g), r)
+    np.testing.assert_array_equal(_np(bu.bbox_point2center(to_dev(boxes, cuda))), oracle.bbox_point2center(boxes))
+    np.testing.assert_array_equal(_np(bu.bbox_center2point(to_dev(boxes, cuda))), oracle.bbox_center2point(boxes))
+
+
+@pytest.mark.parametrize("n,k", [(34125, 5000), (213294, 5000), (3000, 5000), (9000, 100), (1, 4), (8192, 8192)])
+def test_sort_bboxes_vs_oracle(cuda, oracle, n, k):
+    from dan_b200.utility import bbox_util as bu
+    rng = np.random.default_rng(n + k)
+    scores = rng.uniform(0, 1, n).astype(np.float32)
+    scores[rng.uniform(0, 1, n) < 0.7] = 0                     # many zero rows, like after select/filter
+    scores[::97] = np.float32(0.5)                             # exact ties -> lower index first
+    cols = [rng.uniform(0, 600, n).astype(np.float32) for _ in range(4)]
+    ref = oracle.sort_bboxes(scores, *cols, k)
+    got = bu.sort_bboxes(to_dev(scores, cuda), *[to_dev(c, cuda) for c in cols], k)
+    for r, g in zip(ref[:5], got):
+        assert g.shape[0] == k
+        np.testing.assert_array_equal(_np(g), r)
+
+
+@pytest.mark.parametrize("n,topk,thr", [(5000, 750, 0.3), (2000, 50, 0.5), (300, 750, 0.3), (64, 10, 0.0), (65, 100, 0.7)])
+def test_nms_bboxes_vs_oracle(cuda, oracle, n, topk, thr):
+    from dan_b200.utility import bbox_util as bu
+    rng = np.random.default_rng(n + topk)
+    centres = rng.uniform(0, 640, (max(n // 12, 1), 2))
+    c = centres[rng.integers(0, len(centres), n)] + rng.normal(0, 4, (n, 2))
+    wh = rng.uniform(8, 60, (n, 2))
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    boxes[::50] = boxes[::50][:, [2, 3, 0, 1]]                 # flipped corners are normalised by TF
+    boxes[::77, 2] = boxes[::77, 0]                            # zero-area boxes never suppress
+    scores = rng.permutation(n).astype(np.float32) / n
+    rs, rb, rk = oracle.nms_bboxes_with_padding(scores, boxes, topk, thr)
+    gs, gb = bu.nms_bboxes_with_padding(to_dev(scores, cuda), to_dev(boxes, cuda), topk, thr)
+    np.testing.assert_array_equal(_np(gs), rs)
+    np.testing.assert_array_equal(_np(gb), rb)
+    vs, vb = bu.nms_bboxes(to_dev(scores, cuda), to_dev(boxes, cuda), topk, thr)
+    np.testing.assert_array_equal(_np(vs), scores[rk])
+    np.testing.assert_array_equal(_np(vb), boxes[rk])
+
+
+def test_nms_score_ties_are_stable(cuda, oracle):
+    """documented tie policy T6: equal scores keep input order (oracle tie='stable')."""
+    from dan_b200 import functional as F
+    rng = np.random.default_rng(23)
+    n = 400
+    c = rng.uniform(0, 200, (n, 2))
+    boxes = np.concatenate([c, c + rng.uniform(10, 50, (n, 2))], 1).astype(np.float32)
+    scores = (rng.integers(0, 6, n) / 8).astype(np.float32)
+    ref = oracle.tf_non_max_suppression(boxes, scores, 100, 0.3, tie="stable")
+    _, _, keep, cnt = F.nms_boxes(to_dev(scores, cuda), to_dev(boxes, cuda), 100, 0.3)
+    assert int(cnt.item()) == len(ref)
+    np.testing.assert_array_equal(_np(keep)[:len(ref)], ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# a17 fused parse_by_class
+# ------------------------------------------------------------------------------------------------
+def _oracle_parse(oracle, size, cls, loc, anchors_np, **kw):
+    enc = oracle.AnchorEncoder(None, None, PS)
+    boxes = enc.decode_anchors(loc, *anchors_np[:4])
+    p = dict(num_classes=cls.shape[1], select_threshold=0.01, min_size=0, keep_topk=5000, nms_topk=750, nms_threshold=0.3)
+    p.update(kw)
+    return boxes, oracle.parse_by_class(list(size), cls, boxes, p["num_classes"], p["select_threshold"], p["min_size"],
+                                        p["keep_topk"], p["nms_topk"], p["nms_threshold"], return_indices=True)
+
+
+def test_parse_by_class_golden(cuda, oracle):
+    from dan_b200.utility import bbox_util as bu
+    g = np.load(os.path.join(GOLD, "postprocess_golden.npz"))
+    enc = oracle.AnchorEncoder(None, None, PS)
+    a_np = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", border=0.))
+    cls, loc, _ = synthetic.gen_predictions(int(g["image_index"]), np.stack(a_np[:4], -1), max_faces=int(g["max_faces"]))
+    boxes = enc.decode_anchors(loc, *a_np[:4])
+    sb, ss = bu.parse_by_class([640, 640], to_dev(cls, cuda), to_dev(boxes, cuda), 2, 0.01, 0, 5000, 750, 0.3)
+    np.testing.assert_array_equal(_np(ss[1]), g["scores"])
+    np.testing.assert_array_equal(_np(sb[1]), g["boxes"])
+
+
+@pytest.mark.parametrize("size,faces", [((640, 640), 300), ((800, 800), 120), ((1024, 1024), 60)])
+def test_parse_by_class_batch_vs_oracle(cuda, oracle, size, faces):
+    """config 4: decode + threshold 0.01 + top-k 5000 + NMS 0.3 -> 750, anchors regenerated per size (border 0)."""
+    from dan_b200.utility import bbox_util as bu
+    cfg = synthetic.pyramid_config("s3fd", size, border=0.)
+    a_np = synthetic.build_anchors(oracle.AnchorEncoder(None, None, PS), cfg)
+    an = np.stack(a_np[:4], -1)
+    anchors = [to_dev(v, cuda) for v in a_np[:4]]
+    preds = [synthetic.gen_predictions(300 + i, an, size=size, max_faces=faces) for i in range(3)]
+    cls = np.stack([p[0] for p in preds])
+    loc = np.stack([p[1] for p in preds])
+    det = bu.parse_by_class_batch(list(size), to_dev(cls, cuda), 2, 0.01, 0, 5000, 750, 0.3, loc_pred=to_dev(loc, cuda),
+                                  anchors=anchors)
+    for b in range(3):
+        boxes, (sb, ss, idx) = _oracle_parse(oracle, size, cls[b], loc[b], a_np)
+        np.testing.assert_array_equal(_np(det.scores[b, 0]), ss[1], err_msg="image %d" % b)
+        np.testing.assert_array_equal(_np(det.boxes[b, 0]), sb[1], err_msg="image %d" % b)
+        top_idx, keep = idx[1]
+        k = int((ss[1] > 0).sum())
+        assert int(det.counts[b, 0]) == k
+        np.testing.assert_array_equal(_np(det.keep_pos[b, 0])[:len(keep)], keep)        # NMS keep-list, bit exact
+        np.testing.assert_array_equal(_np(det.anchor_index[b, 0])[:k], top_idx[keep[:k]])
+        assert (_np(det.anchor_index[b, 0])[k:] == -1).all()
+    # same result when parse_by_class is given decoded boxes (what the reference function literally takes)
+    boxes0, _ = _oracle_parse(oracle, size, cls[0], loc[0], a_np)
+    det2 = bu.parse_by_class_batch(list(size), to_dev(cls[:1], cuda), 2, 0.01, 0, 5000, 750, 0.3, bboxes_pred=to_dev(boxes0[None], cuda))
+    np.testing.assert_array_equal(_np(det2.scores[0]), _np(det.scores[0]))
+    np.testing.assert_array_equal(_np(det2.boxes[0]), _np(det.boxes[0]))
+
+
+def test_parse_by_class_variants(cuda, oracle):
+    """3 classes, min_size, small keep_topk (radix-select path: more survivors than keep_topk), low nms_topk."""
+    from dan_b200.utility import bbox_util as bu
+    cfg = synthetic.pyramid_config("s3fd", (640, 640), border=0.)
+    a_np = synthetic.build_anchors(oracle.AnchorEncoder(None, None, PS), cfg)
+    n = a_np[0].shape[0]
+    rng = np.random.default_rng(29)
+    cls = rng.normal(0, 2.0, (n, 3)).astype(np.float32)       # ~ everything passes the threshold
+    loc = rng.normal(0, 0.5, (n, 4)).astype(np.float32)
+    anchors = [to_dev(v, cuda) for v in a_np[:4]]
+    for kw in (dict(select_threshold=0.2, min_size=10, keep_topk=400, nms_topk=100, nms_threshold=0.45),
+               dict(select_threshold=0.0, min_size=0, keep_topk=5000, nms_topk=750, nms_threshold=0.3),
+               dict(select_threshold=0.999999, min_size=0, keep_topk=100, nms_topk=20, nms_threshold=0.3)):
+        boxes, (sb, ss, idx) = _oracle_parse(oracle, (640, 640), cls, loc, a_np, num_classes=3, **kw)
+        det = bu.parse_by_class_batch([640, 640], to_dev(cls[None], cuda), 3, kw["select_threshold"], kw["min_size"],
+                                      kw["keep_topk"], kw["nms_topk"], kw["nms_threshold"], loc_pred=to_dev(loc[None], cuda),
+                                      anchors=anchors)
+        for c in (1, 2):
+            np.testing.assert_array_equal(_np(det.scores[0, c - 1]), ss[c], err_msg=str(kw))
+            np.testing.assert_array_equal(_np(det.boxes[0, c - 1]), sb[c], err_msg=str(kw))
+            keep = idx[c][1]
+            np.testing.assert_array_equal(_np(det.keep_pos[0, c - 1])[:len(keep)], keep)
+
+
+def test_postprocess_properties_full_size(cuda):
+    """size-independent properties at 1600^2 (213 294 anchors), batch 4: sorted scores, counts consistent, kept boxes
+    mutually below the NMS threshold (no +1 IoU), idempotence of NMS on its own output."""
+    import torch
+    from dan_b200 import functional as F
+    from dan_b200.utility import anchor_manipulator as am, bbox_util as bu
+    size = (1600, 1600)
+    cfg = synthetic.pyramid_config("s3fd", size, border=0.)
+    anchors = synthetic.build_anchors(am.AnchorEncoder(None, None, PS), cfg)
+    assert anchors[0].numel() == 213294
+    an = np.stack([_np(a) for a in anchors[:4]], -1)
+    preds = [synthetic.gen_predictions(400 + i, an, size=size, max_faces=300) for i in range(4)]
+    cls = to_dev(np.stack([p[0] for p in preds]), cuda)
+    loc = to_dev(np.stack([p[1] for p in preds]), cuda)
+    det = bu.parse_by_class_batch(list(size), cls, 2, 0.01, 0, 5000, 750, 0.3, loc_pred=loc, anchors=anchors[:4])
+    for b in range(4):
+        k = int(det.counts[b, 0])
+        s, bx = det.scores[b, 0], det.boxes[b, 0]
+        assert 0 < k <= 750 and bool((s[:k] > 0.01).all()) and not s[k:].any() and not bx[k:].any()
+        assert bool((s[:k - 1] >= s[1:k]).all())
+        area = (bx[:k, 2] - bx[:k, 0]) * (bx[:k, 3] - bx[:k, 1])
+        ih = (torch.minimum(bx[:k, None, 2], bx[None, :k, 2]) - torch.maximum(bx[:k, None, 0], bx[None, :k, 0])).clamp(min=0)
+        iw = (torch.minimum(bx[:k, None, 3], bx[None, :k, 3]) - torch.maximum(bx[:k, None, 1], bx[None, :k, 1])).clamp(min=0)
+        iou = ih * iw / (area[:, None] + area[None, :] - ih * iw)
+        iou.fill_diagonal_(0)
+        assert float(iou.max()) <= 0.3 + 1e-5
+        s2, b2, keep2, cnt2 = F.nms_boxes(s[:k].contiguous(), bx[:k].contiguous(), 750, 0.3)
+        assert int(cnt2.item()) == k and torch.equal(s2[:k], s[:k])
+
+
+def test_postprocess_errors(cuda):
+    import torch
+    from dan_b200 import _lib
+    from dan_b200.utility import bbox_util as bu
+    cls = torch.zeros((1, 100, 2), device=cuda)
+    box = torch.zeros((1, 100, 4), device=cuda)
+    with pytest.raises(_lib.DanError):
+        bu.parse_by_class_batch([64, 64], cls, 2, -0.5, 0, 100, 10, 0.3, bboxes_pred=box)
+    with pytest.raises(_lib.DanError):
+        bu.parse_by_class_batch([64, 64], cls, 2, 0.1, 0, 100000, 10, 0.3, bboxes_pred=box)
+    with pytest.raises(TypeError):
+        bu.parse_by_class_batch([64, 64], cls.cpu(), 2, 0.1, 0, 100, 10, 0.3, bboxes_pred=box)      # no CPU fallback
+    det = bu.parse_by_class_batch([64, 64], cls, 2, 0.9, 0, 100, 10, 0.3, bboxes_pred=box)
+    assert int(det.counts.sum()) == 0 and not det.scores.any()
