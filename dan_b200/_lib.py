@@ -77,6 +77,9 @@ _SIGNATURES = {
     "dan_encode_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "dan_encode_batch": (ctypes.c_int, [ctypes.POINTER(EncodeParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp,
                                         c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_encode_batch_profile": (ctypes.c_int, [ctypes.POINTER(EncodeParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp,
+                                                c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp,
+                                                ctypes.POINTER(c_f32)]),
     "dan_decode_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(c_f32), c_vp, c_vp]),
     "dan_softmax": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "dan_select_bboxes": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
@@ -90,6 +93,9 @@ _SIGNATURES = {
     "dan_postprocess_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32, c_i32]),
     "dan_postprocess_batch": (ctypes.c_int, [ctypes.POINTER(PostprocessParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                              c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_postprocess_batch_profile": (ctypes.c_int, [ctypes.POINTER(PostprocessParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                                     c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp,
+                                                     ctypes.POINTER(c_f32)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -662,20 +662,42 @@ static void bind_workspace(EncArgs& A, void* workspace, const WsLayout& w) {
   A.spill = reinterpret_cast<HeapItem*>(base + w.spill);
 }
 
+// ev (optional, 4 events): recorded before pass 1 and after each pass, for the profile entry point
 template <bool DENSE>
-static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, cudaStream_t st) {
+static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, cudaStream_t st, cudaEvent_t* ev = nullptr) {
   const dim3 grid((A.n + kEncThreads - 1) / kEncThreads, batch);
+  if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   if (need_row) enc_pass1_kernel<DENSE, true><<<grid, kEncThreads, 0, st>>>(A);
   else enc_pass1_kernel<DENSE, false><<<grid, kEncThreads, 0, st>>>(A);
   DAN_LAUNCH_CHECK("enc_pass1_kernel");
+  if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
   if (mining) enc_pass2_kernel<DENSE, true><<<grid, kEncThreads, 0, st>>>(A);
   else enc_pass2_kernel<DENSE, false><<<grid, kEncThreads, 0, st>>>(A);
   DAN_LAUNCH_CHECK("enc_pass2_kernel");
+  if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
   if (mining) {
     enc_pass3_kernel<DENSE><<<batch, 32, 0, st>>>(A);
     DAN_LAUNCH_CHECK("enc_pass3_kernel");
   }
+  if (ev) DAN_CUDA(cudaEventRecord(ev[3], st));
   return DAN_OK;
+}
+
+// CUDA-event timing of a launch sequence (profile entry points only): creates n events, runs fn(ev), synchronises
+// on the last one and writes the n-1 intervals in milliseconds.
+template <typename Fn>
+static int timed_sequence(int n_events, float* h_ms, Fn fn) {
+  cudaEvent_t ev[8];
+  for (int i = 0; i < n_events; ++i) DAN_CUDA(cudaEventCreate(&ev[i]));
+  int rc = fn(ev);
+  if (rc == DAN_OK) {
+    cudaError_t e = cudaEventSynchronize(ev[n_events - 1]);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
+  }
+  if (rc == DAN_OK)
+    for (int i = 0; i + 1 < n_events; ++i) cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
+  for (int i = 0; i < n_events; ++i) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 }  // namespace dan
@@ -757,11 +779,11 @@ int dan_dual_max_match(const float* overlaps, int32_t num_anchors, int32_t num_g
   return run_passes<true>(A, false, !gt_max_first, 1, st);
 }
 
-int dan_encode_batch(const dan_encode_params* p, const float* a_ymin, const float* a_xmin, const float* a_ymax,
-                     const float* a_xmax, const uint8_t* inside_mask, int32_t num_anchors, const float* gt_boxes,
-                     const int32_t* gt_offsets, int32_t batch, int32_t total_gt, float* out_targets, int64_t* out_labels,
-                     float* out_scores, float* out_matched_gt, int32_t* out_match, void* workspace, size_t workspace_bytes,
-                     void* stream) {
+static int encode_core(const dan_encode_params* p, const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                       const float* a_xmax, const uint8_t* inside_mask, int32_t num_anchors, const float* gt_boxes,
+                       const int32_t* gt_offsets, int32_t batch, int32_t total_gt, float* out_targets, int64_t* out_labels,
+                       float* out_scores, float* out_matched_gt, int32_t* out_match, void* workspace, size_t workspace_bytes,
+                       void* stream, cudaEvent_t* ev) {
   DAN_REQUIRE(p != nullptr, DAN_ERR_INVALID_ARGUMENT, "params is NULL");
   DAN_REQUIRE(p->matcher == DAN_MATCH_DUAL || p->matcher == DAN_MATCH_MINING, DAN_ERR_INVALID_ARGUMENT, "unknown matcher %d", p->matcher);
   DAN_REQUIRE(num_anchors >= 0 && batch >= 0 && total_gt >= 0, DAN_ERR_INVALID_ARGUMENT, "negative size");
@@ -805,7 +827,29 @@ int dan_encode_batch(const dan_encode_params* p, const float* a_ymin, const floa
   A.match32 = out_match;
   bind_workspace(A, workspace, w);
   DAN_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));
-  return run_passes<false>(A, mining, !mining && !A.gt_max_first, batch, st);
+  return run_passes<false>(A, mining, !mining && !A.gt_max_first, batch, st, ev);
+}
+
+int dan_encode_batch(const dan_encode_params* p, const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                     const float* a_xmax, const uint8_t* inside_mask, int32_t num_anchors, const float* gt_boxes,
+                     const int32_t* gt_offsets, int32_t batch, int32_t total_gt, float* out_targets, int64_t* out_labels,
+                     float* out_scores, float* out_matched_gt, int32_t* out_match, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  return encode_core(p, a_ymin, a_xmin, a_ymax, a_xmax, inside_mask, num_anchors, gt_boxes, gt_offsets, batch, total_gt, out_targets,
+                     out_labels, out_scores, out_matched_gt, out_match, workspace, workspace_bytes, stream, nullptr);
+}
+
+int dan_encode_batch_profile(const dan_encode_params* p, const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                             const float* a_xmax, const uint8_t* inside_mask, int32_t num_anchors, const float* gt_boxes,
+                             const int32_t* gt_offsets, int32_t batch, int32_t total_gt, float* out_targets, int64_t* out_labels,
+                             float* out_scores, float* out_matched_gt, int32_t* out_match, void* workspace, size_t workspace_bytes,
+                             void* stream, float* h_pass_ms) {
+  DAN_REQUIRE(h_pass_ms != nullptr, DAN_ERR_INVALID_ARGUMENT, "h_pass_ms is NULL");
+  h_pass_ms[0] = h_pass_ms[1] = h_pass_ms[2] = 0.f;
+  return timed_sequence(4, h_pass_ms, [&](cudaEvent_t* ev) {
+    return encode_core(p, a_ymin, a_xmin, a_ymax, a_xmax, inside_mask, num_anchors, gt_boxes, gt_offsets, batch, total_gt, out_targets,
+                       out_labels, out_scores, out_matched_gt, out_match, workspace, workspace_bytes, stream, ev);
+  });
 }
 
 }  // extern "C"

@@ -436,11 +436,13 @@ static int enable_big_smem() {
   return DAN_OK;
 }
 
-static int run_nms(const PpArgs& A, int lists, cudaStream_t st) {
+static int run_nms(const PpArgs& A, int lists, cudaStream_t st, cudaEvent_t* ev = nullptr) {
   nms_mask_kernel<<<dim3(kMaskTilesPerList, lists), 64, 0, st>>>(A);
   DAN_LAUNCH_CHECK("nms_mask_kernel");
+  if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   nms_sweep_kernel<<<lists, 32, (size_t)A.nms_topk * 4, st>>>(A);
   DAN_LAUNCH_CHECK("nms_sweep_kernel");
+  if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
   return DAN_OK;
 }
 
@@ -465,10 +467,10 @@ size_t dan_nms_workspace_bytes(int64_t n, int32_t nms_topk) {
   return pp_layout(n, 1, n > 0 ? n : 1).total;
 }
 
-int dan_postprocess_batch(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
-                          const float* a_ymin, const float* a_xmin, const float* a_ymax, const float* a_xmax, int32_t num_anchors,
-                          int32_t batch, float* out_boxes, float* out_scores, int32_t* out_counts, int32_t* out_anchor_index,
-                          int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, void* stream) {
+static int postprocess_core(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
+                            const float* a_ymin, const float* a_xmin, const float* a_ymax, const float* a_xmax, int32_t num_anchors,
+                            int32_t batch, float* out_boxes, float* out_scores, int32_t* out_counts, int32_t* out_anchor_index,
+                            int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, void* stream, cudaEvent_t* ev) {
   DAN_REQUIRE(p != nullptr, DAN_ERR_INVALID_ARGUMENT, "params is NULL");
   DAN_REQUIRE(p->num_classes >= 2, DAN_ERR_INVALID_ARGUMENT, "num_classes must be >= 2 (class 0 is background), got %d", p->num_classes);
   DAN_REQUIRE(num_anchors >= 0 && batch >= 0, DAN_ERR_INVALID_ARGUMENT, "negative size");
@@ -514,13 +516,44 @@ int dan_postprocess_batch(const dan_postprocess_params* p, const float* cls_pred
   A.filler = 1;
   pp_bind(A, workspace, w);
   DAN_CUDA(cudaMemsetAsync(A.key_count, 0, (size_t)lists * 4, st));
+  if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   if (num_anchors > 0) {
     pp_filter_kernel<<<dim3((num_anchors + 255) / 256, batch), 256, 0, st>>>(A);
     DAN_LAUNCH_CHECK("pp_filter_kernel");
   }
+  if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
   topk_sort_kernel<true><<<lists, kSortThreads, kSortCap * 8, st>>>(A, nullptr, nullptr, 0);
   DAN_LAUNCH_CHECK("topk_sort_kernel");
-  return run_nms(A, lists, st);
+  if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
+  return run_nms(A, lists, st, ev ? ev + 3 : nullptr);
+}
+
+int dan_postprocess_batch(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
+                          const float* a_ymin, const float* a_xmin, const float* a_ymax, const float* a_xmax, int32_t num_anchors,
+                          int32_t batch, float* out_boxes, float* out_scores, int32_t* out_counts, int32_t* out_anchor_index,
+                          int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, void* stream) {
+  return postprocess_core(p, cls_pred, loc_pred, boxes_pred, a_ymin, a_xmin, a_ymax, a_xmax, num_anchors, batch, out_boxes, out_scores,
+                          out_counts, out_anchor_index, out_keep_pos, workspace, workspace_bytes, stream, nullptr);
+}
+
+int dan_postprocess_batch_profile(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred,
+                                  const float* boxes_pred, const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                                  const float* a_xmax, int32_t num_anchors, int32_t batch, float* out_boxes, float* out_scores,
+                                  int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos, void* workspace,
+                                  size_t workspace_bytes, void* stream, float* h_kernel_ms) {
+  DAN_REQUIRE(h_kernel_ms != nullptr, DAN_ERR_INVALID_ARGUMENT, "h_kernel_ms is NULL");
+  for (int i = 0; i < 4; ++i) h_kernel_ms[i] = 0.f;
+  cudaEvent_t ev[5];
+  for (int i = 0; i < 5; ++i) DAN_CUDA(cudaEventCreate(&ev[i]));
+  int rc = postprocess_core(p, cls_pred, loc_pred, boxes_pred, a_ymin, a_xmin, a_ymax, a_xmax, num_anchors, batch, out_boxes,
+                            out_scores, out_counts, out_anchor_index, out_keep_pos, workspace, workspace_bytes, stream, ev);
+  if (rc == DAN_OK && batch > 0) {
+    cudaError_t e = cudaEventSynchronize(ev[4]);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
+    else for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h_kernel_ms[i], ev[i], ev[i + 1]);
+  }
+  for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t keep_topk, float* out_scores, float* out_boxes,

@@ -19,6 +19,8 @@ Detections = namedtuple("Detections", ["boxes", "scores", "counts", "anchor_inde
 
 
 def _dev(t):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("dan_b200 operates on CUDA torch.Tensors only (no CPU fallback)")
     return t.device
 
 

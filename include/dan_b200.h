@@ -148,6 +148,18 @@ int dan_encode_batch(const dan_encode_params* h_params, const float* a_ymin, con
                      float* out_scores, float* out_matched_gt, int32_t* out_match, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Profiling variant (bench.py roofline): same work, but records CUDA events on `stream`
+ * around each launch, synchronises, and writes the duration in ms of pass 1 (column
+ * maxima), pass 2 (match + encode + all outputs) and pass 3 (mining compensation;
+ * 0 for the dual matcher) to h_pass_ms[3] (HOST pointer).  Not graph capturable. */
+int dan_encode_batch_profile(const dan_encode_params* h_params, const float* a_ymin,
+                             const float* a_xmin, const float* a_ymax, const float* a_xmax,
+                             const uint8_t* inside_mask, int32_t num_anchors, const float* gt_boxes,
+                             const int32_t* gt_offsets, int32_t batch, int32_t total_gt,
+                             float* out_targets, int64_t* out_labels, float* out_scores,
+                             float* out_matched_gt, int32_t* out_match, void* workspace,
+                             size_t workspace_bytes, void* stream, float* h_pass_ms);
+
 /* ------------------------------------------------------------------------- *
  * (a11) decode_anchors / batch_decode_anchors, anchor_manipulator.py:389-424.
  *       pred [B,N,4] (cy,cx,h,w offsets) -> out [B,N,4] boxes.
@@ -231,6 +243,16 @@ int dan_postprocess_batch(const dan_postprocess_params* h_params, const float* c
                           int32_t num_anchors, int32_t batch, float* out_boxes, float* out_scores,
                           int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Profiling variant: durations in ms of filter, top-k/sort, NMS mask, NMS sweep
+ * written to h_kernel_ms[4] (HOST pointer).  Synchronises; not graph capturable. */
+int dan_postprocess_batch_profile(const dan_postprocess_params* h_params, const float* cls_pred,
+                                  const float* loc_pred, const float* boxes_pred,
+                                  const float* a_ymin, const float* a_xmin, const float* a_ymax,
+                                  const float* a_xmax, int32_t num_anchors, int32_t batch,
+                                  float* out_boxes, float* out_scores, int32_t* out_counts,
+                                  int32_t* out_anchor_index, int32_t* out_keep_pos, void* workspace,
+                                  size_t workspace_bytes, void* stream, float* h_kernel_ms);
 
 #ifdef __cplusplus
 }
