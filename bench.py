@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the DAN anchor hot path (match + encode + decode + top-k + NMS) at 640^2.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic images PER GPU (weak scaling):
+  training side    S3FD 640x640 pyramid (34 125 anchors), encode_anchors(match_mining=True), thresholds 0.4/0.4,
+                   G1 ground truth with <= 50 faces / image                      (BASELINE.json configs[1])
+  evaluation side  decode + softmax + threshold 0.01 + top-k 5000 + NMS 0.3 -> 750 on G3 predictions
+                   (parse_by_class semantics, configs[3] at 640^2)
+  N > 1            images are sharded per rank (configs[4]: 8 x 32 = 256 images); one NCCL all-gather of the
+                   fixed-capacity detection slabs per step.
+`value` is timed with inputs resident in HBM (CUDA events, the step replayed as a CUDA graph, rotating input/output
+buffer sets larger than L2); `e2e` is timed through the public python API with HOST (pinned) buffers, H2D and D2H
+copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec anchor match+encode+decode+NMS @640^2"
+UNIT = "images/s"
+IMAGE = (640, 640)
+PP = (0.01, 0, 5000, 750, 0.3)      # select_threshold, min_size, keep_topk, nms_topk, nms_threshold
+CPU_CFG = dict(kind="s3fd", size=IMAGE, pos=0.4, ign=0.4, mining=True, max_gt=50, max_faces=300, pp=PP)
+KERNELS_PER_STEP = 7                # enc_pass1/2/3, pp_filter, topk_sort, nms_mask, nms_sweep
+
+
+def workload_config(batch, n_gpus, extra=None):
+    cfg = {"workload": "S3FD 640x640 (34125 anchors): mining encode of <=50 GT faces/image + decode/threshold 0.01/"
+                       "top-k 5000/NMS 0.3->750 of G3 predictions, batch %d per GPU" % batch,
+           "images_per_gpu": batch, "global_batch": batch * n_gpus, "num_anchors": 34125,
+           "parallelism": "per-image sharding, dp%d" % n_gpus}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the ONLY place bench.py touches oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_measure(images, steps, warmup, procs=None):
+    """The reference's CPU path (oracle/cpu_path.py) on all host cores: `steps` timed passes over `images` images."""
+    from oracle import cpu_path, native
+    native.build()
+    procs = procs or os.cpu_count() or 1
+    idx = list(range(images))
+    cpu_path.generate_inputs(CPU_CFG, idx, procs)
+    pool = cpu_path.CpuPool(CPU_CFG, procs)
+    for _ in range(warmup):
+        pool.run(idx)
+    walls, busy = [], 0.0
+    for _ in range(steps):
+        w, n, b = pool.run(idx)
+        walls.append(w)
+        busy += b
+    pool.close()
+    total = sum(walls)
+    return {"value": images * steps / total, "ms_per_step": 1e3 * total / steps, "cores": procs, "impl": pool.impl,
+            "images": images, "core_seconds_per_image": busy / (images * steps)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    procs = os.cpu_count() or 1
+    images = min(args.batch, max(2 * procs, 8))
+    r = cpu_measure(images, args.steps, max(args.warmup, 1), procs)
+    kind = "port"
+    sample = ("%d images/step x %d steps, %d worker processes (one image per task); numpy fp32 restatement of the TF graph ops"
+              " + %s SmallMiningMatch + restated tf.nn.top_k / non_max_suppression (TF 1.8 is not installable)"
+              % (images, args.steps, procs, "the reference's own compiled" if r["impl"] == "reference" else "ported"))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.batch, args.gpus, {"cpu_sample_images_per_step": images}),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_mhz_max_seen": max(sm), "sm_max_mhz": max(smax), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the CUDA arm
+# --------------------------------------------------------------------------------------------------
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes/launch of the dominant kernel from the committed ncu --set full capture (profiles/), else None."""
+    path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
+def run_cuda(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = args.batch
+
+    # ---- CPU baseline first (rank 0, N == 1 only): needs fork, so it runs before CUDA is initialised ----------
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        procs = os.cpu_count() or 1
+        images = max(4 * procs, 32)
+        r = cpu_measure(images, 5, 1, procs)
+        cpu_base = {"value": r["value"], "unit": UNIT, "cores": procs, "kind": "port",
+                    "sample": "%d images x 5 passes after 1 warm-up pass (%.0f core-seconds), %d worker processes; numpy restatement + %s "
+                              "SmallMiningMatch; %.1f ms per image per core" % (images, r["core_seconds_per_image"] * images * 5, procs,
+                                                                                "reference-compiled" if r["impl"] == "reference" else "ported",
+                                                                                1e3 * r["core_seconds_per_image"])}
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dan_b200 import _lib, functional as F, pipeline, synthetic
+    from dan_b200.utility import anchor_manipulator as am
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback for the product path"
+    _lib.lib()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- anchors, parameters ----------------------------------------------------------------------------------
+    ps = [0.1, 0.1, 0.2, 0.2]
+    enc = am.AnchorEncoder(0.4, 0.4, ps)
+    a_train = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", IMAGE))
+    a_eval = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", IMAGE, border=0.))
+    N = a_train[0].numel()
+    enc_params = F.encode_params(0.4, 0.4, ps, match_mining=True)
+    pp_params = F.postprocess_params(2, IMAGE, *PP, prior_scaling=ps)
+
+    # ---- synthetic inputs: B distinct images per rank; buffer set r holds them rolled by r ----------------------
+    an = np.stack([a.cpu().numpy() for a in a_eval[:4]], -1)
+    base = rank * B
+    gts = [synthetic.gen_faces(base + i, 50) for i in range(B)]
+    preds = [synthetic.gen_predictions(base + i, an, max_faces=300) for i in range(B)]
+    per_set = B * N * (8 + 16 + 44)          # cls + loc in, encode outputs out
+    R = args.sets if args.sets > 0 else max(4, int(np.ceil(3.0 * 126e6 / per_set)))
+    ws = _lib.Workspace()
+    sets = []
+    for r in range(R):
+        order = [(i + r) % B for i in range(B)]
+        cat, offs = synthetic.to_csr([gts[i] for i in order])
+        h = {"gt": torch.from_numpy(cat).pin_memory(), "offs": torch.from_numpy(offs).pin_memory(),
+             "cls": torch.from_numpy(np.stack([preds[i][0] for i in order])).pin_memory(),
+             "loc": torch.from_numpy(np.stack([preds[i][1] for i in order])).pin_memory()}
+        d = {k: v.to(dev) for k, v in h.items()}
+        hp = pipeline.HotPath(a_train[:4], a_train[4], enc_params, pp_params, anchors_eval=a_eval[:4], workspace=ws)
+        sets.append({"host": h, "dev": d, "hp": hp, "total_gt": int(offs[-1])})
+    total_gt_mean = float(np.mean([s["total_gt"] for s in sets]))
+
+    def run_set(s, profile=False):
+        return s["hp"].step(s["dev"]["gt"], s["dev"]["offs"], s["dev"]["cls"], s["dev"]["loc"], profile=profile)
+
+    # warm-up outside graphs (sizes the workspace, sets kernel attributes), then capture one CUDA graph per set
+    for s in sets:
+        run_set(s)
+    torch.cuda.synchronize()
+    graphs = []
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for s in sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    run_set(s)
+                graphs.append(g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+    def step(k):
+        s = sets[k % R]
+        if graphs:
+            graphs[k % R].replay()
+        else:
+            run_set(s)
+        if world > 1:
+            return s["hp"].gather(world)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps between barrier+sync ----------------------
+    # warm-up: at least W steps AND at least ~0.5 s of load so that the SM clocks have ramped up from idle
+    W, K = max(args.warmup, 3), args.steps
+    t_warm = time.time() + 0.5
+    k = 0
+    while k < W or time.time() < t_warm:
+        step(k)
+        k += 1
+        if k % 64 == 0:
+            torch.cuda.synchronize()
+    W = k
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(K):
+        step(W + k)
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    # keep the GPU busy a little longer so that the clock sampler sees the loaded state
+    t_end = time.time() + (1.0 if sampler else 0.0)
+    k = 0
+    while time.time() < t_end:
+        step(k)
+        k += 1
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * B * K / (elapsed_ms * 1e-3)
+
+    # ---- end to end: host buffers in, detections out, every step -------------------------------------------------
+    slab_words = sets[0]["hp"]._slab.words
+    h_out = torch.empty(slab_words, dtype=torch.float32).pin_memory()
+    h_npos = torch.empty(B, dtype=torch.int64).pin_memory()
+
+    def e2e_step(k):
+        s = sets[k % R]
+        for name in ("gt", "offs", "cls", "loc"):
+            s["dev"][name].copy_(s["host"][name], non_blocking=True)
+        step(k)
+        h_out.copy_(s["hp"]._slab.buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h_out
+
+    for k in range(3):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        e2e_step(3 + k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = sum(int(sets[0]["host"][n].numel() * sets[0]["host"][n].element_size()) for n in ("gt", "offs", "cls", "loc"))
+    d2h = slab_words * 4
+    e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * e2e_s / K,
+           "note": "pinned host GT + predictions copied in, detection slab copied out every step; encode targets stay on the "
+                   "device (consumed by the loss there)"}
+
+    # ---- per-kernel CUDA-event durations (profile entry points), cold buffers --------------------------------------
+    prof = {}
+    reps = max(10, R)
+    for k in range(reps):
+        _, _, ms = run_set(sets[k % R], profile=True)
+        for name, v in ms.items():
+            prof.setdefault(name, []).append(v)
+    kernel_ms = {name: statistics.mean(v[2:]) for name, v in prof.items()}
+    step_kernel_sum = sum(kernel_ms.values())
+    dom = max(kernel_ms, key=kernel_ms.get)
+    peak, peak_src = measured_hbm_peak()
+    enc_bytes = B * (44.0 * N) + 16.0 * total_gt_mean + 17.0 * N       # 44N + 16M + 17N/B per image
+    pp_bytes = B * 24.0 * N + B * 20.0 * 750
+    alg = {"enc_pass2": enc_bytes, "enc_pass1": 17.0 * N + 16.0 * total_gt_mean, "pp_filter": pp_bytes}
+    traffic = ncu_traffic()
+    roof_kernel = "enc_pass2"
+    achieved = alg[roof_kernel] / (kernel_ms[roof_kernel] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "enc_pass2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": (traffic or {}).get("enc_pass2_kernel"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[roof_kernel], "kernel_ms": kernel_ms[roof_kernel],
+                "share_of_step_kernel_time": kernel_ms[roof_kernel] / step_kernel_sum,
+                "longest_kernel": dom,
+                "pp_filter_achieved_gbs": alg["pp_filter"] / (kernel_ms["pp_filter"] * 1e-3) / 1e9}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": workload_config(B, world, {"l2_policy": "%d rotating input/output buffer sets (%.0f MB) > 126 MB L2" %
+                                                                  (R, R * per_set / 1e6),
+                                                     "cuda_graph": not args.no_graph, "mean_gt_per_image": total_gt_mean / B}),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * K,
+                "roofline": roofline, "cpu_baseline": cpu_base,
+                "kernel_ms": kernel_ms, "step_kernel_ms_sum": step_kernel_sum}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough for 3x L2)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -186,7 +186,7 @@ def encode_params(positive_threshold, ignore_threshold, prior_scaling, match_min
 
 
 def encode_batch(params, ymin, xmin, ymax, xmax, inside_mask, gt_boxes, gt_offsets, out=None, want_match=False,
-                 want_matched_gt=True, workspace=None):
+                 want_matched_gt=True, workspace=None, profile=False):
     """Fused IoU + match + encode for a batch (anchor_manipulator.py:275-387 per image).
 
     gt_boxes [sum M, 4] fp32, gt_offsets [B+1] int32 (CSR).  Returns EncodeResult with
@@ -210,13 +210,18 @@ def encode_batch(params, ymin, xmin, ymax, xmax, inside_mask, gt_boxes, gt_offse
     mask = _mask_u8(inside_mask)
     nbytes = L.lib().dan_encode_workspace_bytes(n, batch, total_gt)
     ws = (workspace or _ws).get(nbytes, dev)
+    args = [ctypes.byref(params), *_anchor_ptrs(ymin, xmin, ymax, xmax), L.dev_ptr(mask), n,
+            L.dev_ptr(gt_boxes, torch.float32, "gt_boxes") if total_gt else ctypes.c_void_p(0),
+            L.dev_ptr(gt_offsets, torch.int32, "gt_offsets"), batch, total_gt,
+            L.dev_ptr(targets, torch.float32), L.dev_ptr(labels, torch.int64),
+            L.dev_ptr(scores, torch.float32), L.dev_ptr(matched), L.dev_ptr(match),
+            L.dev_ptr(ws), nbytes, L.stream_ptr()]
     with torch.cuda.device(dev):
-        L.check(L.lib().dan_encode_batch(ctypes.byref(params), *_anchor_ptrs(ymin, xmin, ymax, xmax), L.dev_ptr(mask), n,
-                                         L.dev_ptr(gt_boxes, torch.float32, "gt_boxes") if total_gt else ctypes.c_void_p(0),
-                                         L.dev_ptr(gt_offsets, torch.int32, "gt_offsets"), batch, total_gt,
-                                         L.dev_ptr(targets, torch.float32), L.dev_ptr(labels, torch.int64),
-                                         L.dev_ptr(scores, torch.float32), L.dev_ptr(matched), L.dev_ptr(match),
-                                         L.dev_ptr(ws), nbytes, L.stream_ptr()))
+        if profile:   # CUDA-event duration of each pass, [pass1, pass2, pass3] in ms (synchronises)
+            ms = (ctypes.c_float * 3)()
+            L.check(L.lib().dan_encode_batch_profile(*args, ms))
+            return EncodeResult(targets, labels, scores, matched, match), list(ms)
+        L.check(L.lib().dan_encode_batch(*args))
     return EncodeResult(targets, labels, scores, matched, match)
 
 
@@ -356,7 +361,7 @@ def postprocess_params(num_classes, image_shape, select_threshold, min_size, kee
 
 
 def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=None, out=None, want_index=True,
-                      workspace=None):
+                      workspace=None, profile=False):
     """Batched fused parse_by_class (bbox_util.py:103-119).  cls_pred [B,N,C]; give loc_pred [B,N,4]
     (+ anchors = (ymin,xmin,ymax,xmax)) or boxes_pred [B,N,4].  Returns Detections indexed [b, c-1]."""
     L.require_device()
@@ -386,10 +391,14 @@ def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=
         aptr = [ctypes.c_void_p(0)] * 4
     nbytes = L.lib().dan_postprocess_workspace_bytes(n, batch, c, params.keep_topk)
     ws = (workspace or _ws).get(nbytes, dev)
+    args = [ctypes.byref(params), L.dev_ptr(cls_pred, torch.float32, "cls_pred"),
+            L.dev_ptr(loc_pred, torch.float32, "loc_pred"), L.dev_ptr(boxes_pred, torch.float32, "boxes_pred"), *aptr, n, batch,
+            L.dev_ptr(boxes), L.dev_ptr(scores), L.dev_ptr(counts), L.dev_ptr(aidx), L.dev_ptr(kpos), L.dev_ptr(ws), nbytes,
+            L.stream_ptr()]
     with torch.cuda.device(dev):
-        L.check(L.lib().dan_postprocess_batch(ctypes.byref(params), L.dev_ptr(cls_pred, torch.float32, "cls_pred"),
-                                              L.dev_ptr(loc_pred, torch.float32, "loc_pred"),
-                                              L.dev_ptr(boxes_pred, torch.float32, "boxes_pred"), *aptr, n, batch,
-                                              L.dev_ptr(boxes), L.dev_ptr(scores), L.dev_ptr(counts), L.dev_ptr(aidx),
-                                              L.dev_ptr(kpos), L.dev_ptr(ws), nbytes, L.stream_ptr()))
+        if profile:   # [filter, top-k/sort, nms mask, nms sweep] in ms (synchronises)
+            ms = (ctypes.c_float * 4)()
+            L.check(L.lib().dan_postprocess_batch_profile(*args, ms))
+            return Detections(boxes, scores, counts, aidx, kpos), list(ms)
+        L.check(L.lib().dan_postprocess_batch(*args))
     return Detections(boxes, scores, counts, aidx, kpos)

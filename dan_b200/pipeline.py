@@ -98,7 +98,7 @@ class HotPath(object):
     """The whole path for one rank: encode (training side) + postprocess (evaluation side)."""
 
     def __init__(self, anchors_train, inside_mask, encode_params, postprocess_params, anchors_eval=None,
-                 images_per_rank=None):
+                 images_per_rank=None, workspace=None):
         self.anchors_train = anchors_train          # (ymin, xmin, ymax, xmax)
         self.inside_mask = inside_mask
         self.anchors_eval = anchors_eval if anchors_eval is not None else anchors_train
@@ -106,6 +106,7 @@ class HotPath(object):
         self.pp_params = postprocess_params
         self.device = anchors_train[0].device
         self.images_per_rank = images_per_rank
+        self.workspace = workspace
         self._slab = None
         self._enc_out = None
         self._aux = None
@@ -126,16 +127,21 @@ class HotPath(object):
                              torch.empty((images, n, 4), dtype=torch.float32, device=d),
                              None)
 
-    def step(self, gt_boxes, gt_offsets, cls_pred, loc_pred):
-        """One pass over this rank's images.  Everything is enqueued on the current stream."""
+    def step(self, gt_boxes, gt_offsets, cls_pred, loc_pred, profile=False):
+        """One pass over this rank's images.  Everything is enqueued on the current stream.
+        profile=True returns per-kernel CUDA-event durations as a third value (synchronises)."""
         images = gt_offsets.numel() - 1
         self._buffers(images)
         enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
-                             out=self._enc_out)
+                             out=self._enc_out, workspace=self.workspace, profile=profile)
         counts, scores, boxes = self._slab.views()
         det = F.postprocess_batch(self.pp_params, cls_pred, loc_pred=loc_pred, anchors=self.anchors_eval,
                                   out=(boxes[:images], scores[:images], counts[:images], self._aux[0][:images],
-                                       self._aux[1][:images]))
+                                       self._aux[1][:images]), workspace=self.workspace, profile=profile)
+        if profile:
+            return enc[0], det[0], {"enc_pass1": enc[1][0], "enc_pass2": enc[1][1], "enc_pass3": enc[1][2],
+                                    "pp_filter": det[1][0], "pp_topk_sort": det[1][1], "nms_mask": det[1][2],
+                                    "nms_sweep": det[1][3]}
         return enc, det
 
     def gather(self, world_size, group=None):
