@@ -37,7 +37,6 @@ namespace dan {
 constexpr int kEncThreads = 256;
 constexpr int kGtChunk = 1024;     // GT boxes staged in shared memory at a time
 constexpr int kBucketCap = 64;     // compensation candidates bucketed per GT before spilling
-constexpr int kListCap = 256;      // shared-memory candidate list of pass 3
 
 struct EncArgs {
   // anchors (fused)
@@ -67,7 +66,7 @@ struct EncArgs {
   int32_t* haspos;       // [G] GT has a positive anchor-side match (dual, gt_max_first=0)
   int32_t* fill;         // [G] candidates pushed per GT
   HeapItem* bucket;      // [G, kBucketCap]
-  HeapItem* spill;       // [B, 2, n]
+  HeapItem* spill;       // [B, 3, n] (candidate list, sort buffer, heap of the overflow path)
   // outputs
   float4* targets;
   int64_t* labels;
@@ -491,122 +490,206 @@ DAN_D void apply_compensation(const EncArgs& A, const ImageGt& ig, int b, int a,
   }
 }
 
+constexpr int kP3Threads = 128;
+constexpr int kP3Group = 16;        // buckets staged in shared memory at a time
+constexpr int kHashSlots = 8192;    // anchors taken by stage 3 of this image (open addressing)
+
+struct TakenSet {
+  int* slots;      // [kHashSlots], -1 = empty
+  int* count;
+};
+
+DAN_D bool taken_has(const TakenSet& t, int a) {
+  unsigned h = ((unsigned)a * 2654435761u) & (kHashSlots - 1);
+  while (true) {
+    const int v = t.slots[h];
+    if (v == a) return true;
+    if (v < 0) return false;
+    h = (h + 1) & (kHashSlots - 1);
+  }
+}
+
+DAN_D void taken_add(const TakenSet& t, int a) {
+  unsigned h = ((unsigned)a * 2654435761u) & (kHashSlots - 1);
+  while (true) {
+    const int old = atomicCAS(&t.slots[h], -1, a);
+    if (old < 0 || old == a) break;
+    h = (h + 1) & (kHashSlots - 1);
+  }
+  atomicAdd(t.count, 1);
+}
+
+// Select the `need` best of the c entries of `list` (key <= 0 entries are dead) for GT j and apply them.
+// Pop order of a max-heap == descending key; only a tie that straddles the cut depends on libstdc++'s heap
+// layout, which is then reproduced exactly (heap_order.cuh).  Executed by one full warp.
 template <bool DENSE>
-__global__ void __launch_bounds__(32) enc_pass3_kernel(const EncArgs A) {
-  __shared__ HeapItem s_list[kListCap];
-  __shared__ HeapItem s_heap[kListCap];
+DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int j, int need, HeapItem* list, int c,
+                                bool ordered, HeapItem* sort_buf, HeapItem* heap, const TakenSet& taken, bool use_hash) {
+  const int lane = threadIdx.x & 31;
+  int live = 0;
+  for (int e = lane; e < c; e += 32) live += (list[e].key > 0.f) ? 1 : 0;
+  live = __reduce_add_sync(0xffffffffu, live);
+  auto apply = [&](int a, float ov) {
+    apply_compensation<DENSE>(A, ig, b, a, j, ov);
+    if (use_hash) taken_add(taken, a);
+  };
+  if (live <= need) {
+    for (int e = lane; e < c; e += 32)
+      if (list[e].key > 0.f) apply(list[e].id, list[e].key);
+    return;
+  }
+  int got = 0;
+  bool straddle = false;
+  while (got < need) {
+    float lmax = 0.f;
+    for (int e = lane; e < c; e += 32) lmax = fmaxf(lmax, list[e].key);
+    const uint32_t wbits = __reduce_max_sync(0xffffffffu, __float_as_uint(lmax));
+    if (wbits == 0u) break;
+    const float wmax = __uint_as_float(wbits);
+    int eq = 0;
+    for (int e = lane; e < c; e += 32) eq += (list[e].key == wmax) ? 1 : 0;
+    const int total = __reduce_add_sync(0xffffffffu, eq);
+    if (got + total > need) { straddle = true; break; }
+    for (int e = lane; e < c; e += 32) {
+      if (list[e].key == wmax) {
+        apply(list[e].id, wmax);
+        list[e].key = -wmax;     // taken; the value is kept for the exact path
+      }
+    }
+    got += total;
+    __syncwarp();
+  }
+  if (straddle) {
+    __syncwarp();
+    if (lane == 0) {
+      // compact the live + already taken entries (all were heap members) in ascending anchor order:
+      // the reference pushes candidates in ascending anchor index (small_mining_match.cc:204-209)
+      int n = 0;
+      for (int e = 0; e < c; ++e) {
+        if (list[e].key == 0.f) continue;
+        HeapItem v = list[e];
+        v.key = fabsf(v.key);
+        if (ordered) { sort_buf[n++] = v; continue; }
+        int p = n - 1;
+        while (p >= 0 && sort_buf[p].id > v.id) { sort_buf[p + 1] = sort_buf[p]; --p; }
+        sort_buf[p + 1] = v;
+        ++n;
+      }
+      int len = 0;
+      for (int e = 0; e < n; ++e) heap_push(heap, len, sort_buf[e]);
+      for (int p = 0; p < need && len > 0; ++p) {
+        const HeapItem it = heap_pop(heap, len);
+        apply(it.id, it.key);     // re-applying an entry taken above is idempotent
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) {
+  __shared__ HeapItem s_group[kP3Group][kBucketCap];
+  __shared__ HeapItem s_sort[kBucketCap];
+  __shared__ HeapItem s_heap[kBucketCap];
+  __shared__ int s_hash[kHashSlots];
+  __shared__ int s_taken_n;
+  __shared__ int s_needy_j[kP3Threads], s_needy_need[kP3Threads], s_needy_fill[kP3Threads];
+  __shared__ int s_warp_cnt[kP3Threads / 32];
+
   const int b = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const ImageGt ig = image_gt<DENSE>(A, b);
+  TakenSet taken{s_hash, &s_taken_n};
 
-  for (int j0 = 0; j0 < ig.m_eff; j0 += 32) {
-    int my_need = 0;
-    if (j0 + lane < ig.m_eff) my_need = A.min_match - A.cnt[ig.slot0 + j0 + lane];
-    unsigned todo = __ballot_sync(0xffffffffu, my_need > 0);
-    while (todo) {
-      const int jj = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int j = j0 + jj;
-      const int need = __shfl_sync(0xffffffffu, my_need, jj);
-      const int filled = A.fill[ig.slot0 + j];
+  for (int i = tid; i < kHashSlots; i += kP3Threads) s_hash[i] = -1;
+  if (tid == 0) s_taken_n = 0;
+  __syncthreads();
 
-      HeapItem* list = s_list;
-      HeapItem* heap = s_heap;
-      bool ordered = false;
-      int c = 0;
-      if (filled <= kBucketCap) {
-        const HeapItem* bk = A.bucket + (int64_t)(ig.slot0 + j) * kBucketCap;
-        for (int e0 = 0; e0 < filled; e0 += 32) {
-          const int e = e0 + lane;
-          bool ok = false;
-          HeapItem it;
-          if (e < filled) {
-            it = bk[e];
-            ok = still_unmatched<DENSE>(A, (int64_t)b * A.n + it.id);
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (ok) s_list[c + __popc(m & lt_mask)] = it;
-          c += __popc(m);
-        }
-      } else {
-        // bucket overflowed: rescan every anchor of the image in index order
-        list = A.spill + (int64_t)b * 2 * A.n;
-        heap = list + A.n;
-        ordered = true;
-        const float4 g = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : gt_box(A, ig, j);
-        const float garea = box_area(g.x, g.y, g.z, g.w);
-        for (int a0 = 0; a0 < A.n; a0 += 32) {
-          const int a = a0 + lane;
-          bool ok = false;
-          float ov = 0.f;
-          if (a < A.n) {
-            if (DENSE) {
-              ov = A.overlaps[(int64_t)a * ig.m_eff + j];
-            } else if (A.mask == nullptr || A.mask[a] != 0) {
-              const AnchorBox ab = load_anchor(A, a);
-              bool hit;
-              ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, g.x, g.y, g.z, g.w, garea, hit);
-            }
-            ok = (ov > A.stop) && still_unmatched<DENSE>(A, (int64_t)b * A.n + a);
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (ok) list[c + __popc(m & lt_mask)] = HeapItem{ov, a};
-          c += __popc(m);
-        }
-        __threadfence_block();
+  for (int j0 = 0; j0 < ig.m_eff; j0 += kP3Threads) {
+    // ---- GTs of this range that are short of min_match, in ascending order
+    const int j = j0 + tid;
+    int need = 0, fill = 0;
+    if (j < ig.m_eff) {
+      need = A.min_match - A.cnt[ig.slot0 + j];
+      fill = A.fill[ig.slot0 + j];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, need > 0);
+    if (lane == 0) s_warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, nneedy = 0;
+    for (int w = 0; w < kP3Threads / 32; ++w) {
+      if (w < warp) before += s_warp_cnt[w];
+      nneedy += s_warp_cnt[w];
+    }
+    if (need > 0) {
+      const int pos = before + __popc(m & lt_mask);
+      s_needy_j[pos] = j;
+      s_needy_need[pos] = need;
+      s_needy_fill[pos] = fill;
+    }
+    __syncthreads();
+
+    for (int g0 = 0; g0 < nneedy; g0 += kP3Group) {
+      const int ng = min(kP3Group, nneedy - g0);
+      // ---- stage the group's candidate buckets (all threads, coalesced)
+      for (int e = tid; e < ng * kBucketCap; e += kP3Threads) {
+        const int g = e / kBucketCap, k = e % kBucketCap;
+        const int f = s_needy_fill[g0 + g];
+        if (f <= kBucketCap && k < f) s_group[g][k] = A.bucket[(int64_t)(ig.slot0 + s_needy_j[g0 + g]) * kBucketCap + k];
       }
-      __syncwarp();
-
-      if (c <= need) {
-        for (int e = lane; e < c; e += 32) apply_compensation<DENSE>(A, ig, b, list[e].id, j, list[e].key);
-      } else {
-        // pop order of a max-heap == descending key; only a tie that straddles the
-        // cut depends on libstdc++'s heap layout -> exact transcription below.
-        int taken = 0;
-        bool straddle = false;
-        while (taken < need) {
-          float lmax = 0.f;
-          for (int e = lane; e < c; e += 32) lmax = fmaxf(lmax, list[e].key);
-          const uint32_t wbits = __reduce_max_sync(0xffffffffu, __float_as_uint(lmax));
-          if (wbits == 0u) break;
-          const float wmax = __uint_as_float(wbits);
-          int eq = 0;
-          for (int e = lane; e < c; e += 32) eq += (list[e].key == wmax) ? 1 : 0;
-          const int total = __reduce_add_sync(0xffffffffu, eq);
-          if (taken + total > need) { straddle = true; break; }
-          for (int e = lane; e < c; e += 32) {
-            if (list[e].key == wmax) {
-              apply_compensation<DENSE>(A, ig, b, list[e].id, j, wmax);
-              list[e].key = -wmax;   // mark as taken, value kept for the exact path
+      __syncthreads();
+      // ---- the stage is order dependent: warp 0 walks the GTs in ascending order
+      if (warp == 0) {
+        for (int g = 0; g < ng; ++g) {
+          const int gj = s_needy_j[g0 + g];
+          const int gneed = s_needy_need[g0 + g];
+          const int gfill = s_needy_fill[g0 + g];
+          const bool use_hash = s_taken_n < kHashSlots / 2;
+          if (gfill <= kBucketCap) {
+            HeapItem* list = s_group[g];
+            for (int e = lane; e < gfill; e += 32) {
+              const int a = list[e].id;
+              const bool dead = use_hash ? taken_has(taken, a) : !still_unmatched<DENSE>(A, (int64_t)b * A.n + a);
+              if (dead) list[e].key = 0.f;
             }
-          }
-          taken += total;
-          __syncwarp();
-        }
-        if (straddle) {
-          __syncwarp();
-          if (lane == 0) {
-            for (int e = 0; e < c; ++e) list[e].key = fabsf(list[e].key);
-            if (!ordered) {  // reference pushes candidates in ascending anchor index (:204-209)
-              for (int e = 1; e < c; ++e) {
-                const HeapItem v = list[e];
-                int p = e - 1;
-                while (p >= 0 && list[p].id > v.id) { list[p + 1] = list[p]; --p; }
-                list[p + 1] = v;
+            __syncwarp();
+            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, gfill, false, s_sort, s_heap, taken, use_hash);
+          } else {
+            // bucket overflowed: rescan every anchor of the image in index order (labels in HBM are the truth)
+            HeapItem* list = A.spill + (int64_t)b * 3 * A.n;
+            int c = 0;
+            const float4 gb = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : gt_box(A, ig, gj);
+            const float garea = box_area(gb.x, gb.y, gb.z, gb.w);
+            for (int a0 = 0; a0 < A.n; a0 += 32) {
+              const int a = a0 + lane;
+              bool ok = false;
+              float ov = 0.f;
+              if (a < A.n) {
+                if (DENSE) {
+                  ov = A.overlaps[(int64_t)a * ig.m_eff + gj];
+                } else if (A.mask == nullptr || A.mask[a] != 0) {
+                  const AnchorBox ab = load_anchor(A, a);
+                  bool hit;
+                  ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, gb.x, gb.y, gb.z, gb.w, garea, hit);
+                }
+                ok = (ov > A.stop) && still_unmatched<DENSE>(A, (int64_t)b * A.n + a);
               }
+              const unsigned mm = __ballot_sync(0xffffffffu, ok);
+              if (ok) list[c + __popc(mm & lt_mask)] = HeapItem{ov, a};
+              c += __popc(mm);
             }
-            int len = 0;
-            for (int e = 0; e < c; ++e) heap_push(heap, len, list[e]);
-            for (int p = 0; p < need && len > 0; ++p) {
-              const HeapItem it = heap_pop(heap, len);
-              apply_compensation<DENSE>(A, ig, b, it.id, j, it.key);
-            }
+            __threadfence_block();
+            __syncwarp();
+            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, c, true, list + A.n, list + 2 * (int64_t)A.n, taken, use_hash);
           }
+          __threadfence_block();
+          __syncwarp();
         }
       }
-      __threadfence_block();
-      __syncwarp();
+      __syncthreads();
     }
   }
 }
@@ -636,7 +719,7 @@ static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
   w.fill = off;   off += align_up(slots * 4, 256);
   w.zero_bytes = off;
   w.bucket = off; off += align_up(slots * kBucketCap * sizeof(HeapItem), 256);
-  w.spill = off;  off += align_up(batch * 2 * n * sizeof(HeapItem), 256);
+  w.spill = off;  off += align_up(batch * 3 * n * sizeof(HeapItem), 256);
   w.total = off;
   return w;
 }
@@ -676,7 +759,7 @@ static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, c
   DAN_LAUNCH_CHECK("enc_pass2_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
   if (mining) {
-    enc_pass3_kernel<DENSE><<<batch, 32, 0, st>>>(A);
+    enc_pass3_kernel<DENSE><<<batch, kP3Threads, 0, st>>>(A);
     DAN_LAUNCH_CHECK("enc_pass3_kernel");
   }
   if (ev) DAN_CUDA(cudaEventRecord(ev[3], st));

@@ -95,10 +95,14 @@ def flatten_detections(gathered, image_counts=None):
 
 
 class HotPath(object):
-    """The whole path for one rank: encode (training side) + postprocess (evaluation side)."""
+    """The whole path for one rank: encode (training side) + postprocess (evaluation side).
+
+    The two halves are independent, so step() forks the encode chain onto a side stream and joins it at the end
+    (inside a CUDA-graph capture this becomes two parallel branches); each half has its own workspace."""
 
     def __init__(self, anchors_train, inside_mask, encode_params, postprocess_params, anchors_eval=None,
-                 images_per_rank=None, workspace=None):
+                 images_per_rank=None, workspaces=None, overlap=True):
+        from . import _lib
         self.anchors_train = anchors_train          # (ymin, xmin, ymax, xmax)
         self.inside_mask = inside_mask
         self.anchors_eval = anchors_eval if anchors_eval is not None else anchors_train
@@ -106,7 +110,9 @@ class HotPath(object):
         self.pp_params = postprocess_params
         self.device = anchors_train[0].device
         self.images_per_rank = images_per_rank
-        self.workspace = workspace
+        self.ws_enc, self.ws_pp = workspaces if workspaces is not None else (_lib.Workspace(), _lib.Workspace())
+        self.overlap = overlap
+        self._side = None
         self._slab = None
         self._enc_out = None
         self._aux = None
@@ -128,20 +134,31 @@ class HotPath(object):
                              None)
 
     def step(self, gt_boxes, gt_offsets, cls_pred, loc_pred, profile=False):
-        """One pass over this rank's images.  Everything is enqueued on the current stream.
-        profile=True returns per-kernel CUDA-event durations as a third value (synchronises)."""
+        """One pass over this rank's images.  Everything is enqueued (current stream + one forked side stream).
+        profile=True runs serially and returns per-kernel CUDA-event durations as a third value (synchronises)."""
         images = gt_offsets.numel() - 1
         self._buffers(images)
-        enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
-                             out=self._enc_out, workspace=self.workspace, profile=profile)
         counts, scores, boxes = self._slab.views()
+        det_out = (boxes[:images], scores[:images], counts[:images], self._aux[0][:images], self._aux[1][:images])
+        if profile or not self.overlap:
+            enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
+                                 out=self._enc_out, workspace=self.ws_enc, profile=profile)
+            det = F.postprocess_batch(self.pp_params, cls_pred, loc_pred=loc_pred, anchors=self.anchors_eval,
+                                      out=det_out, workspace=self.ws_pp, profile=profile)
+            if profile:
+                return enc[0], det[0], {"enc_pass1": enc[1][0], "enc_pass2": enc[1][1], "enc_pass3": enc[1][2],
+                                        "pp_filter": det[1][0], "pp_sort_nms": det[1][1]}
+            return enc, det
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
+                                 out=self._enc_out, workspace=self.ws_enc)
         det = F.postprocess_batch(self.pp_params, cls_pred, loc_pred=loc_pred, anchors=self.anchors_eval,
-                                  out=(boxes[:images], scores[:images], counts[:images], self._aux[0][:images],
-                                       self._aux[1][:images]), workspace=self.workspace, profile=profile)
-        if profile:
-            return enc[0], det[0], {"enc_pass1": enc[1][0], "enc_pass2": enc[1][1], "enc_pass3": enc[1][2],
-                                    "pp_filter": det[1][0], "pp_topk_sort": det[1][1], "nms_mask": det[1][2],
-                                    "nms_sweep": det[1][3]}
+                                  out=det_out, workspace=self.ws_pp)
+        main.wait_stream(self._side)
         return enc, det
 
     def gather(self, world_size, group=None):

@@ -82,7 +82,7 @@ def test_attr_validation_before_device(lib):
     assert lib.dan_dual_max_match(null, 10, 0, .35, .35, 1, 1, null, null, null, 0, null) == -1           # empty GT axis
     assert lib.dan_match_workspace_bytes(34125, 50) > 0
     assert lib.dan_encode_workspace_bytes(34125, 32, 1600) > 0
-    assert lib.dan_postprocess_workspace_bytes(34125, 32, 2, 5000) >= 32 * 5000 * 79 * 8
+    assert lib.dan_postprocess_workspace_bytes(34125, 32, 2, 5000) >= 32 * 34125 * 8
     assert lib.dan_postprocess_workspace_bytes(34125, 32, 1, 5000) == 0
 
 
