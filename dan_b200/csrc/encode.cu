@@ -28,6 +28,7 @@
 // Precondition shared with the op's own doc string (small_mining_match.cc:42-43):
 // overlaps are in [0, 1], i.e. boxes have non-negative (+1 convention) extents.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "heap_order.cuh"
@@ -470,6 +471,163 @@ __global__ void __launch_bounds__(kEncThreads) enc_pass2_kernel(const EncArgs A)
 }
 
 // ---------------------------------------------------------------------------
+// FUSED path, passes 1 and 2 as warp-autonomous kernels.
+//   * a warp owns 32 consecutive anchors and walks kEncImgPerWarp images with them: the anchor loads, the PA
+//     transform, the areas and the warp bounding box are paid once per group of images;
+//   * no shared memory and no CTA barrier: the ground truth of an image is a few hundred bytes, read through the
+//     read-only path (32 boxes per coalesced load for the cull test, broadcast loads for the hits);
+//   * per-GT column maxima of pass 1 are reduced in the warp (redux.sync) and the lane that loaded GT k issues one
+//     atomicMax for it, so the atomics of a warp go to 32 different addresses.
+// The dense-matrix kernels above keep the tiled shared-memory scheme (they have to transpose the matrix).
+// ---------------------------------------------------------------------------
+// images per warp pass: runtime (DAN_ENC_IMAGES_PER_WARP, default 1: more, smaller CTAs balance better on 148 SMs)
+
+struct WarpAnchors {
+  AnchorBox ab;
+  WarpBox wb;
+  bool valid, active;
+  int a;
+};
+
+DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
+  WarpAnchors w;
+  w.a = blockIdx.x * kEncThreads + threadIdx.x;
+  w.valid = w.a < A.n;
+  w.ab = AnchorBox{};
+  w.active = false;
+  if (w.valid) {
+    w.ab = load_anchor(A, w.a);
+    w.active = (A.mask == nullptr) || (A.mask[w.a] != 0);
+  }
+  w.wb = warp_bbox(w.active, w.ab);
+  return w;
+}
+
+template <bool NEED_ROW>
+__global__ void __launch_bounds__(kEncThreads) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
+  const int lane = threadIdx.x & 31;
+  const WarpAnchors W = load_warp_anchors(A);
+  const int b_end = min(batch, (int)(blockIdx.y + 1) * ipw);
+  for (int b = blockIdx.y * ipw; b < b_end; ++b) {
+    const ImageGt ig = image_gt<false>(A, b);
+    float best = 0.f;
+    int best_gt = 0;
+    for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
+      const int k = k0 + lane;
+      const float4 gk = (k < ig.m_eff) ? gt_box(A, ig, k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned hits = __ballot_sync(0xffffffffu, (k < ig.m_eff) && may_hit(W.wb, gk));
+      uint32_t my_colmax = 0u;            // column maximum of GT k over this warp's anchors
+      while (hits) {
+        const int kl = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const float4 g = gt_box(A, ig, k0 + kl);
+        bool hit = false;
+        float ov = 0.f;
+        if (W.active) ov = pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g.x, g.y, g.z, g.w,
+                                    box_area(g.x, g.y, g.z, g.w), hit);
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, (ov > 0.f) ? __float_as_uint(ov) : 0u);
+        if (lane == kl) my_colmax = wmax;
+        if (NEED_ROW && ov > best) { best = ov; best_gt = k0 + kl; }
+      }
+      if (my_colmax != 0u) atomicMax(A.colmax + ig.slot0 + k, my_colmax);
+    }
+    if (NEED_ROW && W.valid) {
+      const bool less = best < A.low;
+      const bool between = (best < A.high) && (best >= A.low);
+      if (!less && !between) A.haspos[ig.slot0 + best_gt] = 1;
+    }
+  }
+}
+
+template <bool MINING>
+__global__ void __launch_bounds__(kEncThreads) enc_pass2_fused_kernel(const EncArgs A, int batch, int ipw) {
+  const int lane = threadIdx.x & 31;
+  const WarpAnchors W = load_warp_anchors(A);
+  const bool need_haspos = !MINING && !A.gt_max_first;
+  const int b_end = min(batch, (int)(blockIdx.y + 1) * ipw);
+  for (int b = blockIdx.y * ipw; b < b_end; ++b) {
+    const ImageGt ig = image_gt<false>(A, b);
+    RowState s;
+    s.best = 0.f; s.best_gt = 0; s.ov0 = 0.f;
+    s.claimed = false; s.cbest = 0.f; s.cbest_gt = 0;
+    s.owner = -1; s.owner_ov = 0.f;
+    int match = -1;
+    float score = 0.f;
+    bool push = false;
+    for (int round = 0; round < 2; ++round) {
+      for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
+        const int k = k0 + lane;
+        bool test = false;
+        if (k < ig.m_eff) {
+          const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + k));
+          const bool wide = MINING ? (cm < FLT_EPSILON) : (cm == 0.f);
+          test = may_hit(W.wb, gt_box(A, ig, k)) || (round == 0 && wide);
+        }
+        unsigned hits = __ballot_sync(0xffffffffu, test);
+        while (hits) {
+          const int kk = k0 + __ffs(hits) - 1;
+          hits &= hits - 1;
+          const float4 g = gt_box(A, ig, kk);
+          bool hit = false;
+          float ov = 0.f;
+          if (W.active) ov = pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g.x, g.y, g.z, g.w,
+                                      box_area(g.x, g.y, g.z, g.w), hit);
+          if (round == 0) {
+            const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + kk));
+            const bool claimable = !need_haspos || __ldg(A.haspos + ig.slot0 + kk) == 0;
+            row_update<MINING>(s, kk, ov, cm, claimable);
+          } else if (MINING && push && ov > A.stop) {
+            const int pos = atomicAdd(A.fill + ig.slot0 + kk, 1);
+            if (pos < kBucketCap) A.bucket[(int64_t)(ig.slot0 + kk) * kBucketCap + pos] = HeapItem{ov, W.a};
+          }
+        }
+      }
+      if (round == 1) break;
+      if (MINING) {
+        // stage 1, small_mining_match.cc:85-93
+        if (s.best >= A.neg_low && s.best < A.low) match = -1;
+        else if (s.best >= A.high) match = s.best_gt;
+        else match = -2;
+        score = s.best;
+        // stage 2, :178-186
+        if (s.owner >= 0) { match = s.owner; score = s.owner_ov; }
+        if (W.valid && match >= 0) atomicAdd(A.cnt + ig.slot0 + match, 1);
+        push = W.valid && match < 0 && s.best > A.stop;
+      } else {
+        // anchor_manipulator.py:67-76
+        const bool less = s.best < A.low;
+        const bool between = (s.best < A.high) && (s.best >= A.low);
+        const bool neg = A.ignore_between ? less : between;
+        const bool ign = A.ignore_between ? between : less;
+        match = s.best_gt;
+        if (neg) match = -1;
+        if (ign) match = -2;
+        score = s.best;
+        // :95-104 GT-side claim has priority; argmax over (overlap * claim mask)
+        if (s.claimed) {
+          if (s.cbest > 0.f) { match = s.cbest_gt; score = s.cbest; }
+          else { match = 0; score = s.ov0; }
+        }
+      }
+      // compensation candidates are pushed in a second sweep, only by warps that have one (warp-uniform decision)
+      if (!MINING || !__any_sync(0xffffffffu, push)) break;
+    }
+    if (W.valid) {
+      const int64_t row = (int64_t)b * A.n + W.a;
+      if (match >= 0) {
+        write_positive(A, row, W.ab, gt_box(A, ig, match), score, match);
+      } else {
+        A.targets[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+        A.labels[row] = (match < -1) ? -1 : 0;   // anchor_manipulator.py:300-302
+        A.scores[row] = score;
+        if (A.matched != nullptr) A.matched[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (A.match32 != nullptr) A.match32[row] = match;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // pass 3: stage 3 "hard face compensation", small_mining_match.cc:199-222.
 // One warp per image, GTs in ascending order.
 // ---------------------------------------------------------------------------
@@ -492,11 +650,21 @@ DAN_D void apply_compensation(const EncArgs& A, const ImageGt& ig, int b, int a,
 
 constexpr int kP3Threads = 128;
 constexpr int kP3Group = 16;        // buckets staged in shared memory at a time
-constexpr int kHashSlots = 8192;    // anchors taken by stage 3 of this image (open addressing)
+constexpr int kHashSlots = 4096;    // anchors taken by stage 3 of this image (open addressing)
+constexpr int kApplyCap = 1024;     // deferred output patches
 
 struct TakenSet {
   int* slots;      // [kHashSlots], -1 = empty
   int* count;
+};
+
+// Output patches of stage 3 are deferred: the serial walk over the GTs only needs the taken SET (shared memory),
+// so the encode + global stores of each patched anchor run afterwards, in parallel over the whole CTA.
+struct ApplyList {
+  int* a;
+  int* j;
+  float* ov;
+  int* n;
 };
 
 DAN_D bool taken_has(const TakenSet& t, int a) {
@@ -523,15 +691,31 @@ DAN_D void taken_add(const TakenSet& t, int a) {
 // Pop order of a max-heap == descending key; only a tie that straddles the cut depends on libstdc++'s heap
 // layout, which is then reproduced exactly (heap_order.cuh).  Executed by one full warp.
 template <bool DENSE>
+DAN_D void flush_applies(const EncArgs& A, const ImageGt& ig, int b, const ApplyList& al, int first, int step) {
+  const int n = min(*al.n, kApplyCap);
+  for (int e = first; e < n; e += step) apply_compensation<DENSE>(A, ig, b, al.a[e], al.j[e], al.ov[e]);
+}
+
+template <bool DENSE>
 DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int j, int need, HeapItem* list, int c,
-                                bool ordered, HeapItem* sort_buf, HeapItem* heap, const TakenSet& taken, bool use_hash) {
+                                bool ordered, HeapItem* sort_buf, HeapItem* heap, const TakenSet& taken, bool use_hash,
+                                const ApplyList& al, bool defer) {
   const int lane = threadIdx.x & 31;
   int live = 0;
   for (int e = lane; e < c; e += 32) live += (list[e].key > 0.f) ? 1 : 0;
   live = __reduce_add_sync(0xffffffffu, live);
   auto apply = [&](int a, float ov) {
-    apply_compensation<DENSE>(A, ig, b, a, j, ov);
     if (use_hash) taken_add(taken, a);
+    if (defer) {
+      const int slot = atomicAdd(al.n, 1);
+      if (slot < kApplyCap) {
+        al.a[slot] = a;
+        al.j[slot] = j;
+        al.ov[slot] = ov;
+        return;
+      }
+    }
+    apply_compensation<DENSE>(A, ig, b, a, j, ov);
   };
   if (live <= need) {
     for (int e = lane; e < c; e += 32)
@@ -540,6 +724,29 @@ DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int 
   }
   int got = 0;
   bool straddle = false;
+  if (c <= 64) {
+    // one ranking pass: entry e is popped before the cut iff its whole tie group fits (ge <= need), after the
+    // cut iff g >= need; a tie group with g < need < ge straddles the cut
+    const float k0 = (lane < c) ? list[lane].key : 0.f;
+    const float k1 = (lane + 32 < c) ? list[lane + 32].key : 0.f;
+    int g0 = 0, ge0 = 0, g1 = 0, ge1 = 0;
+    for (int e = 0; e < c; ++e) {
+      const float v = list[e].key;
+      if (v > 0.f) {
+        g0 += (v > k0) ? 1 : 0;
+        ge0 += (v >= k0) ? 1 : 0;
+        g1 += (v > k1) ? 1 : 0;
+        ge1 += (v >= k1) ? 1 : 0;
+      }
+    }
+    const bool st = (k0 > 0.f && g0 < need && ge0 > need) || (k1 > 0.f && g1 < need && ge1 > need);
+    straddle = __any_sync(0xffffffffu, st);
+    if (!straddle) {
+      if (k0 > 0.f && ge0 <= need) apply(list[lane].id, k0);
+      if (k1 > 0.f && ge1 <= need) apply(list[lane + 32].id, k1);
+    }
+    got = need;
+  }
   while (got < need) {
     float lmax = 0.f;
     for (int e = lane; e < c; e += 32) lmax = fmaxf(lmax, list[e].key);
@@ -593,6 +800,9 @@ __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) 
   __shared__ HeapItem s_heap[kBucketCap];
   __shared__ int s_hash[kHashSlots];
   __shared__ int s_taken_n;
+  __shared__ int s_apply_a[kApplyCap], s_apply_j[kApplyCap];
+  __shared__ float s_apply_ov[kApplyCap];
+  __shared__ int s_apply_n;
   __shared__ int s_needy_j[kP3Threads], s_needy_need[kP3Threads], s_needy_fill[kP3Threads];
   __shared__ int s_warp_cnt[kP3Threads / 32];
 
@@ -603,9 +813,10 @@ __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) 
   const unsigned lt_mask = (1u << lane) - 1u;
   const ImageGt ig = image_gt<DENSE>(A, b);
   TakenSet taken{s_hash, &s_taken_n};
+  ApplyList al{s_apply_a, s_apply_j, s_apply_ov, &s_apply_n};
 
   for (int i = tid; i < kHashSlots; i += kP3Threads) s_hash[i] = -1;
-  if (tid == 0) s_taken_n = 0;
+  if (tid == 0) { s_taken_n = 0; s_apply_n = 0; }
   __syncthreads();
 
   for (int j0 = 0; j0 < ig.m_eff; j0 += kP3Threads) {
@@ -648,6 +859,14 @@ __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) 
           const int gneed = s_needy_need[g0 + g];
           const int gfill = s_needy_fill[g0 + g];
           const bool use_hash = s_taken_n < kHashSlots / 2;
+          if (!use_hash || gfill > kBucketCap) {
+            // this GT reads the labels in HBM as the truth: write the pending patches first
+            flush_applies<DENSE>(A, ig, b, al, lane, 32);
+            __syncwarp();
+            if (lane == 0) s_apply_n = 0;
+            __threadfence_block();
+            __syncwarp();
+          }
           if (gfill <= kBucketCap) {
             HeapItem* list = s_group[g];
             for (int e = lane; e < gfill; e += 32) {
@@ -656,9 +875,10 @@ __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) 
               if (dead) list[e].key = 0.f;
             }
             __syncwarp();
-            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, gfill, false, s_sort, s_heap, taken, use_hash);
+            // patches can be deferred as long as the taken set is tracked in shared memory
+            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, gfill, false, s_sort, s_heap, taken, use_hash, al, use_hash);
           } else {
-            // bucket overflowed: rescan every anchor of the image in index order (labels in HBM are the truth)
+            // bucket overflowed: rescan every anchor of the image in index order (patches are immediate here)
             HeapItem* list = A.spill + (int64_t)b * 3 * A.n;
             int c = 0;
             const float4 gb = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : gt_box(A, ig, gj);
@@ -683,13 +903,18 @@ __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) 
             }
             __threadfence_block();
             __syncwarp();
-            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, c, true, list + A.n, list + 2 * (int64_t)A.n, taken, use_hash);
+            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, c, true, list + A.n, list + 2 * (int64_t)A.n, taken, use_hash,
+                                        al, false);
           }
           __threadfence_block();
           __syncwarp();
         }
       }
       __syncthreads();
+      // ---- deferred output patches of the group, all threads
+      flush_applies<DENSE>(A, ig, b, al, tid, kP3Threads);
+      __syncthreads();
+      if (tid == 0) s_apply_n = 0;
     }
   }
 }
@@ -749,13 +974,26 @@ static void bind_workspace(EncArgs& A, void* workspace, const WsLayout& w) {
 template <bool DENSE>
 static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, cudaStream_t st, cudaEvent_t* ev = nullptr) {
   const dim3 grid((A.n + kEncThreads - 1) / kEncThreads, batch);
+  static const int ipw_env = []() { const char* e = getenv("DAN_ENC_IMAGES_PER_WARP"); const int v = e ? atoi(e) : 1; return v >= 1 ? v : 1; }();
+  const int ipw = ipw_env;
+  const dim3 fgrid((A.n + kEncThreads - 1) / kEncThreads, (batch + ipw - 1) / ipw);
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
-  if (need_row) enc_pass1_kernel<DENSE, true><<<grid, kEncThreads, 0, st>>>(A);
-  else enc_pass1_kernel<DENSE, false><<<grid, kEncThreads, 0, st>>>(A);
+  if (DENSE) {
+    if (need_row) enc_pass1_kernel<true, true><<<grid, kEncThreads, 0, st>>>(A);
+    else enc_pass1_kernel<true, false><<<grid, kEncThreads, 0, st>>>(A);
+  } else {
+    if (need_row) enc_pass1_fused_kernel<true><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
+    else enc_pass1_fused_kernel<false><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
+  }
   DAN_LAUNCH_CHECK("enc_pass1_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
-  if (mining) enc_pass2_kernel<DENSE, true><<<grid, kEncThreads, 0, st>>>(A);
-  else enc_pass2_kernel<DENSE, false><<<grid, kEncThreads, 0, st>>>(A);
+  if (DENSE) {
+    if (mining) enc_pass2_kernel<true, true><<<grid, kEncThreads, 0, st>>>(A);
+    else enc_pass2_kernel<true, false><<<grid, kEncThreads, 0, st>>>(A);
+  } else {
+    if (mining) enc_pass2_fused_kernel<true><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
+    else enc_pass2_fused_kernel<false><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
+  }
   DAN_LAUNCH_CHECK("enc_pass2_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
   if (mining) {

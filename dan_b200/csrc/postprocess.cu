@@ -25,6 +25,8 @@ namespace dan {
 
 constexpr int kSortCap = 8192;      // keys sorted in shared memory (64 KB)
 constexpr int kSortThreads = 1024;
+constexpr int kAdjCap = 64;        // suppressor list capacity per candidate
+constexpr int kPairCtasPerList = 32;
 
 
 DAN_D uint32_t score_to_key(float s) { return (uint32_t)float_to_ordered(s) ^ 0x80000000u; }
@@ -44,6 +46,7 @@ struct PpArgs {
   float select_thr, min_size_p1;
   float ps0, ps1, ps2, ps3;
   int keep_topk, nms_topk;
+  int nms_cap;                // kept-list capacity in shared memory = min(nms_topk, keep_topk)
   float nms_thr;
   // workspace
   unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
@@ -51,6 +54,14 @@ struct PpArgs {
   float* s_scores;            // sort_bboxes outputs [keep_topk]
   float4* s_boxes;
   int32_t* s_index;
+  // sorted candidates (sort kernel -> pairs kernel -> resolve kernel), per list
+  unsigned long long* s_key;  // [L, keep_topk] sorted keys
+  float4* s_box;              // [L, keep_topk] normalised corners (y0, x0, y1, x1)
+  float* s_area;              // [L, keep_topk] (y1-y0)*(x1-x0)
+  int32_t* s_len;             // [L] number of sorted candidates K
+  int32_t* deg;               // [L, keep_topk] number of higher-ranked boxes that suppress candidate i
+  uint16_t* adj;              // [L, kAdjCap, keep_topk] their positions
+  int32_t* ovf;               // [L] some candidate has more than kAdjCap suppressors -> round-based fallback
   // outputs
   float4* out_boxes;
   float* out_scores;
@@ -71,14 +82,33 @@ DAN_D float4 pp_clip(float4 b, float height, float width) {
   return make_float4(ymin, xmin, ymax, xmax);
 }
 
-// decode (when offsets are given) + clip for anchor `a` of image `b`
-DAN_D float4 pp_box(const PpArgs& A, int b, int a) {
+// decode (when offsets are given) + clip for anchor `a` of image `b`, split into the global loads and the
+// arithmetic so that a caller can put independent work between the two
+struct RawBox {
+  float4 v;        // offsets or decoded box
+  float4 anchor;   // ymin, xmin, ymax, xmax (only when decoding)
+};
+
+DAN_D RawBox pp_load(const PpArgs& A, int b, int a) {
   const int64_t row = (int64_t)b * A.n + a;
-  float4 bx;
-  if (A.loc != nullptr) bx = decode_box(A.loc[row], A.ay0[a], A.ax0[a], A.ay1[a], A.ax1[a], A.ps0, A.ps1, A.ps2, A.ps3);
-  else bx = A.boxes[row];
+  RawBox r;
+  if (A.loc != nullptr) {
+    r.v = A.loc[row];
+    r.anchor = make_float4(A.ay0[a], A.ax0[a], A.ay1[a], A.ax1[a]);
+  } else {
+    r.v = A.boxes[row];
+    r.anchor = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return r;
+}
+
+DAN_D float4 pp_finish(const PpArgs& A, const RawBox& r) {
+  float4 bx = r.v;
+  if (A.loc != nullptr) bx = decode_box(r.v, r.anchor.x, r.anchor.y, r.anchor.z, r.anchor.w, A.ps0, A.ps1, A.ps2, A.ps3);
   return pp_clip(bx, A.img_h, A.img_w);
 }
+
+DAN_D float4 pp_box(const PpArgs& A, int b, int a) { return pp_finish(A, pp_load(A, b, a)); }
 
 // ---------------------------------------------------------------------------
 // K3: filter + compaction.  grid (ceil(N/256), B)
@@ -276,103 +306,290 @@ DAN_D bool nms_suppresses(float4 a, float a_area, float4 b, float b_area, float 
   return fdiv(inter, fsub(fadd(a_area, b_area), inter)) > thr;
 }
 
+// ---------------------------------------------------------------------------
+// K4: one CTA per list: top-k select + sort, then decode + clip + normalise the K best boxes (sorted order) to HBM
+// ---------------------------------------------------------------------------
 template <bool DECODE>
-__global__ void __launch_bounds__(kSortThreads) pp_nms_kernel(const PpArgs A, const float* __restrict__ src_scores,
-                                                              const float4* __restrict__ src_boxes) {
+__global__ void __launch_bounds__(kSortThreads) pp_sort_kernel(const PpArgs A, const float4* __restrict__ src_boxes) {
   extern __shared__ unsigned long long s_keys[];             // [kSortCap]
-  float4* kept_box = reinterpret_cast<float4*>(s_keys + kSortCap);     // [nms_topk]
-  float* kept_area = reinterpret_cast<float*>(kept_box + A.nms_topk);  // [nms_topk]
-  int32_t* kept_pos = reinterpret_cast<int32_t*>(kept_area + A.nms_topk);   // [nms_topk]
   __shared__ SortScratch sc;
-  __shared__ float4 cand_box[2][64];
-  __shared__ float cand_area[2][64];
-  __shared__ int s_flag[64];
+  const int list = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int b = list / max(A.num_classes - 1, 1);
+  const int cnt = min(A.key_count[list], A.n);
+  const int K = min(select_and_sort(A.keys + (int64_t)list * A.n, cnt, min(A.keep_topk, cnt), s_keys, sc), A.keep_topk);
+  const int64_t o = (int64_t)list * A.keep_topk;
+  for (int r = tid; r < K; r += kSortThreads) {
+    const unsigned long long key = s_keys[r];
+    const uint32_t idx = key_index(key);
+    const NmsBox nb = nms_norm(DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx]);
+    A.s_key[o + r] = key;
+    A.s_box[o + r] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
+    A.s_area[o + r] = nb.area;
+    A.deg[o + r] = 0;
+  }
+  if (tid == 0) {
+    A.s_len[list] = K;
+    A.ovf[list] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5a: all SMs: for every candidate i the positions j < i (higher rank) with IoU(j, i) > thr, i.e. the boxes that
+// would suppress it if they are kept.  64x64 tiles of the strictly-lower triangle, kPairCtasPerList CTAs per list.
+// The relation is sparse (a detection overlaps the few other detections of the same face), so it is stored as
+// short per-candidate lists instead of a K x K bit matrix.
+// ---------------------------------------------------------------------------
+DAN_D bool pair_suppresses(const float4& a, float a_area, const float4& b, float b_area, float thr) {
+  if (thr < 0.f) return nms_suppresses(a, a_area, b, b_area, thr);
+  // boxes that do not overlap cannot exceed thr >= 0
+  const float h = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float w = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  if (!(h > 0.f && w > 0.f)) return false;
+  if (!(a_area > 0.f && b_area > 0.f)) return false;
+  const float inter = fmul(h, w);
+  const float uni = fsub(fadd(a_area, b_area), inter);
+  // inter/uni > thr decided without the division unless the ratio is within 1e-6 (relative) of the threshold
+  const float t = fmul(thr, uni);
+  if (t > 1e-30f && inter > fmul(t, 1.000001f)) return true;
+  if (t > 1e-30f && inter < fmul(t, 0.999999f)) return false;
+  return fdiv(inter, uni) > thr;
+}
+
+__global__ void __launch_bounds__(256) nms_pairs_kernel(const PpArgs A) {
+  __shared__ float4 s_cb[64];
+  __shared__ float s_ca[64];
+  const int list = blockIdx.y;
+  const int K = A.s_len[list];
+  const int nb = (K + 63) >> 6;
+  const int tiles = nb * (nb + 1) / 2;
+  const int64_t o = (int64_t)list * A.keep_topk;
+  const float4* box = A.s_box + o;
+  const float* area = A.s_area + o;
+  const int t = threadIdx.x;
+  const int r = t & 63, q = t >> 6;
+  const bool prune = A.nms_thr >= 0.f;     // boxes that do not overlap cannot exceed thr >= 0
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // row block rb (candidates i), column block cb <= rb; row block rb owns rb + 1 tiles: rb = floor((sqrt(8t+1)-1)/2)
+    int rb = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+    while (rb * (rb + 1) / 2 > tile) --rb;
+    while ((rb + 1) * (rb + 2) / 2 <= tile) ++rb;
+    const int cb = tile - rb * (rb + 1) / 2;
+    __syncthreads();
+    if (t < 64) {
+      const int j = cb * 64 + t;
+      if (j < K) { s_cb[t] = box[j]; s_ca[t] = area[j]; }
+    }
+    const int i = rb * 64 + r;
+    const bool have = i < K;
+    const float4 me = have ? box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float my_area = have ? area[i] : 0.f;
+    __syncthreads();
+    // tight branch-free loop: one bit per column that may suppress (spatial overlap); the rare exact tests and the
+    // list appends run afterwards, so that a hit in one lane does not stall the other 31 inside the loop
+    const int jmax = min(i, K) - cb * 64;            // columns c < jmax are higher ranked than i
+    unsigned bits = 0u;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = q * 16 + u;
+      const float4 kb = s_cb[c];
+      const float h = fsub(fminf(kb.z, me.z), fmaxf(kb.x, me.x));
+      const float w = fsub(fminf(kb.w, me.w), fmaxf(kb.y, me.y));
+      const bool cand = (c < jmax) & (!prune | ((h > 0.f) & (w > 0.f)));
+      bits |= (cand ? 1u : 0u) << u;
+    }
+    if (!have) bits = 0u;
+    while (__any_sync(0xffffffffu, bits != 0u)) {      // warp-uniform loop
+      if (bits != 0u) {
+        const int u = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        const int c = q * 16 + u;
+        if (pair_suppresses(s_cb[c], s_ca[c], me, my_area, A.nms_thr)) {
+          const int pos = atomicAdd(A.deg + o + i, 1);
+          if (pos < kAdjCap) A.adj[((int64_t)list * kAdjCap + pos) * A.keep_topk + i] = (uint16_t)(cb * 64 + c);
+          else A.ovf[list] = 1;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5b: one CTA per list: resolve the greedy NMS and write the zero padded outputs (bbox_util.py:80-90).
+//   Greedy NMS keeps candidate i iff none of its suppressors j < i is kept: kept(i) = !any(kept(j), j in adj(i)).
+//   The dependency graph is a DAG ordered by rank; it is evaluated by parallel relaxation: a candidate is decided
+//   as soon as one suppressor is known kept (-> suppressed) or all are known suppressed (-> kept).  The number of
+//   sweeps is the longest dependency chain (a handful for detections), not K.  Truncation at nms_topk keeps the
+//   first nms_topk kept candidates in rank order, which is what the sequential loop of TF selects.
+//   Fallback (a candidate with more than kAdjCap suppressors): rounds of 64 candidates tested on the fly against
+//   the kept list in shared memory, resolved serially per round.
+// ---------------------------------------------------------------------------
+template <bool DECODE>
+__global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs A, const float* __restrict__ src_scores,
+                                                                   const float4* __restrict__ src_boxes) {
+  extern __shared__ float4 dyn_smem[];
+  float4* kept_box = dyn_smem;                                         // [nms_cap]   (fallback)
+  float4* cand_box = kept_box + A.nms_cap;                             // [keep_topk] (fallback)
+  float* kept_area = reinterpret_cast<float*>(cand_box + A.keep_topk); // [nms_cap]   (fallback)
+  float* cand_area = kept_area + A.nms_cap;                            // [keep_topk] (fallback)
+  int32_t* kept_pos = reinterpret_cast<int32_t*>(cand_area + A.keep_topk);   // [nms_cap]
+  uint8_t* status = reinterpret_cast<uint8_t*>(kept_pos + A.nms_cap);  // [keep_topk] 0 undecided, 1 kept, 2 suppressed
+  __shared__ int s_flag[2][64];
   __shared__ unsigned long long s_rows[64];
-  __shared__ int s_kept_n;
+  __shared__ int s_new_n;
+  __shared__ int s_scan[kSortThreads / 32];
 
   const int list = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int b = list / max(A.num_classes - 1, 1);
-  const int cnt = min(A.key_count[list], A.n);
-  const int K = min(select_and_sort(A.keys + (int64_t)list * A.n, cnt, min(A.keep_topk, cnt), s_keys, sc), A.keep_topk);
+  const int K = A.s_len[list];
+  const int64_t o = (int64_t)list * A.keep_topk;
   const int nchunks = (K + 63) >> 6;
+  int kept_n = 0;
 
-  auto fetch_box = [&](int r) -> float4 {
-    const uint32_t idx = key_index(s_keys[r]);
-    return DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx];
-  };
-
-  if (tid == 0) s_kept_n = 0;
-  if (tid < 64) {
-    s_flag[tid] = 0;
-    if (tid < K) {
-      const NmsBox nb = nms_norm(fetch_box(tid));
-      cand_box[0][tid] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
-      cand_area[0][tid] = nb.area;
+  if (A.ovf[list] == 0) {
+    // ---- parallel relaxation over the suppressor lists
+    for (int i = tid; i < K; i += kSortThreads) status[i] = 0;
+    __syncthreads();
+    const uint16_t* adj = A.adj + (int64_t)list * kAdjCap * A.keep_topk;
+    // candidate i = tid + 1024*m (m < 8 since K <= kSortCap); its suppressor count stays in a register
+    int dreg[kSortCap / kSortThreads];
+#pragma unroll
+    for (int m = 0; m < kSortCap / kSortThreads; ++m) {
+      const int i = tid + m * kSortThreads;
+      dreg[m] = (i < K) ? A.deg[o + i] : 0;
     }
+    while (true) {
+      bool pending_any = false;
+#pragma unroll
+      for (int m = 0; m < kSortCap / kSortThreads; ++m) {
+        if (m * kSortThreads < K) {                     // CTA-uniform
+          const int i = tid + m * kSortThreads;
+          const bool mine = (i < K) && (status[i] == 0);
+          const int d = mine ? dreg[m] : 0;
+          const int dmax = __reduce_max_sync(0xffffffffu, d);
+          int res = 1;                                   // kept unless a suppressor says otherwise
+          for (int e0 = 0; e0 < dmax; e0 += 8) {         // warp-uniform trip count, structured body
+            int js[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)                  // 8 independent loads in flight, one L2 round trip
+              js[u] = (e0 + u < d) ? (int)adj[(int64_t)(e0 + u) * A.keep_topk + i] : -1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (js[u] >= 0) {
+                const int sj = status[js[u]];
+                res = (sj == 1) ? 2 : ((sj == 0 && res != 2) ? 0 : res);
+              }
+            }
+          }
+          if (mine) {
+            if (res != 0) status[i] = (uint8_t)res;
+            else pending_any = true;
+          }
+        }
+      }
+      if (!__syncthreads_or(pending_any ? 1 : 0)) break;
+    }
+    // ordered compaction of the kept candidates: thread t owns positions [t*E, (t+1)*E)
+    const int E = (K + kSortThreads - 1) / kSortThreads;
+    int mine_cnt = 0;
+    for (int e = 0; e < E; ++e) {
+      const int i = tid * E + e;
+      if (i < K && status[i] == 1) ++mine_cnt;
+    }
+    int incl = mine_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      if (w < warp) before += s_scan[w];
+      total += s_scan[w];
+    }
+    int pos = before + incl - mine_cnt;
+    for (int e = 0; e < E; ++e) {
+      const int i = tid * E + e;
+      if (i < K && status[i] == 1) {
+        if (pos < A.nms_topk) kept_pos[pos] = i;
+        ++pos;
+      }
+    }
+    kept_n = min(total, A.nms_topk);
+    __syncthreads();
+  } else {
+  // ---- fallback: rounds of 64 candidates against the kept list (shared memory resident)
+  for (int r = tid; r < K; r += kSortThreads) {
+    cand_box[r] = A.s_box[o + r];
+    cand_area[r] = A.s_area[o + r];
   }
+  if (tid < 128) (&s_flag[0][0])[tid] = 0;
   __syncthreads();
 
-  int kept_n = 0;
+  // Software pipeline over rounds of 64 candidates (see the kernel comment).  In round c:
+  //   S1  all warps      b: suppression bits among the candidates of round c (their flags vs the kept list are final)
+  //   S2  warp 0         c: serial resolve of round c -> appends nk boxes to the kept list
+  //       warps 1..30    a1: candidates of round c+1 vs the kept list as it was BEFORE round c
+  //   S3  all warps      a2: candidates of round c+1 vs the nk boxes round c just appended
+  const float thr = A.nms_thr;
+  auto kept_suppresses = [&](int kk, const float4& me, float my_area) -> bool {
+    return pair_suppresses(kept_box[kk], kept_area[kk], me, my_area, thr);
+  };
+
   for (int c = 0; c < nchunks; ++c) {
     const int base = c << 6;
     const int nvalid = min(64, K - base);
-    const int buf = c & 1;
-    // prefetch + decode the next round's candidates; the global loads overlap phase a
-    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool do_fetch = (tid < 64) && (base + 64 + tid < K);
-    if (do_fetch) nxt = fetch_box(base + 64 + tid);
+    const int nvalid_next = max(0, min(64, K - base - 64));
+    const float4* cur_box = cand_box + base;           // candidates of round c
+    const float* cur_area = cand_area + base;
+    const float4* nxt_box = cand_box + base + 64;      // candidates of round c+1
+    const float* nxt_area = cand_area + base + 64;
+    const int fb = c & 1, fb1 = fb ^ 1;
 
-    // ---- a. candidates vs kept list: warp w -> candidates 32*(w&1)+lane, kept slice (w>>1) of 16
-    {
-      const int i = ((warp & 1) << 5) | lane;
-      const float4 me = cand_box[buf][i];
-      const float my_area = cand_area[buf][i];
-      bool sup = (i >= nvalid);
-      for (int k = kept_n - 1 - (warp >> 1); k >= 0; k -= 16) {
-        if (!sup && nms_suppresses(kept_box[k], kept_area[k], me, my_area, A.nms_thr)) sup = true;
-        if (__all_sync(0xffffffffu, sup)) break;
-      }
-      if (sup && i < nvalid) s_flag[i] = 1;
-    }
-    __syncthreads();
-    // ---- b. suppression bits among the round's candidates: warp w -> rows 2w, 2w+1; lane -> cols lane, lane+32
-    {
+    // ---- S1 (b): warp w -> rows 2w, 2w+1; lane -> cols lane, lane+32
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = 2 * warp + rr;
-        const float4 rb = cand_box[buf][r];
-        const float ra = cand_area[buf][r];
-        const bool row_ok = (r < nvalid) && (s_flag[r] == 0);
-        const int c0 = lane, c1 = lane + 32;
-        const bool t0 = row_ok && c0 > r && c0 < nvalid && nms_suppresses(rb, ra, cand_box[buf][c0], cand_area[buf][c0], A.nms_thr);
-        const bool t1 = row_ok && c1 > r && c1 < nvalid && nms_suppresses(rb, ra, cand_box[buf][c1], cand_area[buf][c1], A.nms_thr);
-        const unsigned lo = __ballot_sync(0xffffffffu, t0);
-        const unsigned hi = __ballot_sync(0xffffffffu, t1);
-        if (lane == 0) s_rows[r] = ((unsigned long long)hi << 32) | lo;
-      }
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = 2 * warp + rr;
+      const bool row_ok = (r < nvalid) && (s_flag[fb][r] == 0);
+      const float4 rb = row_ok ? cur_box[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float ra = row_ok ? cur_area[r] : 0.f;
+      const int c0 = lane, c1 = lane + 32;
+      const bool t0 = row_ok && c0 > r && c0 < nvalid && nms_suppresses(rb, ra, cur_box[c0], cur_area[c0], thr);
+      const bool t1 = row_ok && c1 > r && c1 < nvalid && nms_suppresses(rb, ra, cur_box[c1], cur_area[c1], thr);
+      const unsigned lo = __ballot_sync(0xffffffffu, t0);
+      const unsigned hi = __ballot_sync(0xffffffffu, t1);
+      if (lane == 0) s_rows[r] = ((unsigned long long)hi << 32) | lo;
     }
     __syncthreads();
-    // ---- c. serial resolve + append (warp 0); the other warps stage the prefetched candidates
+
+    // ---- S2
     if (warp == 0) {
+      // (c) greedy resolve of the round, 32-bit halves: bit i of cl/ch set <=> candidate i / 32+i is suppressed
       const unsigned long long d0 = s_rows[lane], d1 = s_rows[lane + 32];
-      const unsigned f0 = __ballot_sync(0xffffffffu, s_flag[lane] != 0);
-      const unsigned f1 = __ballot_sync(0xffffffffu, s_flag[lane + 32] != 0);
-      const unsigned long long valid_bits = (nvalid >= 64) ? ~0ull : ((1ull << nvalid) - 1ull);
-      unsigned long long cur = (((unsigned long long)f1 << 32) | f0) | ~valid_bits;
+      const unsigned d0lo = (unsigned)d0, d0hi = (unsigned)(d0 >> 32), d1hi = (unsigned)(d1 >> 32);
+      const unsigned vlo = (nvalid >= 32) ? 0xffffffffu : ((1u << nvalid) - 1u);
+      const unsigned vhi = (nvalid >= 64) ? 0xffffffffu : ((nvalid > 32) ? ((1u << (nvalid - 32)) - 1u) : 0u);
+      unsigned cl = __ballot_sync(0xffffffffu, s_flag[fb][lane] != 0) | ~vlo;
+      unsigned ch = __ballot_sync(0xffffffffu, s_flag[fb][lane + 32] != 0) | ~vhi;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const unsigned long long row = __shfl_sync(0xffffffffu, d0, i);
-        if (!((cur >> i) & 1ull)) cur |= row;
+        const unsigned rl = __shfl_sync(0xffffffffu, d0lo, i);
+        const unsigned rh = __shfl_sync(0xffffffffu, d0hi, i);
+        const unsigned alive = ((cl >> i) & 1u) - 1u;       // all ones when candidate i survives
+        cl |= rl & alive;
+        ch |= rh & alive;
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const unsigned long long row = __shfl_sync(0xffffffffu, d1, i);
-        if (!((cur >> (32 + i)) & 1ull)) cur |= row;
+        const unsigned rh = __shfl_sync(0xffffffffu, d1hi, i);
+        const unsigned alive = ((ch >> i) & 1u) - 1u;
+        ch |= rh & alive;
       }
-      unsigned long long kept = ~cur & valid_bits;
+      unsigned long long kept = (((unsigned long long)(~ch & vhi)) << 32) | (unsigned long long)(~cl & vlo);
       int nk = __popcll(kept);
       if (kept_n + nk > A.nms_topk) {             // max_output_size reached inside the round
         int drop = kept_n + nk - A.nms_topk;
@@ -384,45 +601,79 @@ __global__ void __launch_bounds__(kSortThreads) pp_nms_kernel(const PpArgs A, co
         const int i = lane + 32 * h;
         if ((kept >> i) & 1ull) {
           const int pos = kept_n + __popcll(kept & ((1ull << i) - 1ull));
-          kept_box[pos] = cand_box[buf][i];
-          kept_area[pos] = cand_area[buf][i];
+          kept_box[pos] = cur_box[i];
+          kept_area[pos] = cur_area[i];
           kept_pos[pos] = base + i;
         }
       }
-      if (lane == 0) s_kept_n = kept_n + nk;
-      s_flag[lane] = 0;
-      s_flag[lane + 32] = 0;
-    }
-    if (do_fetch) {
-      const NmsBox nb = nms_norm(nxt);
-      cand_box[buf ^ 1][tid] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
-      cand_area[buf ^ 1][tid] = nb.area;
+      if (lane == 0) s_new_n = nk;
+      s_flag[fb][lane] = 0;          // this flag buffer is reused by round c+2
+      s_flag[fb][lane + 32] = 0;
+    } else if (warp < 31) {
+      // (a1) round c+1 vs kept[0, kept_n): warp w in 1..30 -> candidates 32*((w-1)&1)+lane, slice (w-1)>>1 of 15.
+      // The loop is kept WARP-UNIFORM (uniform trip count, structured ifs): a per-lane continue/break would let
+      // the lanes drift apart for the rest of the loop and multiply the issued instructions.
+      const int i = (((warp - 1) & 1) << 5) | lane;
+      const bool have = i < nvalid_next;
+      const float4 me = have ? nxt_box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float my_area = have ? nxt_area[i] : 0.f;
+      bool done = !(have && my_area > 0.f);
+      bool sup = false;
+      for (int k = kept_n - 1 - ((warp - 1) >> 1); k >= 0; k -= 60) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int kk = k - 15 * u;
+          if (kk >= 0 && !done && kept_suppresses(kk, me, my_area)) { sup = true; done = true; }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+      }
+      if (sup) s_flag[fb1][i] = 1;
     }
     __syncthreads();
-    kept_n = s_kept_n;
+
+    // ---- S3 (a2): round c+1 vs the boxes appended by round c: thread -> candidate tid&63, new boxes (tid>>6)+16j
+    const int nk = s_new_n;
+    if (nvalid_next > 0 && nk > 0) {
+      const int i = tid & 63;
+      const bool have = i < nvalid_next;
+      const float4 me = have ? nxt_box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float my_area = have ? nxt_area[i] : 0.f;
+      if (have && my_area > 0.f) {
+        bool sup = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = (tid >> 6) + 16 * u;
+          if (j < nk && !sup && kept_suppresses(kept_n + j, me, my_area)) sup = true;
+        }
+        if (sup) s_flag[fb1][i] = 1;
+      }
+    }
+    kept_n += nk;
+    __syncthreads();
     if (kept_n >= A.nms_topk) break;
   }
+  }   // fallback
 
   // ---- outputs, zero padded to nms_topk
   for (int t = tid; t < A.nms_topk; t += kSortThreads) {
-    const int64_t o = (int64_t)list * A.nms_topk + t;
+    const int64_t oo = (int64_t)list * A.nms_topk + t;
     if (t < kept_n) {
       const int pos = kept_pos[t];
-      const unsigned long long key = s_keys[pos];
+      const unsigned long long key = A.s_key[o + pos];
       const uint32_t idx = key_index(key);
-      A.out_scores[o] = DECODE ? key_to_score((uint32_t)(key >> 32)) : src_scores[idx];
-      A.out_boxes[o] = DECODE ? kept_box[t] : src_boxes[idx];     // clipped boxes are already min/max ordered
-      if (A.out_index != nullptr) A.out_index[o] = (int32_t)idx;
-      if (A.out_keep != nullptr) A.out_keep[o] = A.filler ? pos : (int32_t)idx;
+      A.out_scores[oo] = DECODE ? key_to_score((uint32_t)(key >> 32)) : src_scores[idx];
+      A.out_boxes[oo] = DECODE ? A.s_box[o + pos] : src_boxes[idx];     // clipped boxes are already min/max ordered
+      if (A.out_index != nullptr) A.out_index[oo] = (int32_t)idx;
+      if (A.out_keep != nullptr) A.out_keep[oo] = A.filler ? pos : (int32_t)idx;
     } else {
-      A.out_scores[o] = 0.f;
-      A.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (A.out_index != nullptr) A.out_index[o] = -1;
+      A.out_scores[oo] = 0.f;
+      A.out_boxes[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A.out_index != nullptr) A.out_index[oo] = -1;
       if (A.out_keep != nullptr) {
         // parse_by_class runs NMS on the zero padded top-k list: zero-area filler rows are never suppressed
         // and get selected until nms_topk is reached
         const int fpos = K + (t - kept_n);
-        A.out_keep[o] = (A.filler && fpos < A.keep_topk) ? fpos : -1;
+        A.out_keep[oo] = (A.filler && fpos < A.keep_topk) ? fpos : -1;
       }
     }
   }
@@ -432,17 +683,23 @@ __global__ void __launch_bounds__(kSortThreads) pp_nms_kernel(const PpArgs A, co
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-constexpr int kNmsTopkCap = 6144;   // kept list (24 B / box) + 64 KB of keys must fit in 227 KB of shared memory
 
 struct PpLayout {
-  size_t key_count, keys, total;
+  size_t key_count, s_len, ovf, keys, s_key, s_box, s_area, deg, adj, total;
 };
 
-static PpLayout pp_layout(int64_t n, int64_t lists) {
+static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk) {
   PpLayout w;
   size_t off = 0;
   w.key_count = off; off += align_up(lists * 4, 256);
+  w.s_len = off;     off += align_up(lists * 4, 256);
+  w.ovf = off;       off += align_up(lists * 4, 256);
   w.keys = off;      off += align_up(lists * n * 8, 256);
+  w.s_key = off;     off += align_up(lists * keep_topk * 8, 256);
+  w.s_box = off;     off += align_up(lists * keep_topk * 16, 256);
+  w.s_area = off;    off += align_up(lists * keep_topk * 4, 256);
+  w.deg = off;       off += align_up(lists * keep_topk * 4, 256);
+  w.adj = off;       off += align_up(lists * keep_topk * (size_t)kAdjCap * 2, 256);
   w.total = off;
   return w;
 }
@@ -450,19 +707,47 @@ static PpLayout pp_layout(int64_t n, int64_t lists) {
 static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
   char* base = static_cast<char*>(ws);
   A.key_count = reinterpret_cast<int32_t*>(base + w.key_count);
+  A.s_len = reinterpret_cast<int32_t*>(base + w.s_len);
+  A.ovf = reinterpret_cast<int32_t*>(base + w.ovf);
   A.keys = reinterpret_cast<unsigned long long*>(base + w.keys);
+  A.s_key = reinterpret_cast<unsigned long long*>(base + w.s_key);
+  A.s_box = reinterpret_cast<float4*>(base + w.s_box);
+  A.s_area = reinterpret_cast<float*>(base + w.s_area);
+  A.deg = reinterpret_cast<int32_t*>(base + w.deg);
+  A.adj = reinterpret_cast<uint16_t*>(base + w.adj);
 }
 
-static size_t nms_smem_bytes(int nms_topk) { return (size_t)kSortCap * 8 + (size_t)nms_topk * 24; }
+// resolve kernel: fallback arrays (20 B per candidate, 24 B per kept box) + kept positions + 1 status byte per candidate
+static size_t nms_smem_bytes(int nms_cap, int keep_topk) { return (size_t)nms_cap * 24 + (size_t)keep_topk * 20 + align_up((size_t)keep_topk, 16); }
+constexpr size_t kNmsSmemMax = 227 * 1024 - 8 * 1024;   // dynamic part; a few KB of static shared memory on top
 
 static int enable_big_smem() {
   static bool done = false;
   if (!done) {
     DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
-    DAN_CUDA(cudaFuncSetAttribute(pp_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes(kNmsTopkCap)));
-    DAN_CUDA(cudaFuncSetAttribute(pp_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes(kNmsTopkCap)));
+    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
+    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
+    DAN_CUDA(cudaFuncSetAttribute(nms_resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
+    DAN_CUDA(cudaFuncSetAttribute(nms_resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
     done = true;
   }
+  return DAN_OK;
+}
+
+// sort -> pairs -> resolve for `lists` lists whose keys are already in the workspace; ev (optional): 3 events recorded
+// after each kernel
+template <bool DECODE>
+static int run_sort_nms(const PpArgs& A, int lists, const float* src_scores, const float4* src_boxes, cudaStream_t st,
+                        cudaEvent_t* ev = nullptr) {
+  pp_sort_kernel<DECODE><<<lists, kSortThreads, kSortCap * 8, st>>>(A, src_boxes);
+  DAN_LAUNCH_CHECK("pp_sort_kernel");
+  if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
+  nms_pairs_kernel<<<dim3(kPairCtasPerList, lists), 256, 0, st>>>(A);
+  DAN_LAUNCH_CHECK("nms_pairs_kernel");
+  if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
+  nms_resolve_kernel<DECODE><<<lists, kSortThreads, nms_smem_bytes(A.nms_cap, A.keep_topk), st>>>(A, src_scores, src_boxes);
+  DAN_LAUNCH_CHECK("nms_resolve_kernel");
+  if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
   return DAN_OK;
 }
 
@@ -474,17 +759,17 @@ extern "C" {
 
 size_t dan_postprocess_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t num_classes, int32_t keep_topk) {
   if (num_anchors < 0 || batch < 0 || num_classes < 2 || keep_topk < 1) return 0;
-  return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1)).total;
+  return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1), keep_topk).total;
 }
 
 size_t dan_sort_workspace_bytes(int64_t n, int32_t keep_topk) {
   if (n < 0 || keep_topk < 1) return 0;
-  return pp_layout(n, 1).total;
+  return pp_layout(n, 1, 1).total;
 }
 
 size_t dan_nms_workspace_bytes(int64_t n, int32_t nms_topk) {
   if (n < 0 || nms_topk < 0) return 0;
-  return pp_layout(n, 1).total;
+  return pp_layout(n, 1, n > 0 ? n : 1).total;
 }
 
 static int postprocess_core(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
@@ -499,14 +784,16 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
               "select_threshold must be >= 0 (a negative threshold would let zero-score rows carry boxes), got %g", p->select_threshold);
   DAN_REQUIRE(p->keep_topk >= 1 && p->nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "keep_topk and nms_topk must be >= 1");
   DAN_REQUIRE(p->keep_topk <= kSortCap, DAN_ERR_UNSUPPORTED, "keep_topk %d exceeds the in-shared-memory sort capacity %d", p->keep_topk, kSortCap);
-  DAN_REQUIRE(p->nms_topk <= kNmsTopkCap, DAN_ERR_UNSUPPORTED, "nms_topk %d exceeds %d", p->nms_topk, kNmsTopkCap);
+  DAN_REQUIRE(nms_smem_bytes(p->nms_topk < p->keep_topk ? p->nms_topk : p->keep_topk, p->keep_topk) <= kNmsSmemMax, DAN_ERR_UNSUPPORTED,
+              "keep_topk %d / nms_topk %d need more than %zu bytes of shared memory (20 B per candidate + 24 B per kept box + 64 KB)",
+              p->keep_topk, p->nms_topk, kNmsSmemMax);
   DAN_REQUIRE((loc_pred != nullptr) != (boxes_pred != nullptr), DAN_ERR_INVALID_ARGUMENT, "exactly one of loc_pred / boxes_pred must be given");
   if (batch == 0) return DAN_OK;
   DAN_REQUIRE(cls_pred && out_boxes && out_scores, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
   DAN_REQUIRE(loc_pred == nullptr || (a_ymin && a_xmin && a_ymax && a_xmax), DAN_ERR_INVALID_ARGUMENT, "anchors needed to decode loc_pred");
   DAN_REQUIRE(aligned16(loc_pred) && aligned16(boxes_pred) && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "box tensors must be 16-byte aligned");
   const int lists = batch * (p->num_classes - 1);
-  const PpLayout w = pp_layout(num_anchors, lists);
+  const PpLayout w = pp_layout(num_anchors, lists, p->keep_topk);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   int rc = enable_big_smem();
@@ -527,6 +814,7 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   A.ps0 = p->prior_scaling[0]; A.ps1 = p->prior_scaling[1]; A.ps2 = p->prior_scaling[2]; A.ps3 = p->prior_scaling[3];
   A.keep_topk = p->keep_topk;
   A.nms_topk = p->nms_topk;
+  A.nms_cap = p->nms_topk < p->keep_topk ? p->nms_topk : p->keep_topk;
   A.nms_thr = p->nms_threshold;
   A.out_boxes = reinterpret_cast<float4*>(out_boxes);
   A.out_scores = out_scores;
@@ -542,10 +830,7 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
     DAN_LAUNCH_CHECK("pp_filter_kernel");
   }
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
-  pp_nms_kernel<true><<<lists, kSortThreads, nms_smem_bytes(A.nms_topk), st>>>(A, nullptr, nullptr);
-  DAN_LAUNCH_CHECK("pp_nms_kernel");
-  if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
-  return DAN_OK;
+  return run_sort_nms<true>(A, lists, nullptr, nullptr, st, ev ? ev + 2 : nullptr);
 }
 
 int dan_postprocess_batch(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
@@ -562,17 +847,17 @@ int dan_postprocess_batch_profile(const dan_postprocess_params* p, const float* 
                                   int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos, void* workspace,
                                   size_t workspace_bytes, void* stream, float* h_kernel_ms) {
   DAN_REQUIRE(h_kernel_ms != nullptr, DAN_ERR_INVALID_ARGUMENT, "h_kernel_ms is NULL");
-  h_kernel_ms[0] = h_kernel_ms[1] = 0.f;
-  cudaEvent_t ev[3];
-  for (int i = 0; i < 3; ++i) DAN_CUDA(cudaEventCreate(&ev[i]));
+  for (int i = 0; i < 4; ++i) h_kernel_ms[i] = 0.f;
+  cudaEvent_t ev[5];
+  for (int i = 0; i < 5; ++i) DAN_CUDA(cudaEventCreate(&ev[i]));
   int rc = postprocess_core(p, cls_pred, loc_pred, boxes_pred, a_ymin, a_xmin, a_ymax, a_xmax, num_anchors, batch, out_boxes,
                             out_scores, out_counts, out_anchor_index, out_keep_pos, workspace, workspace_bytes, stream, ev);
   if (rc == DAN_OK && batch > 0) {
-    cudaError_t e = cudaEventSynchronize(ev[2]);
+    cudaError_t e = cudaEventSynchronize(ev[4]);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
-    else for (int i = 0; i < 2; ++i) cudaEventElapsedTime(&h_kernel_ms[i], ev[i], ev[i + 1]);
+    else for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h_kernel_ms[i], ev[i], ev[i + 1]);
   }
-  for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+  for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
   return rc;
 }
 
@@ -582,7 +867,7 @@ int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t 
   DAN_REQUIRE(keep_topk <= kSortCap || n <= kSortCap, DAN_ERR_UNSUPPORTED, "min(keep_topk, n) exceeds the sort capacity %d", kSortCap);
   DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
   DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
-  const PpLayout w = pp_layout(n, 1);
+  const PpLayout w = pp_layout(n, 1, 1);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   int rc = enable_big_smem();
@@ -606,10 +891,13 @@ int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t 
 int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t nms_topk, float nms_threshold, float* out_scores,
                    float* out_boxes, int32_t* out_keep, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
   DAN_REQUIRE(n >= 0 && nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "bad size");
-  DAN_REQUIRE(n <= kSortCap && nms_topk <= kNmsTopkCap, DAN_ERR_UNSUPPORTED, "n > %d or nms_topk > %d", kSortCap, kNmsTopkCap);
+  const int n_eff = n > 0 ? (int)(n < kSortCap ? n : kSortCap) : 1;
+  const int cap = nms_topk < n_eff ? nms_topk : n_eff;
+  DAN_REQUIRE(n <= kSortCap && nms_smem_bytes(cap, n_eff) <= kNmsSmemMax, DAN_ERR_UNSUPPORTED,
+              "n %lld (max %d) / nms_topk %d need more than %zu bytes of shared memory", (long long)n, kSortCap, nms_topk, kNmsSmemMax);
   DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
   DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
-  const PpLayout w = pp_layout(n, 1);
+  const PpLayout w = pp_layout(n, 1, n_eff);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   int rc = enable_big_smem();
@@ -618,8 +906,9 @@ int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t n
   PpArgs A = {};
   A.n = (int)n;
   A.num_classes = 2;
-  A.keep_topk = n > 0 ? (int)n : 1;
+  A.keep_topk = n_eff;
   A.nms_topk = nms_topk;
+  A.nms_cap = cap;
   A.nms_thr = nms_threshold;
   A.out_boxes = reinterpret_cast<float4*>(out_boxes);
   A.out_scores = out_scores;
@@ -630,9 +919,7 @@ int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t n
   pp_bind(A, workspace, w);
   key_build_kernel<<<grid_for(n), 256, 0, st>>>(scores, n, A.keys, A.key_count);
   DAN_LAUNCH_CHECK("key_build_kernel");
-  pp_nms_kernel<false><<<1, kSortThreads, nms_smem_bytes(nms_topk), st>>>(A, scores, reinterpret_cast<const float4*>(boxes));
-  DAN_LAUNCH_CHECK("pp_nms_kernel");
-  return DAN_OK;
+  return run_sort_nms<false>(A, 1, scores, reinterpret_cast<const float4*>(boxes), st);
 }
 
 }  // extern "C"

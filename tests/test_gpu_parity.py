@@ -413,6 +413,23 @@ def test_nms_bboxes_vs_oracle(cuda, oracle, n, topk, thr):
     np.testing.assert_array_equal(_np(vb), boxes[rk])
 
 
+def test_nms_dense_cluster_uses_fallback(cuda, oracle):
+    """hundreds of mutually overlapping boxes: candidates have more than 64 suppressors, which switches the resolve
+    kernel from the suppressor-list relaxation to its round-based fallback; both must give TF's greedy result."""
+    from dan_b200.utility import bbox_util as bu
+    rng = np.random.default_rng(31)
+    for n, topk, thr in ((400, 750, 0.3), (1500, 100, 0.5), (3000, 750, 0.3)):
+        c = np.array([[300., 300.]]) + rng.normal(0, 12, (n, 2))
+        c[n // 2:] = rng.uniform(50, 600, (n - n // 2, 2))          # half in one dense cluster, half scattered
+        wh = rng.uniform(60, 90, (n, 2))
+        boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        scores = rng.permutation(n).astype(np.float32) / n
+        rs, rb, rk = oracle.nms_bboxes_with_padding(scores, boxes, topk, thr)
+        gs, gb = bu.nms_bboxes_with_padding(to_dev(scores, cuda), to_dev(boxes, cuda), topk, thr)
+        np.testing.assert_array_equal(_np(gs), rs)
+        np.testing.assert_array_equal(_np(gb), rb)
+
+
 def test_nms_score_ties_are_stable(cuda, oracle):
     """documented tie policy T6: equal scores keep input order (oracle tie='stable')."""
     from dan_b200 import functional as F
