@@ -25,8 +25,6 @@ namespace dan {
 
 constexpr int kSortCap = 8192;      // keys sorted in shared memory (64 KB)
 constexpr int kSortThreads = 1024;
-constexpr int kAdjCap = 64;        // suppressor list capacity per candidate
-constexpr int kPairCtasPerList = 32;
 
 
 DAN_D uint32_t score_to_key(float s) { return (uint32_t)float_to_ordered(s) ^ 0x80000000u; }
@@ -54,14 +52,19 @@ struct PpArgs {
   float* s_scores;            // sort_bboxes outputs [keep_topk]
   float4* s_boxes;
   int32_t* s_index;
-  // sorted candidates (sort kernel -> pairs kernel -> resolve kernel), per list
+  // per list, written by the sort kernel, read by the pair and resolve kernels (all L2 resident)
   unsigned long long* s_key;  // [L, keep_topk] sorted keys
-  float4* s_box;              // [L, keep_topk] normalised corners (y0, x0, y1, x1)
+  float4* s_box;              // [L, keep_topk] normalised corners (y0, x0, y1, x1), rank order
   float* s_area;              // [L, keep_topk] (y1-y0)*(x1-x0)
   int32_t* s_len;             // [L] number of sorted candidates K
-  int32_t* deg;               // [L, keep_topk] number of higher-ranked boxes that suppress candidate i
-  uint16_t* adj;              // [L, kAdjCap, keep_topk] their positions
-  int32_t* ovf;               // [L] some candidate has more than kAdjCap suppressors -> round-based fallback
+  float4* grid_info;          // [L] (origin y, origin x, extent, bit mask of the non-empty size classes)
+  float* class_amin;          // [L, 16] smallest box area per size class (IoU <= area ratio: whole classes are skipped)
+  uint16_t* box_cell;         // [L, keep_topk] flattened (class, cy, cx) of each box, 0xffff = not binned
+  uint16_t* cell_start;       // [L, kTotalCells + 1]
+  uint16_t* cell_items;       // [L, keep_topk] ranks grouped by cell
+  uint32_t* edges;            // [L, kEdgeCap] (hi << 16 | lo): lo suppresses hi when lo is kept
+  int32_t* edge_n;            // [L]
+  int32_t* ovf;               // [L] edge list overflow / negative threshold -> round-based fallback
   // outputs
   float4* out_boxes;
   float* out_scores;
@@ -268,19 +271,23 @@ __global__ void __launch_bounds__(kSortThreads) topk_sort_kernel(const PpArgs A,
 }
 
 // ---------------------------------------------------------------------------
-// K4+K5 fused: one CTA per (image, class) list.
-//   1. top-k select + sort of the surviving keys in shared memory (above)
-//   2. greedy NMS with tf.image.non_max_suppression's IoU (no +1, corners min/max normalised, area<=0 never
-//      suppresses, strict >), 64 candidates per round:
-//        a. all warps test the 64 candidates against the boxes kept so far (kept list lives in shared memory,
-//           newest first like TF's inner loop; the result does not depend on the order)
-//        b. all warps build the 64x64 suppression bits among the candidates (ballots, no atomics)
-//        c. warp 0 resolves the round serially with a register/shuffle sweep (bit i of `cur` = candidate i is
-//           suppressed), truncates at nms_topk and appends the survivors to the kept list
-//      Only the rows of KEPT boxes are ever evaluated, so ~K*kept/2 IoU tests instead of K*K/2, no K x K bit
-//      matrix in HBM, and no dependent global loads on the serial path: the next round's candidate boxes are
-//      fetched (and decoded) while the current round is being tested.
-//   3. zero padded outputs (bbox_util.py:80-90).
+// K4+K5: one CTA per (image, class) list does everything after the filter:
+//   1. top-k select + sort of the surviving keys in shared memory (select_and_sort above);
+//   2. decode + clip + normalise the K best boxes into shared memory;
+//   3. broad phase: boxes are binned by size class (max side in [2^c, 2^(c+1))) and by the cell of their centre in a
+//      per-class uniform grid whose cell is as large as the class's boxes, so that a box only has to look at <= 3x3
+//      cells per class to find everything it can overlap (counting sort in shared memory);
+//   4. narrow phase: tf.image.non_max_suppression's IoU test (no +1, corners min/max normalised, area <= 0 never
+//      suppresses, strict >) on those few candidates; every pair (lo, hi) with lo ranked above hi and IoU > thr
+//      becomes an edge "lo suppresses hi if lo is kept".  ~K*6 edges instead of K*K/2 tests;
+//   5. greedy NMS == evaluation of the DAG  kept(i) = !any(kept(j) : edge j -> i)  in rank order.  It is evaluated by
+//      parallel relaxation over the edges: a box is decided as soon as one suppressor is known kept (suppressed) or
+//      all of them are known suppressed (kept).  The number of sweeps is the longest dependency chain (6 for the
+//      benchmark detections), not K;
+//   6. the first nms_topk kept boxes in rank order are written out, zero padded (bbox_util.py:80-90); this is what
+//      TF's sequential loop selects because a decision never depends on lower ranked boxes.
+// Fallback (more edges than fit, or a negative threshold where even disjoint boxes suppress): rounds of 64
+// candidates tested against the kept list in shared memory, resolved serially per round (nms_rounds below).
 // ---------------------------------------------------------------------------
 struct NmsBox {
   float y0, x0, y1, x1, area;
@@ -306,251 +313,99 @@ DAN_D bool nms_suppresses(float4 a, float a_area, float4 b, float b_area, float 
   return fdiv(inter, fsub(fadd(a_area, b_area), inter)) > thr;
 }
 
-// ---------------------------------------------------------------------------
-// K4: one CTA per list: top-k select + sort, then decode + clip + normalise the K best boxes (sorted order) to HBM
-// ---------------------------------------------------------------------------
-template <bool DECODE>
-__global__ void __launch_bounds__(kSortThreads) pp_sort_kernel(const PpArgs A, const float4* __restrict__ src_boxes) {
-  extern __shared__ unsigned long long s_keys[];             // [kSortCap]
-  __shared__ SortScratch sc;
-  const int list = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int b = list / max(A.num_classes - 1, 1);
-  const int cnt = min(A.key_count[list], A.n);
-  const int K = min(select_and_sort(A.keys + (int64_t)list * A.n, cnt, min(A.keep_topk, cnt), s_keys, sc), A.keep_topk);
-  const int64_t o = (int64_t)list * A.keep_topk;
-  for (int r = tid; r < K; r += kSortThreads) {
-    const unsigned long long key = s_keys[r];
-    const uint32_t idx = key_index(key);
-    const NmsBox nb = nms_norm(DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx]);
-    A.s_key[o + r] = key;
-    A.s_box[o + r] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
-    A.s_area[o + r] = nb.area;
-    A.deg[o + r] = 0;
-  }
-  if (tid == 0) {
-    A.s_len[list] = K;
-    A.ovf[list] = 0;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// K5a: all SMs: for every candidate i the positions j < i (higher rank) with IoU(j, i) > thr, i.e. the boxes that
-// would suppress it if they are kept.  64x64 tiles of the strictly-lower triangle, kPairCtasPerList CTAs per list.
-// The relation is sparse (a detection overlaps the few other detections of the same face), so it is stored as
-// short per-candidate lists instead of a K x K bit matrix.
-// ---------------------------------------------------------------------------
+// same predicate; for thr >= 0 disjoint boxes are rejected first and the division is only evaluated when
+// inter / union is within 1e-6 (relative) of the threshold
 DAN_D bool pair_suppresses(const float4& a, float a_area, const float4& b, float b_area, float thr) {
   if (thr < 0.f) return nms_suppresses(a, a_area, b, b_area, thr);
-  // boxes that do not overlap cannot exceed thr >= 0
   const float h = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
   const float w = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
   if (!(h > 0.f && w > 0.f)) return false;
   if (!(a_area > 0.f && b_area > 0.f)) return false;
   const float inter = fmul(h, w);
   const float uni = fsub(fadd(a_area, b_area), inter);
-  // inter/uni > thr decided without the division unless the ratio is within 1e-6 (relative) of the threshold
   const float t = fmul(thr, uni);
   if (t > 1e-30f && inter > fmul(t, 1.000001f)) return true;
   if (t > 1e-30f && inter < fmul(t, 0.999999f)) return false;
   return fdiv(inter, uni) > thr;
 }
 
-__global__ void __launch_bounds__(256) nms_pairs_kernel(const PpArgs A) {
-  __shared__ float4 s_cb[64];
-  __shared__ float s_ca[64];
-  const int list = blockIdx.y;
-  const int K = A.s_len[list];
-  const int nb = (K + 63) >> 6;
-  const int tiles = nb * (nb + 1) / 2;
-  const int64_t o = (int64_t)list * A.keep_topk;
-  const float4* box = A.s_box + o;
-  const float* area = A.s_area + o;
-  const int t = threadIdx.x;
-  const int r = t & 63, q = t >> 6;
-  const bool prune = A.nms_thr >= 0.f;     // boxes that do not overlap cannot exceed thr >= 0
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    // row block rb (candidates i), column block cb <= rb; row block rb owns rb + 1 tiles: rb = floor((sqrt(8t+1)-1)/2)
-    int rb = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
-    while (rb * (rb + 1) / 2 > tile) --rb;
-    while ((rb + 1) * (rb + 2) / 2 <= tile) ++rb;
-    const int cb = tile - rb * (rb + 1) / 2;
-    __syncthreads();
-    if (t < 64) {
-      const int j = cb * 64 + t;
-      if (j < K) { s_cb[t] = box[j]; s_ca[t] = area[j]; }
-    }
-    const int i = rb * 64 + r;
-    const bool have = i < K;
-    const float4 me = have ? box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float my_area = have ? area[i] : 0.f;
-    __syncthreads();
-    // tight branch-free loop: one bit per column that may suppress (spatial overlap); the rare exact tests and the
-    // list appends run afterwards, so that a hit in one lane does not stall the other 31 inside the loop
-    const int jmax = min(i, K) - cb * 64;            // columns c < jmax are higher ranked than i
-    unsigned bits = 0u;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int c = q * 16 + u;
-      const float4 kb = s_cb[c];
-      const float h = fsub(fminf(kb.z, me.z), fmaxf(kb.x, me.x));
-      const float w = fsub(fminf(kb.w, me.w), fmaxf(kb.y, me.y));
-      const bool cand = (c < jmax) & (!prune | ((h > 0.f) & (w > 0.f)));
-      bits |= (cand ? 1u : 0u) << u;
-    }
-    if (!have) bits = 0u;
-    while (__any_sync(0xffffffffu, bits != 0u)) {      // warp-uniform loop
-      if (bits != 0u) {
-        const int u = __ffs(bits) - 1;
-        bits &= bits - 1u;
-        const int c = q * 16 + u;
-        if (pair_suppresses(s_cb[c], s_ca[c], me, my_area, A.nms_thr)) {
-          const int pos = atomicAdd(A.deg + o + i, 1);
-          if (pos < kAdjCap) A.adj[((int64_t)list * kAdjCap + pos) * A.keep_topk + i] = (uint16_t)(cb * 64 + c);
-          else A.ovf[list] = 1;
-        }
-      }
-    }
+constexpr int kNmsClasses = 10;                                    // class 9: max side >= 512, one cell
+constexpr int kGridDim = 24;                                       // cells per dimension and class
+constexpr int kCellsPerClass = kGridDim * kGridDim;
+constexpr int kTotalCells = kNmsClasses * kCellsPerClass;
+constexpr int kEdgeCap = 1 << 18;                                  // suppression edges per list (1 MB)
+
+// geometry of the per-class grids of one list
+struct GridGeom {
+  float oy, ox, extent;
+  DAN_D float cell_size(int c) const { return fmaxf((float)(2 << c), extent * (1.f / (kGridDim - 1))); }
+  DAN_D static int cell_of(float v, float org, float inv) {
+    const int q = (int)((v - org) * inv);
+    return min(max(q, 0), kGridDim - 1);
   }
+};
+
+// shared memory of the resolve kernel
+struct NmsSmem {
+  float4* kept_box;      // [nms_cap]   (fallback)
+  float* kept_area;      // [nms_cap]   (fallback)
+  float4* cand_box;      // [keep_topk] (fallback)
+  float* cand_area;      // [keep_topk] (fallback)
+  uint8_t* status;       // [keep_topk] 0 undecided, 1 kept, 2 suppressed
+  uint8_t* pending;      // [keep_topk]
+  int32_t* kept_pos;     // [nms_cap]
+};
+
+static size_t nms_smem_bytes(int nms_cap, int keep_topk) {
+  return (size_t)nms_cap * 20 + (size_t)keep_topk * 20 + align_up((size_t)keep_topk, 16) * 2 + align_up((size_t)nms_cap * 4, 16);
+}
+constexpr size_t kNmsSmemMax = 227 * 1024 - 6 * 1024;   // dynamic part; a few KB of static shared memory on top
+constexpr size_t kSortSmem = (size_t)kSortCap * 8;       // sort kernel: keys, then (aliased) the cell counters
+
+DAN_D NmsSmem nms_carve(unsigned char* base, int nms_cap, int keep_topk) {
+  NmsSmem m;
+  unsigned char* p = base;
+  m.kept_box = reinterpret_cast<float4*>(p); p += (size_t)nms_cap * 16;
+  m.cand_box = reinterpret_cast<float4*>(p); p += (size_t)keep_topk * 16;
+  m.kept_area = reinterpret_cast<float*>(p); p += (size_t)nms_cap * 4;
+  m.cand_area = reinterpret_cast<float*>(p); p += (size_t)keep_topk * 4;
+  m.status = p; p += ((size_t)keep_topk + 15) / 16 * 16;
+  m.pending = p; p += ((size_t)keep_topk + 15) / 16 * 16;
+  m.kept_pos = reinterpret_cast<int32_t*>(p);
+  return m;
 }
 
-// ---------------------------------------------------------------------------
-// K5b: one CTA per list: resolve the greedy NMS and write the zero padded outputs (bbox_util.py:80-90).
-//   Greedy NMS keeps candidate i iff none of its suppressors j < i is kept: kept(i) = !any(kept(j), j in adj(i)).
-//   The dependency graph is a DAG ordered by rank; it is evaluated by parallel relaxation: a candidate is decided
-//   as soon as one suppressor is known kept (-> suppressed) or all are known suppressed (-> kept).  The number of
-//   sweeps is the longest dependency chain (a handful for detections), not K.  Truncation at nms_topk keeps the
-//   first nms_topk kept candidates in rank order, which is what the sequential loop of TF selects.
-//   Fallback (a candidate with more than kAdjCap suppressors): rounds of 64 candidates tested on the fly against
-//   the kept list in shared memory, resolved serially per round.
-// ---------------------------------------------------------------------------
-template <bool DECODE>
-__global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs A, const float* __restrict__ src_scores,
-                                                                   const float4* __restrict__ src_boxes) {
-  extern __shared__ float4 dyn_smem[];
-  float4* kept_box = dyn_smem;                                         // [nms_cap]   (fallback)
-  float4* cand_box = kept_box + A.nms_cap;                             // [keep_topk] (fallback)
-  float* kept_area = reinterpret_cast<float*>(cand_box + A.keep_topk); // [nms_cap]   (fallback)
-  float* cand_area = kept_area + A.nms_cap;                            // [keep_topk] (fallback)
-  int32_t* kept_pos = reinterpret_cast<int32_t*>(cand_area + A.keep_topk);   // [nms_cap]
-  uint8_t* status = reinterpret_cast<uint8_t*>(kept_pos + A.nms_cap);  // [keep_topk] 0 undecided, 1 kept, 2 suppressed
+// ---- fallback: rounds of 64 candidates against the kept list.  In round c:
+//   S1  all warps      suppression bits among the candidates of round c (their flags vs the kept list are final)
+//   S2  warp 0         serial resolve of round c -> appends nk boxes to the kept list
+//       warps 1..30    candidates of round c+1 vs the kept list as it was BEFORE round c
+//   S3  all warps      candidates of round c+1 vs the nk boxes round c just appended
+// Returns the number of kept boxes; their positions are in m.kept_pos.
+DAN_D int nms_rounds(const NmsSmem& m, int K, int nms_topk, float thr) {
   __shared__ int s_flag[2][64];
   __shared__ unsigned long long s_rows[64];
   __shared__ int s_new_n;
-  __shared__ int s_scan[kSortThreads / 32];
-
-  const int list = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int K = A.s_len[list];
-  const int64_t o = (int64_t)list * A.keep_topk;
   const int nchunks = (K + 63) >> 6;
-  int kept_n = 0;
-
-  if (A.ovf[list] == 0) {
-    // ---- parallel relaxation over the suppressor lists
-    for (int i = tid; i < K; i += kSortThreads) status[i] = 0;
-    __syncthreads();
-    const uint16_t* adj = A.adj + (int64_t)list * kAdjCap * A.keep_topk;
-    // candidate i = tid + 1024*m (m < 8 since K <= kSortCap); its suppressor count stays in a register
-    int dreg[kSortCap / kSortThreads];
-#pragma unroll
-    for (int m = 0; m < kSortCap / kSortThreads; ++m) {
-      const int i = tid + m * kSortThreads;
-      dreg[m] = (i < K) ? A.deg[o + i] : 0;
-    }
-    while (true) {
-      bool pending_any = false;
-#pragma unroll
-      for (int m = 0; m < kSortCap / kSortThreads; ++m) {
-        if (m * kSortThreads < K) {                     // CTA-uniform
-          const int i = tid + m * kSortThreads;
-          const bool mine = (i < K) && (status[i] == 0);
-          const int d = mine ? dreg[m] : 0;
-          const int dmax = __reduce_max_sync(0xffffffffu, d);
-          int res = 1;                                   // kept unless a suppressor says otherwise
-          for (int e0 = 0; e0 < dmax; e0 += 8) {         // warp-uniform trip count, structured body
-            int js[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)                  // 8 independent loads in flight, one L2 round trip
-              js[u] = (e0 + u < d) ? (int)adj[(int64_t)(e0 + u) * A.keep_topk + i] : -1;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (js[u] >= 0) {
-                const int sj = status[js[u]];
-                res = (sj == 1) ? 2 : ((sj == 0 && res != 2) ? 0 : res);
-              }
-            }
-          }
-          if (mine) {
-            if (res != 0) status[i] = (uint8_t)res;
-            else pending_any = true;
-          }
-        }
-      }
-      if (!__syncthreads_or(pending_any ? 1 : 0)) break;
-    }
-    // ordered compaction of the kept candidates: thread t owns positions [t*E, (t+1)*E)
-    const int E = (K + kSortThreads - 1) / kSortThreads;
-    int mine_cnt = 0;
-    for (int e = 0; e < E; ++e) {
-      const int i = tid * E + e;
-      if (i < K && status[i] == 1) ++mine_cnt;
-    }
-    int incl = mine_cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
-    }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < kSortThreads / 32; ++w) {
-      if (w < warp) before += s_scan[w];
-      total += s_scan[w];
-    }
-    int pos = before + incl - mine_cnt;
-    for (int e = 0; e < E; ++e) {
-      const int i = tid * E + e;
-      if (i < K && status[i] == 1) {
-        if (pos < A.nms_topk) kept_pos[pos] = i;
-        ++pos;
-      }
-    }
-    kept_n = min(total, A.nms_topk);
-    __syncthreads();
-  } else {
-  // ---- fallback: rounds of 64 candidates against the kept list (shared memory resident)
-  for (int r = tid; r < K; r += kSortThreads) {
-    cand_box[r] = A.s_box[o + r];
-    cand_area[r] = A.s_area[o + r];
-  }
+  float4* kept_box = m.kept_box;
+  float* kept_area = m.kept_area;
+  const float4* cand_box = m.cand_box;
+  const float* cand_area = m.cand_area;
   if (tid < 128) (&s_flag[0][0])[tid] = 0;
   __syncthreads();
-
-  // Software pipeline over rounds of 64 candidates (see the kernel comment).  In round c:
-  //   S1  all warps      b: suppression bits among the candidates of round c (their flags vs the kept list are final)
-  //   S2  warp 0         c: serial resolve of round c -> appends nk boxes to the kept list
-  //       warps 1..30    a1: candidates of round c+1 vs the kept list as it was BEFORE round c
-  //   S3  all warps      a2: candidates of round c+1 vs the nk boxes round c just appended
-  const float thr = A.nms_thr;
-  auto kept_suppresses = [&](int kk, const float4& me, float my_area) -> bool {
-    return pair_suppresses(kept_box[kk], kept_area[kk], me, my_area, thr);
-  };
-
+  int kept_n = 0;
   for (int c = 0; c < nchunks; ++c) {
     const int base = c << 6;
     const int nvalid = min(64, K - base);
     const int nvalid_next = max(0, min(64, K - base - 64));
-    const float4* cur_box = cand_box + base;           // candidates of round c
+    const float4* cur_box = cand_box + base;
     const float* cur_area = cand_area + base;
-    const float4* nxt_box = cand_box + base + 64;      // candidates of round c+1
+    const float4* nxt_box = cand_box + base + 64;
     const float* nxt_area = cand_area + base + 64;
     const int fb = c & 1, fb1 = fb ^ 1;
-
-    // ---- S1 (b): warp w -> rows 2w, 2w+1; lane -> cols lane, lane+32
+    // ---- S1: warp w -> rows 2w, 2w+1; lane -> cols lane, lane+32
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const int r = 2 * warp + rr;
@@ -565,10 +420,9 @@ __global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs 
       if (lane == 0) s_rows[r] = ((unsigned long long)hi << 32) | lo;
     }
     __syncthreads();
-
     // ---- S2
     if (warp == 0) {
-      // (c) greedy resolve of the round, 32-bit halves: bit i of cl/ch set <=> candidate i / 32+i is suppressed
+      // greedy resolve of the round, 32-bit halves: bit i of cl/ch set <=> candidate i / 32+i is suppressed
       const unsigned long long d0 = s_rows[lane], d1 = s_rows[lane + 32];
       const unsigned d0lo = (unsigned)d0, d0hi = (unsigned)(d0 >> 32), d1hi = (unsigned)(d1 >> 32);
       const unsigned vlo = (nvalid >= 32) ? 0xffffffffu : ((1u << nvalid) - 1u);
@@ -591,10 +445,10 @@ __global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs 
       }
       unsigned long long kept = (((unsigned long long)(~ch & vhi)) << 32) | (unsigned long long)(~cl & vlo);
       int nk = __popcll(kept);
-      if (kept_n + nk > A.nms_topk) {             // max_output_size reached inside the round
-        int drop = kept_n + nk - A.nms_topk;
+      if (kept_n + nk > nms_topk) {             // max_output_size reached inside the round
+        int drop = kept_n + nk - nms_topk;
         while (drop-- > 0) kept &= ~(1ull << (63 - __clzll((long long)kept)));
-        nk = A.nms_topk - kept_n;
+        nk = nms_topk - kept_n;
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -603,14 +457,14 @@ __global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs 
           const int pos = kept_n + __popcll(kept & ((1ull << i) - 1ull));
           kept_box[pos] = cur_box[i];
           kept_area[pos] = cur_area[i];
-          kept_pos[pos] = base + i;
+          m.kept_pos[pos] = base + i;
         }
       }
       if (lane == 0) s_new_n = nk;
       s_flag[fb][lane] = 0;          // this flag buffer is reused by round c+2
       s_flag[fb][lane + 32] = 0;
     } else if (warp < 31) {
-      // (a1) round c+1 vs kept[0, kept_n): warp w in 1..30 -> candidates 32*((w-1)&1)+lane, slice (w-1)>>1 of 15.
+      // round c+1 vs kept[0, kept_n): warp w in 1..30 -> candidates 32*((w-1)&1)+lane, slice (w-1)>>1 of 15.
       // The loop is kept WARP-UNIFORM (uniform trip count, structured ifs): a per-lane continue/break would let
       // the lanes drift apart for the rest of the loop and multiply the issued instructions.
       const int i = (((warp - 1) & 1) << 5) | lane;
@@ -623,15 +477,14 @@ __global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int kk = k - 15 * u;
-          if (kk >= 0 && !done && kept_suppresses(kk, me, my_area)) { sup = true; done = true; }
+          if (kk >= 0 && !done && pair_suppresses(kept_box[kk], kept_area[kk], me, my_area, thr)) { sup = true; done = true; }
         }
         if (__all_sync(0xffffffffu, done)) break;
       }
       if (sup) s_flag[fb1][i] = 1;
     }
     __syncthreads();
-
-    // ---- S3 (a2): round c+1 vs the boxes appended by round c: thread -> candidate tid&63, new boxes (tid>>6)+16j
+    // ---- S3: round c+1 vs the boxes appended by round c: thread -> candidate tid&63, new boxes (tid>>6)+16j
     const int nk = s_new_n;
     if (nvalid_next > 0 && nk > 0) {
       const int i = tid & 63;
@@ -643,22 +496,351 @@ __global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = (tid >> 6) + 16 * u;
-          if (j < nk && !sup && kept_suppresses(kept_n + j, me, my_area)) sup = true;
+          if (j < nk && !sup && pair_suppresses(kept_box[kept_n + j], kept_area[kept_n + j], me, my_area, thr)) sup = true;
         }
         if (sup) s_flag[fb1][i] = 1;
       }
     }
     kept_n += nk;
     __syncthreads();
-    if (kept_n >= A.nms_topk) break;
+    if (kept_n >= nms_topk) break;
   }
-  }   // fallback
+  return kept_n;
+}
+
+// block-wide min / max of a float over all threads (every thread gets the result)
+DAN_D void block_minmax(float lo, float hi, float& out_lo, float& out_hi) {
+  __shared__ int s_lo[kSortThreads / 32], s_hi[kSortThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wl = __reduce_min_sync(0xffffffffu, float_to_ordered(lo));
+  const int wh = __reduce_max_sync(0xffffffffu, float_to_ordered(hi));
+  if (lane == 0) { s_lo[warp] = wl; s_hi[warp] = wh; }
+  __syncthreads();
+  int a = s_lo[lane], b = s_hi[lane];
+  a = __reduce_min_sync(0xffffffffu, a);
+  b = __reduce_max_sync(0xffffffffu, b);
+  out_lo = ordered_to_float(a);
+  out_hi = ordered_to_float(b);
+  __syncthreads();
+}
+
+// ---- kernel S: one CTA per list: top-k + sort, decode, broad-phase grid (steps 1-3) -> HBM (L2 resident)
+template <bool DECODE>
+__global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A, const float4* __restrict__ src_boxes) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dyn_smem);
+  int* cell_cnt = reinterpret_cast<int*>(dyn_smem);            // aliases the keys once they are in HBM
+  __shared__ SortScratch sc;
+  __shared__ int s_scan[kSortThreads / 32];
+  __shared__ int s_class_mask;
+  __shared__ int s_class_amin[kNmsClasses];
+
+  const int list = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int b = list / max(A.num_classes - 1, 1);
+  const int cnt = min(A.key_count[list], A.n);
+  const int64_t o = (int64_t)list * A.keep_topk;
+
+  const int K = min(select_and_sort(A.keys + (int64_t)list * A.n, cnt, min(A.keep_topk, cnt), keys, sc), A.keep_topk);
+  float ylo = 3.0e38f, yhi = -3.0e38f, xlo = 3.0e38f, xhi = -3.0e38f;
+  for (int r = tid; r < K; r += kSortThreads) {
+    const unsigned long long key = keys[r];
+    const uint32_t idx = key_index(key);
+    A.s_key[o + r] = key;
+    const NmsBox nb = nms_norm(DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx]);
+    A.s_box[o + r] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
+    A.s_area[o + r] = nb.area;
+    if (nb.area > 0.f) {
+      ylo = fminf(ylo, nb.y0); yhi = fmaxf(yhi, nb.y1);
+      xlo = fminf(xlo, nb.x0); xhi = fmaxf(xhi, nb.x1);
+    }
+  }
+  if (tid == 0) s_class_mask = 0;
+  if (tid < kNmsClasses) s_class_amin[tid] = 0x7f7fffff;     // FLT_MAX as ordered int (areas are positive)
+  GridGeom g;
+  float ey, ex;
+  block_minmax(ylo, yhi, g.oy, ey);      // (contains barriers: the keys are dead from here on)
+  block_minmax(xlo, xhi, g.ox, ex);
+  g.extent = fmaxf(fmaxf(ey - g.oy, ex - g.ox), 1.f);
+
+  for (int i = tid; i < kTotalCells; i += kSortThreads) cell_cnt[i] = 0;
+  __syncthreads();
+  uint16_t* box_cell = A.box_cell + o;
+  for (int i = tid; i < K; i += kSortThreads) {
+    const float4 bx = A.s_box[o + i];
+    int cid = 0xffff;
+    if (A.s_area[o + i] > 0.f) {
+      const float side = fmaxf(bx.z - bx.x, bx.w - bx.y);
+      const int c = (side < 1.f) ? 0 : min(kNmsClasses - 1, (int)((__float_as_uint(side) >> 23) & 255u) - 127);
+      if (c == kNmsClasses - 1) {
+        cid = c * kCellsPerClass;
+      } else {
+        const float inv = 1.f / g.cell_size(c);
+        cid = c * kCellsPerClass + GridGeom::cell_of(0.5f * (bx.x + bx.z), g.oy, inv) * kGridDim +
+              GridGeom::cell_of(0.5f * (bx.y + bx.w), g.ox, inv);
+      }
+      atomicAdd(&cell_cnt[cid], 1);
+      atomicOr(&s_class_mask, 1 << c);
+      atomicMin(&s_class_amin[c], __float_as_int(A.s_area[o + i]));
+    }
+    box_cell[i] = (uint16_t)cid;
+  }
+  __syncthreads();
+  uint16_t* cell_start = A.cell_start + (int64_t)list * (kTotalCells + 1);
+  {  // exclusive scan of the cell counters: consecutive cells per thread
+    constexpr int per = (kTotalCells + kSortThreads - 1) / kSortThreads;
+    int local[per];
+    int sum = 0;
+#pragma unroll
+    for (int e = 0; e < per; ++e) {
+      const int cidx = tid * per + e;
+      local[e] = (cidx < kTotalCells) ? cell_cnt[cidx] : 0;
+      sum += local[e];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_scan[w];
+    int run = before + incl - sum;
+#pragma unroll
+    for (int e = 0; e < per; ++e) {
+      const int cidx = tid * per + e;
+      if (cidx < kTotalCells) {
+        cell_start[cidx] = (uint16_t)run;
+        cell_cnt[cidx] = run;          // becomes the scatter cursor
+        run += local[e];
+      }
+    }
+    if (tid == kSortThreads - 1) cell_start[kTotalCells] = (uint16_t)run;
+  }
+  __syncthreads();
+  uint16_t* cell_items = A.cell_items + o;
+  for (int i = tid; i < K; i += kSortThreads) {
+    const int cid = box_cell[i];
+    if (cid != 0xffff) cell_items[atomicAdd(&cell_cnt[cid], 1)] = (uint16_t)i;
+  }
+  if (tid == 0) {
+    A.s_len[list] = K;
+    A.grid_info[list] = make_float4(g.oy, g.ox, g.extent, __int_as_float(s_class_mask));
+    A.edge_n[list] = 0;
+    A.ovf[list] = (A.nms_thr < 0.f) ? 1 : 0;     // disjoint boxes suppress too: no spatial pruning possible
+  }
+  if (tid < kNmsClasses) A.class_amin[list * 16 + tid] = __int_as_float(s_class_amin[tid]);
+}
+
+// ---- kernel P: narrow phase (step 4), kPairCtas CTAs per list.  Every CTA stages the list's boxes and grid in shared
+// memory (the searches are chains of dependent lookups: ~30 cycles there instead of an L2 round trip) and handles a
+// slice of the (box i, size class d >= class(i)) work items, one per thread.  A box j of class d that overlaps box i
+// has its centre within 2^d (half its largest possible side) of i (+1 px and 1e-6 relative for fp32 rounding), i.e.
+// in a window of at most 4x4 cells of class d's grid.  Edges are collected in shared memory and appended to the
+// list's edge array with one atomic per CTA.
+constexpr int kPairCtas = 8;
+constexpr int kPairEdgeBuf = 8192;
+
+static size_t pairs_smem_bytes(int keep_topk) {
+  return (size_t)keep_topk * 16 + (size_t)keep_topk * 4 + align_up((size_t)keep_topk * 2, 16) * 2 +
+         align_up((size_t)(kTotalCells + 1) * 2, 16) + (size_t)kPairEdgeBuf * 4;
+}
+
+__global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs A) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ int s_e_n, s_base;
+  __shared__ float s_amin[kNmsClasses];
+  const int list = blockIdx.y;
+  if (A.ovf[list] != 0) return;
+  const int K = A.s_len[list];
+  const int tid = threadIdx.x;
+  const int64_t o = (int64_t)list * A.keep_topk;
+  unsigned char* p = dyn_smem;
+  float4* box = reinterpret_cast<float4*>(p); p += (size_t)A.keep_topk * 16;
+  float* area = reinterpret_cast<float*>(p); p += (size_t)A.keep_topk * 4;
+  uint16_t* box_cell = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
+  uint16_t* cell_items = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
+  uint16_t* cell_start = reinterpret_cast<uint16_t*>(p); p += ((size_t)(kTotalCells + 1) * 2 + 15) / 16 * 16;
+  uint32_t* ebuf = reinterpret_cast<uint32_t*>(p);
+
+  for (int i = tid; i < K; i += kSortThreads) {
+    box[i] = A.s_box[o + i];
+    area[i] = A.s_area[o + i];
+    box_cell[i] = A.box_cell[o + i];
+    cell_items[i] = A.cell_items[o + i];
+  }
+  const uint16_t* g_start = A.cell_start + (int64_t)list * (kTotalCells + 1);
+  for (int i = tid; i <= kTotalCells; i += kSortThreads) cell_start[i] = g_start[i];
+  if (tid == 0) s_e_n = 0;
+  if (tid < kNmsClasses) s_amin[tid] = A.class_amin[list * 16 + tid];
+  __syncthreads();
+
+  const float4 gi = A.grid_info[list];
+  GridGeom g;
+  g.oy = gi.x; g.ox = gi.y; g.extent = gi.z;
+  const int class_mask = __float_as_int(gi.w);
+  uint32_t* edges = A.edges + (int64_t)list * kEdgeCap;
+  const float thr = A.nms_thr;
+  // warp-cooperative search: a warp takes one box i at a time and walks its size classes d >= class(i); for every
+  // grid row of the class-d window the 32 lanes test 32 consecutive items of the row's contiguous item range.
+  // (A thread-per-query loop is SIMT-hostile here: the windows hold anything from 0 to hundreds of boxes.)
+  const int lane = tid & 31;
+  const int warps_total = gridDim.x * (kSortThreads / 32);
+  for (int i = blockIdx.x * (kSortThreads / 32) + (tid >> 5); i < K; i += warps_total) {
+    const int my_cid = box_cell[i];
+    if (my_cid == 0xffff) continue;                       // warp-uniform
+    const int c = my_cid / kCellsPerClass;
+    const float4 me = box[i];
+    const float my_area = area[i];
+    for (int d = c; d < kNmsClasses; ++d) {
+      if (!((class_mask >> d) & 1)) continue;
+      // IoU <= area_i / area_j: a class whose smallest box is already too large for the threshold cannot suppress i
+      if (d > c && my_area < thr * s_amin[d] * 0.999f) continue;
+      int cy0 = 0, cy1 = 0, cx0 = 0, cx1 = 0;
+      if (d < kNmsClasses - 1) {
+        const float inv = 1.f / g.cell_size(d);
+        const float reach = (float)(1 << d) + 1.f;
+        cy0 = GridGeom::cell_of(me.x - reach - 1e-6f * fabsf(me.x), g.oy, inv);
+        cy1 = GridGeom::cell_of(me.z + reach + 1e-6f * fabsf(me.z), g.oy, inv);
+        cx0 = GridGeom::cell_of(me.y - reach - 1e-6f * fabsf(me.y), g.ox, inv);
+        cx1 = GridGeom::cell_of(me.w + reach + 1e-6f * fabsf(me.w), g.ox, inv);
+      }
+      for (int cy = cy0; cy <= cy1; ++cy) {
+        // the cells of one grid row are contiguous: one [begin, end) range of items per row
+        const int row = d * kCellsPerClass + cy * kGridDim;
+        const int p1 = cell_start[row + cx1 + 1];
+        for (int q0 = cell_start[row + cx0]; q0 < p1; q0 += 32) {      // warp-uniform trip count
+          const int q = q0 + lane;
+          bool edge = false;
+          int j = 0;
+          if (q < p1) {
+            j = cell_items[q];
+            // same class: each unordered pair is met from both sides, keep the one seen from the lower rank
+            if (j != i && !(d == c && j > i)) edge = pair_suppresses(box[j], area[j], me, my_area, thr);
+          }
+          const unsigned em = __ballot_sync(0xffffffffu, edge);
+          if (em != 0u) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_e_n, __popc(em));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (edge) {
+              const uint32_t ed = ((uint32_t)max(i, j) << 16) | (uint32_t)min(i, j);
+              const int e = base + __popc(em & ((1u << lane) - 1u));
+              if (e < kPairEdgeBuf) {
+                ebuf[e] = ed;
+              } else {                                   // CTA buffer full: append directly
+                const int ge = atomicAdd(A.edge_n + list, 1);
+                if (ge < kEdgeCap) edges[ge] = ed;
+                else A.ovf[list] = 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int n_local = min(s_e_n, kPairEdgeBuf);
+  if (tid == 0) s_base = atomicAdd(A.edge_n + list, n_local);
+  __syncthreads();
+  const int base = s_base;
+  if (base + n_local > kEdgeCap) {
+    if (tid == 0) A.ovf[list] = 1;
+  } else {
+    for (int e = tid; e < n_local; e += kSortThreads) edges[base + e] = ebuf[e];
+  }
+}
+
+// ---- kernel R: one CTA per list: relaxation over the edges (step 5) and the outputs (step 6)
+template <bool DECODE>
+__global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpArgs A, const float* __restrict__ src_scores,
+                                                                      const float4* __restrict__ src_boxes) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const NmsSmem m = nms_carve(dyn_smem, A.nms_cap, A.keep_topk);
+  __shared__ int s_scan[kSortThreads / 32];
+
+  const int list = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int K = A.s_len[list];
+  const int64_t o = (int64_t)list * A.keep_topk;
+  int kept_n = 0;
+
+  if (A.ovf[list] == 0) {
+    const int n_edges = min(A.edge_n[list], kEdgeCap);
+    const uint32_t* edges = A.edges + (int64_t)list * kEdgeCap;
+    for (int i = tid; i < K; i += kSortThreads) m.status[i] = 0;
+    while (true) {
+      for (int i = tid; i < K; i += kSortThreads) m.pending[i] = 0;
+      __syncthreads();
+      for (int e = tid; e < n_edges; e += kSortThreads) {
+        const uint32_t ed = edges[e];
+        const int hi = (int)(ed >> 16), lo = (int)(ed & 0xffffu);
+        if (m.status[hi] == 0) {
+          const int sl = m.status[lo];
+          if (sl == 1) m.status[hi] = 2;
+          else if (sl == 0) m.pending[hi] = 1;
+        }
+      }
+      __syncthreads();
+      bool any = false;
+      for (int i = tid; i < K; i += kSortThreads) {
+        if (m.status[i] == 0) {
+          if (m.pending[i] == 0) m.status[i] = 1;
+          else any = true;
+        }
+      }
+      if (!__syncthreads_or(any ? 1 : 0)) break;
+    }
+    // ordered compaction of the kept boxes: thread t owns ranks [t*E, (t+1)*E)
+    const int E = (K + kSortThreads - 1) / kSortThreads;
+    int mine_cnt = 0;
+    for (int e = 0; e < E; ++e) {
+      const int i = tid * E + e;
+      if (i < K && m.status[i] == 1) ++mine_cnt;
+    }
+    int incl = mine_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      if (w < warp) before += s_scan[w];
+      total += s_scan[w];
+    }
+    int pos = before + incl - mine_cnt;
+    for (int e = 0; e < E; ++e) {
+      const int i = tid * E + e;
+      if (i < K && m.status[i] == 1) {
+        if (pos < A.nms_topk) m.kept_pos[pos] = i;
+        ++pos;
+      }
+    }
+    kept_n = min(total, A.nms_topk);
+    __syncthreads();
+  } else {
+    for (int r = tid; r < K; r += kSortThreads) {
+      m.cand_box[r] = A.s_box[o + r];
+      m.cand_area[r] = A.s_area[o + r];
+    }
+    __syncthreads();
+    kept_n = nms_rounds(m, K, A.nms_topk, A.nms_thr);
+  }
 
   // ---- outputs, zero padded to nms_topk
   for (int t = tid; t < A.nms_topk; t += kSortThreads) {
     const int64_t oo = (int64_t)list * A.nms_topk + t;
     if (t < kept_n) {
-      const int pos = kept_pos[t];
+      const int pos = m.kept_pos[t];
       const unsigned long long key = A.s_key[o + pos];
       const uint32_t idx = key_index(key);
       A.out_scores[oo] = DECODE ? key_to_score((uint32_t)(key >> 32)) : src_scores[idx];
@@ -685,21 +867,27 @@ __global__ void __launch_bounds__(kSortThreads) nms_resolve_kernel(const PpArgs 
 // ---------------------------------------------------------------------------
 
 struct PpLayout {
-  size_t key_count, s_len, ovf, keys, s_key, s_box, s_area, deg, adj, total;
+  size_t key_count, s_len, edge_n, ovf, grid_info, class_amin, keys, s_key, s_box, s_area, box_cell, cell_start, cell_items, edges, total;
 };
 
-static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk) {
+static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms) {
   PpLayout w;
   size_t off = 0;
-  w.key_count = off; off += align_up(lists * 4, 256);
-  w.s_len = off;     off += align_up(lists * 4, 256);
-  w.ovf = off;       off += align_up(lists * 4, 256);
-  w.keys = off;      off += align_up(lists * n * 8, 256);
-  w.s_key = off;     off += align_up(lists * keep_topk * 8, 256);
-  w.s_box = off;     off += align_up(lists * keep_topk * 16, 256);
-  w.s_area = off;    off += align_up(lists * keep_topk * 4, 256);
-  w.deg = off;       off += align_up(lists * keep_topk * 4, 256);
-  w.adj = off;       off += align_up(lists * keep_topk * (size_t)kAdjCap * 2, 256);
+  auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
+  w.key_count = take(lists * 4);
+  w.keys = take(lists * n * 8);
+  w.s_len = take(nms ? lists * 4 : 0);
+  w.edge_n = take(nms ? lists * 4 : 0);
+  w.ovf = take(nms ? lists * 4 : 0);
+  w.grid_info = take(nms ? lists * 16 : 0);
+  w.class_amin = take(nms ? lists * 64 : 0);
+  w.s_key = take(nms ? lists * keep_topk * 8 : 0);
+  w.s_box = take(nms ? lists * keep_topk * 16 : 0);
+  w.s_area = take(nms ? lists * keep_topk * 4 : 0);
+  w.box_cell = take(nms ? lists * keep_topk * 2 : 0);
+  w.cell_start = take(nms ? lists * (size_t)(kTotalCells + 1) * 2 : 0);
+  w.cell_items = take(nms ? lists * keep_topk * 2 : 0);
+  w.edges = take(nms ? lists * (size_t)kEdgeCap * 4 : 0);
   w.total = off;
   return w;
 }
@@ -707,26 +895,32 @@ static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk) {
 static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
   char* base = static_cast<char*>(ws);
   A.key_count = reinterpret_cast<int32_t*>(base + w.key_count);
-  A.s_len = reinterpret_cast<int32_t*>(base + w.s_len);
-  A.ovf = reinterpret_cast<int32_t*>(base + w.ovf);
   A.keys = reinterpret_cast<unsigned long long*>(base + w.keys);
+  A.s_len = reinterpret_cast<int32_t*>(base + w.s_len);
+  A.edge_n = reinterpret_cast<int32_t*>(base + w.edge_n);
+  A.ovf = reinterpret_cast<int32_t*>(base + w.ovf);
+  A.grid_info = reinterpret_cast<float4*>(base + w.grid_info);
+  A.class_amin = reinterpret_cast<float*>(base + w.class_amin);
   A.s_key = reinterpret_cast<unsigned long long*>(base + w.s_key);
   A.s_box = reinterpret_cast<float4*>(base + w.s_box);
   A.s_area = reinterpret_cast<float*>(base + w.s_area);
-  A.deg = reinterpret_cast<int32_t*>(base + w.deg);
-  A.adj = reinterpret_cast<uint16_t*>(base + w.adj);
+  A.box_cell = reinterpret_cast<uint16_t*>(base + w.box_cell);
+  A.cell_start = reinterpret_cast<uint16_t*>(base + w.cell_start);
+  A.cell_items = reinterpret_cast<uint16_t*>(base + w.cell_items);
+  A.edges = reinterpret_cast<uint32_t*>(base + w.edges);
 }
 
-// resolve kernel: fallback arrays (20 B per candidate, 24 B per kept box) + kept positions + 1 status byte per candidate
-static size_t nms_smem_bytes(int nms_cap, int keep_topk) { return (size_t)nms_cap * 24 + (size_t)keep_topk * 20 + align_up((size_t)keep_topk, 16); }
-constexpr size_t kNmsSmemMax = 227 * 1024 - 8 * 1024;   // dynamic part; a few KB of static shared memory on top
+static bool nms_fits(int nms_cap, int keep_topk) {
+  return nms_smem_bytes(nms_cap, keep_topk) <= kNmsSmemMax && pairs_smem_bytes(keep_topk) <= kNmsSmemMax;
+}
 
 static int enable_big_smem() {
   static bool done = false;
   if (!done) {
-    DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
-    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
-    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
+    DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DAN_CUDA(cudaFuncSetAttribute(nms_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
     DAN_CUDA(cudaFuncSetAttribute(nms_resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
     DAN_CUDA(cudaFuncSetAttribute(nms_resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
     done = true;
@@ -734,15 +928,15 @@ static int enable_big_smem() {
   return DAN_OK;
 }
 
-// sort -> pairs -> resolve for `lists` lists whose keys are already in the workspace; ev (optional): 3 events recorded
-// after each kernel
+// sort+grid -> pairs -> resolve for `lists` lists whose keys are in the workspace; ev (optional): 3 events, one after
+// each kernel
 template <bool DECODE>
 static int run_sort_nms(const PpArgs& A, int lists, const float* src_scores, const float4* src_boxes, cudaStream_t st,
                         cudaEvent_t* ev = nullptr) {
-  pp_sort_kernel<DECODE><<<lists, kSortThreads, kSortCap * 8, st>>>(A, src_boxes);
+  pp_sort_kernel<DECODE><<<lists, kSortThreads, kSortSmem, st>>>(A, src_boxes);
   DAN_LAUNCH_CHECK("pp_sort_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
-  nms_pairs_kernel<<<dim3(kPairCtasPerList, lists), 256, 0, st>>>(A);
+  nms_pairs_kernel<<<dim3(kPairCtas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
   DAN_LAUNCH_CHECK("nms_pairs_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
   nms_resolve_kernel<DECODE><<<lists, kSortThreads, nms_smem_bytes(A.nms_cap, A.keep_topk), st>>>(A, src_scores, src_boxes);
@@ -759,17 +953,17 @@ extern "C" {
 
 size_t dan_postprocess_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t num_classes, int32_t keep_topk) {
   if (num_anchors < 0 || batch < 0 || num_classes < 2 || keep_topk < 1) return 0;
-  return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1), keep_topk).total;
+  return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1), keep_topk, true).total;
 }
 
 size_t dan_sort_workspace_bytes(int64_t n, int32_t keep_topk) {
   if (n < 0 || keep_topk < 1) return 0;
-  return pp_layout(n, 1, 1).total;
+  return pp_layout(n, 1, 1, false).total;
 }
 
 size_t dan_nms_workspace_bytes(int64_t n, int32_t nms_topk) {
   if (n < 0 || nms_topk < 0) return 0;
-  return pp_layout(n, 1, n > 0 ? n : 1).total;
+  return pp_layout(n, 1, n > 0 ? n : 1, true).total;
 }
 
 static int postprocess_core(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
@@ -784,16 +978,16 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
               "select_threshold must be >= 0 (a negative threshold would let zero-score rows carry boxes), got %g", p->select_threshold);
   DAN_REQUIRE(p->keep_topk >= 1 && p->nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "keep_topk and nms_topk must be >= 1");
   DAN_REQUIRE(p->keep_topk <= kSortCap, DAN_ERR_UNSUPPORTED, "keep_topk %d exceeds the in-shared-memory sort capacity %d", p->keep_topk, kSortCap);
-  DAN_REQUIRE(nms_smem_bytes(p->nms_topk < p->keep_topk ? p->nms_topk : p->keep_topk, p->keep_topk) <= kNmsSmemMax, DAN_ERR_UNSUPPORTED,
-              "keep_topk %d / nms_topk %d need more than %zu bytes of shared memory (20 B per candidate + 24 B per kept box + 64 KB)",
-              p->keep_topk, p->nms_topk, kNmsSmemMax);
+  DAN_REQUIRE(nms_fits(p->nms_topk < p->keep_topk ? p->nms_topk : p->keep_topk, p->keep_topk), DAN_ERR_UNSUPPORTED,
+              "keep_topk %d / nms_topk %d do not fit the NMS kernel's shared memory (22 B per candidate + 24 B per kept box in "
+              "%zu bytes)", p->keep_topk, p->nms_topk, kNmsSmemMax);
   DAN_REQUIRE((loc_pred != nullptr) != (boxes_pred != nullptr), DAN_ERR_INVALID_ARGUMENT, "exactly one of loc_pred / boxes_pred must be given");
   if (batch == 0) return DAN_OK;
   DAN_REQUIRE(cls_pred && out_boxes && out_scores, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
   DAN_REQUIRE(loc_pred == nullptr || (a_ymin && a_xmin && a_ymax && a_xmax), DAN_ERR_INVALID_ARGUMENT, "anchors needed to decode loc_pred");
   DAN_REQUIRE(aligned16(loc_pred) && aligned16(boxes_pred) && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "box tensors must be 16-byte aligned");
   const int lists = batch * (p->num_classes - 1);
-  const PpLayout w = pp_layout(num_anchors, lists, p->keep_topk);
+  const PpLayout w = pp_layout(num_anchors, lists, p->keep_topk, true);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   int rc = enable_big_smem();
@@ -867,7 +1061,7 @@ int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t 
   DAN_REQUIRE(keep_topk <= kSortCap || n <= kSortCap, DAN_ERR_UNSUPPORTED, "min(keep_topk, n) exceeds the sort capacity %d", kSortCap);
   DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
   DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
-  const PpLayout w = pp_layout(n, 1, 1);
+  const PpLayout w = pp_layout(n, 1, 1, false);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   int rc = enable_big_smem();
@@ -893,11 +1087,12 @@ int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t n
   DAN_REQUIRE(n >= 0 && nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "bad size");
   const int n_eff = n > 0 ? (int)(n < kSortCap ? n : kSortCap) : 1;
   const int cap = nms_topk < n_eff ? nms_topk : n_eff;
-  DAN_REQUIRE(n <= kSortCap && nms_smem_bytes(cap, n_eff) <= kNmsSmemMax, DAN_ERR_UNSUPPORTED,
-              "n %lld (max %d) / nms_topk %d need more than %zu bytes of shared memory", (long long)n, kSortCap, nms_topk, kNmsSmemMax);
+  DAN_REQUIRE(n <= kSortCap && nms_fits(cap, n_eff), DAN_ERR_UNSUPPORTED,
+              "n %lld (max %d) / nms_topk %d do not fit the NMS kernel's shared memory (%zu bytes)", (long long)n, kSortCap, nms_topk,
+              kNmsSmemMax);
   DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
   DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
-  const PpLayout w = pp_layout(n, 1, n_eff);
+  const PpLayout w = pp_layout(n, 1, n_eff, true);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   int rc = enable_big_smem();

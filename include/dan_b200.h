@@ -244,8 +244,8 @@ int dan_postprocess_batch(const dan_postprocess_params* h_params, const float* c
                           int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos,
                           void* workspace, size_t workspace_bytes, void* stream);
 
-/* Profiling variant: durations in ms of the filter, top-k/sort, NMS pair and NMS
- * resolve kernels written to h_kernel_ms[4] (HOST pointer).
+/* Profiling variant: durations in ms of the filter, top-k/sort(+grid), NMS pair and
+ * NMS resolve kernels written to h_kernel_ms[4] (HOST pointer).
  * Synchronises; not graph capturable. */
 int dan_postprocess_batch_profile(const dan_postprocess_params* h_params, const float* cls_pred,
                                   const float* loc_pred, const float* boxes_pred,
