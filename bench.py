@@ -250,15 +250,31 @@ def run_cuda(args):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
 
-    def step(k):
+    # the all-gather of step k runs on its own stream and overlaps the compute of step k+1 (different buffer set);
+    # a set is not replayed again before its previous gather has finished
+    comm = torch.cuda.Stream() if world > 1 else None
+    ev_comm = [torch.cuda.Event() for _ in range(R)]
+
+    def step(k, gather=True):
         s = sets[k % R]
+        cur = torch.cuda.current_stream()
+        if comm is not None:
+            cur.wait_event(ev_comm[k % R])
         if graphs:
             graphs[k % R].replay()
         else:
             run_set(s)
-        if world > 1:
-            return s["hp"].gather(world)
+        if comm is not None and gather:
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                out = s["hp"].gather(world)
+                ev_comm[k % R].record(comm)
+            return out
         return None
+
+    def drain():
+        if comm is not None:
+            torch.cuda.current_stream().wait_stream(comm)
 
     def barrier():
         if world > 1:
@@ -267,15 +283,17 @@ def run_cuda(args):
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps between barrier+sync ----------------------
     # warm-up: at least W steps AND at least ~0.5 s of load so that the SM clocks have ramped up from idle
+    # (the time-based part runs without the collective: ranks may do different numbers of those)
     W, K = max(args.warmup, 3), args.steps
+    for k in range(W):
+        step(k)
     t_warm = time.time() + 0.5
     k = 0
-    while k < W or time.time() < t_warm:
-        step(k)
+    while time.time() < t_warm:
+        step(k, gather=False)
         k += 1
         if k % 64 == 0:
             torch.cuda.synchronize()
-    W = k
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
@@ -286,6 +304,7 @@ def run_cuda(args):
     e0.record()
     for k in range(K):
         step(W + k)
+    drain()
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -293,7 +312,7 @@ def run_cuda(args):
     t_end = time.time() + (1.0 if sampler else 0.0)
     k = 0
     while time.time() < t_end:
-        step(k)
+        step(k, gather=False)
         k += 1
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None

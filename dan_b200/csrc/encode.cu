@@ -768,10 +768,26 @@ DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int 
   }
   if (straddle) {
     __syncwarp();
-    if (lane == 0) {
-      // compact the live + already taken entries (all were heap members) in ascending anchor order:
-      // the reference pushes candidates in ascending anchor index (small_mining_match.cc:204-209)
-      int n = 0;
+    // The exact path: every live or already taken entry was a member of the reference's heap, pushed in ascending
+    // anchor order (small_mining_match.cc:204-209).  Bucket lists (c <= 64) are unordered: each lane ranks its two
+    // entries by anchor index in parallel; spill lists are already ordered and are compacted by lane 0.
+    int n = 0;
+    if (c <= 64 && !ordered) {
+      const int e0 = lane, e1 = lane + 32;
+      const bool l0 = e0 < c && list[e0].key != 0.f, l1 = e1 < c && list[e1].key != 0.f;
+      const int id0 = l0 ? list[e0].id : 0x7fffffff, id1 = l1 ? list[e1].id : 0x7fffffff;
+      int r0 = 0, r1 = 0;
+      for (int f = 0; f < c; ++f) {
+        const bool lf = list[f].key != 0.f;
+        const int idf = list[f].id;
+        r0 += (lf && idf < id0) ? 1 : 0;
+        r1 += (lf && idf < id1) ? 1 : 0;
+      }
+      if (l0) sort_buf[r0] = HeapItem{fabsf(list[e0].key), id0};
+      if (l1) sort_buf[r1] = HeapItem{fabsf(list[e1].key), id1};
+      n = __popc(__ballot_sync(0xffffffffu, l0)) + __popc(__ballot_sync(0xffffffffu, l1));
+      __syncwarp();
+    } else if (lane == 0) {
       for (int e = 0; e < c; ++e) {
         if (list[e].key == 0.f) continue;
         HeapItem v = list[e];
@@ -782,6 +798,8 @@ DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int 
         sort_buf[p + 1] = v;
         ++n;
       }
+    }
+    if (lane == 0) {
       int len = 0;
       for (int e = 0; e < n; ++e) heap_push(heap, len, sort_buf[e]);
       for (int p = 0; p < need && len > 0; ++p) {

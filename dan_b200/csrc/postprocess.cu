@@ -19,6 +19,8 @@
 //                      part is a register-resident shuffle sweep over the diagonal
 //                      word, the kept rows are OR-ed into the removed set by all
 //                      lanes; writes the zero padded outputs (bbox_util.py:80-90).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dan {
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
 // has its centre within 2^d (half its largest possible side) of i (+1 px and 1e-6 relative for fp32 rounding), i.e.
 // in a window of at most 4x4 cells of class d's grid.  Edges are collected in shared memory and appended to the
 // list's edge array with one atomic per CTA.
-constexpr int kPairCtas = 8;
+constexpr int kPairCtas = 16;         // upper bound of CTAs per list
 constexpr int kPairEdgeBuf = 8192;
 
 static size_t pairs_smem_bytes(int keep_topk) {
@@ -657,6 +659,10 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   const int list = blockIdx.y;
   if (A.ovf[list] != 0) return;
   const int K = A.s_len[list];
+  // long lists get all the CTAs of their grid row, short ones only a few (the others exit at once): the launch time
+  // is set by the longest list
+  const int my_ctas = min((int)gridDim.x, max(1, K / 160));
+  if ((int)blockIdx.x >= my_ctas) return;
   const int tid = threadIdx.x;
   const int64_t o = (int64_t)list * A.keep_topk;
   unsigned char* p = dyn_smem;
@@ -689,7 +695,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   // grid row of the class-d window the 32 lanes test 32 consecutive items of the row's contiguous item range.
   // (A thread-per-query loop is SIMT-hostile here: the windows hold anything from 0 to hundreds of boxes.)
   const int lane = tid & 31;
-  const int warps_total = gridDim.x * (kSortThreads / 32);
+  const int warps_total = my_ctas * (kSortThreads / 32);
   for (int i = blockIdx.x * (kSortThreads / 32) + (tid >> 5); i < K; i += warps_total) {
     const int my_cid = box_cell[i];
     if (my_cid == 0xffff) continue;                       // warp-uniform
@@ -936,7 +942,11 @@ static int run_sort_nms(const PpArgs& A, int lists, const float* src_scores, con
   pp_sort_kernel<DECODE><<<lists, kSortThreads, kSortSmem, st>>>(A, src_boxes);
   DAN_LAUNCH_CHECK("pp_sort_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
-  nms_pairs_kernel<<<dim3(kPairCtas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
+  // up to kPairCtas CTAs per list; a CTA exits at once when its list is short (see the kernel)
+  static const int ctas_env = []() { const char* e = getenv("DAN_PAIR_CTAS"); return e ? atoi(e) : 0; }();
+  int ctas = ctas_env > 0 ? ctas_env : kPairCtas;
+  ctas = ctas < 1 ? 1 : (ctas > kPairCtas ? kPairCtas : ctas);
+  nms_pairs_kernel<<<dim3(ctas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
   DAN_LAUNCH_CHECK("nms_pairs_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
   nms_resolve_kernel<DECODE><<<lists, kSortThreads, nms_smem_bytes(A.nms_cap, A.keep_topk), st>>>(A, src_scores, src_boxes);
