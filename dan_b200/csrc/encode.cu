@@ -504,7 +504,7 @@ DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
 }
 
 template <bool NEED_ROW>
-__global__ void __launch_bounds__(kEncThreads) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
+__global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
   const WarpAnchors W = load_warp_anchors(A);
   const int b_end = min(batch, (int)(blockIdx.y + 1) * ipw);
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kEncThreads) enc_pass1_fused_kernel(const EncA
 }
 
 template <bool MINING>
-__global__ void __launch_bounds__(kEncThreads) enc_pass2_fused_kernel(const EncArgs A, int batch, int ipw) {
+__global__ void __launch_bounds__(kEncThreads, 8) enc_pass2_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
   const WarpAnchors W = load_warp_anchors(A);
   const bool need_haspos = !MINING && !A.gt_max_first;

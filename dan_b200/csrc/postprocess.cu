@@ -185,6 +185,80 @@ struct SortScratch {
   int fill;
 };
 
+// compare-exchange stage at distance ST (1, 2 or 4) inside a thread's 8 keys; all register indices are static
+template <int ST>
+DAN_D void reg_stage(unsigned long long (&r)[8], int lsize, bool desc_t) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if ((e & ST) == 0) {
+      const bool desc = (lsize >= 3) ? desc_t : (((e >> lsize) & 1) == 0);
+      const unsigned long long x = r[e], y = r[e | ST];
+      if ((x < y) == desc) { r[e] = y; r[e | ST] = x; }
+    }
+  }
+}
+
+// Bitonic sort (descending) of P = 2^lp2 >= 256 64-bit keys with the keys held in REGISTERS: thread t owns the 8
+// consecutive keys 8t..8t+7.  Compare-exchange partners at distance 1, 2, 4 are in the same thread, at distance
+// 8..128 in another lane of the same warp (shfl.xor), and only distances >= 256 go through shared memory, written
+// transposed ([e][thread]) so that both the store and the partner's load are conflict free.  The plain shared-memory
+// version is bandwidth bound (4 x 8 B accesses per compare-exchange, ~800 wavefronts per stage for 4096 keys).
+DAN_D void bitonic_sort_regs(unsigned long long* s_keys, int lp2) {
+  const int tid = threadIdx.x;
+  const int T = 1 << (lp2 - 3);                 // threads that own keys
+  const bool active = tid < T;
+  unsigned long long r[8];
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = s_keys[8 * tid + e];
+  }
+  for (int lsize = 1; lsize <= lp2; ++lsize) {
+    // direction of the merge this key takes part in: descending iff bit `lsize` of its index is 0
+    const bool desc_t = ((tid >> (lsize >= 3 ? lsize - 3 : 0)) & 1) == 0;
+    for (int ls = lsize - 1; ls >= 0; --ls) {
+      if (ls >= 8) {
+        __syncthreads();
+        if (active) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s_keys[e * T + tid] = r[e];
+        }
+        __syncthreads();
+        if (active) {
+          const int partner = tid ^ (1 << (ls - 3));
+          const bool keep_max = ((tid & (1 << (ls - 3))) == 0) == desc_t;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const unsigned long long o = s_keys[e * T + partner];
+            r[e] = keep_max ? (r[e] > o ? r[e] : o) : (r[e] < o ? r[e] : o);
+          }
+        }
+      } else if (!active) {
+        // warps that own no keys only take part in the barriers above (T is a multiple of 32: warp-uniform)
+      } else if (ls >= 3) {
+        const int lmask = 1 << (ls - 3);
+        const bool keep_max = ((tid & lmask) == 0) == desc_t;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, r[e], lmask);
+          r[e] = keep_max ? (r[e] > o ? r[e] : o) : (r[e] < o ? r[e] : o);
+        }
+      } else if (ls == 2) {
+        reg_stage<4>(r, lsize, desc_t);
+      } else if (ls == 1) {
+        reg_stage<2>(r, lsize, desc_t);
+      } else {
+        reg_stage<1>(r, lsize, desc_t);
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_keys[8 * tid + e] = r[e];
+  }
+  __syncthreads();
+}
+
 DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, int k, unsigned long long* s_keys, SortScratch& sc) {
   const int tid = threadIdx.x;
   int m = cnt;
@@ -230,7 +304,11 @@ DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, 
   const int p2 = 1 << lp2;
   for (int i = m + tid; i < p2; i += kSortThreads) s_keys[i] = 0ull;
   __syncthreads();
-  // bitonic sort, descending; strides are powers of two -> shifts only
+  if (lp2 >= 8) {
+    bitonic_sort_regs(s_keys, lp2);
+    return m;
+  }
+  // small lists: plain bitonic sort in shared memory, descending; strides are powers of two -> shifts only
   for (int lsize = 1; lsize <= lp2; ++lsize) {
     for (int ls = lsize - 1; ls >= 0; --ls) {
       const int stride = 1 << ls;
@@ -250,7 +328,7 @@ DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, 
 DAN_D uint32_t key_index(unsigned long long key) { return 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull); }
 
 // sort_bboxes: tf.nn.top_k + gather + zero pad (bbox_util.py:61-72)
-__global__ void __launch_bounds__(kSortThreads) topk_sort_kernel(const PpArgs A, const float* __restrict__ src_scores,
+__global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const PpArgs A, const float* __restrict__ src_scores,
                                                                  const float4* __restrict__ src_boxes) {
   extern __shared__ unsigned long long s_keys[];
   __shared__ SortScratch sc;
