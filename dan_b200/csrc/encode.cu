@@ -61,6 +61,7 @@ struct EncArgs {
   float ps0, ps1, ps2, ps3;
   float pa_scale;
   int debug;
+  int dbg_skip;          // experiment switch (DAN_DEBUG_SKIP): 1 = pass 2 skips the GT sweep
   // workspace
   uint32_t* colmax;      // [G] fp32 bit patterns (>= 0)
   int32_t* cnt;          // [G] anchors matched per GT after stage 2
@@ -68,6 +69,8 @@ struct EncArgs {
   int32_t* fill;         // [G] candidates pushed per GT
   HeapItem* bucket;      // [G, kBucketCap]
   HeapItem* spill;       // [B, 3, n] (candidate list, sort buffer, heap of the overflow path)
+  float* rowbest;        // [B, n] per-anchor row maximum, written by fused pass 1, read by fused pass 2
+  int32_t* rowgt;        // [B, n] its (first) argmax
   // outputs
   float4* targets;
   int64_t* labels;
@@ -491,7 +494,7 @@ struct WarpAnchors {
 
 DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
   WarpAnchors w;
-  w.a = blockIdx.x * kEncThreads + threadIdx.x;
+  w.a = blockIdx.x * blockDim.x + threadIdx.x;
   w.valid = w.a < A.n;
   w.ab = AnchorBox{};
   w.active = false;
@@ -503,7 +506,7 @@ DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
   return w;
 }
 
-template <bool NEED_ROW>
+template <bool NEED_ROW, bool MINING>
 __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
   const WarpAnchors W = load_warp_anchors(A);
@@ -527,14 +530,26 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const E
                                     box_area(g.x, g.y, g.z, g.w), hit);
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, (ov > 0.f) ? __float_as_uint(ov) : 0u);
         if (lane == kl) my_colmax = wmax;
-        if (NEED_ROW && ov > best) { best = ov; best_gt = k0 + kl; }
+        if (ov > best) { best = ov; best_gt = k0 + kl; }      // first strictly-greatest GT wins (tf.argmax / :76-83)
+        if (MINING && ov > A.stop) {
+          // possible stage-3 compensation candidate (small_mining_match.cc:206); whether the anchor is still
+          // unmatched is only known after stage 2, pass 3 filters on that
+          const int pos = atomicAdd(A.fill + ig.slot0 + k0 + kl, 1);
+          if (pos < kBucketCap) A.bucket[(int64_t)(ig.slot0 + k0 + kl) * kBucketCap + pos] = HeapItem{ov, W.a};
+        }
       }
       if (my_colmax != 0u) atomicMax(A.colmax + ig.slot0 + k, my_colmax);
     }
-    if (NEED_ROW && W.valid) {
-      const bool less = best < A.low;
-      const bool between = (best < A.high) && (best >= A.low);
-      if (!less && !between) A.haspos[ig.slot0 + best_gt] = 1;
+    if (W.valid) {
+      // the row maximum is final here; pass 2 only needs the overlaps that can tie with a column maximum
+      const int64_t row = (int64_t)b * A.n + W.a;
+      A.rowbest[row] = best;
+      A.rowgt[row] = best_gt;
+      if (NEED_ROW) {
+        const bool less = best < A.low;
+        const bool between = (best < A.high) && (best >= A.low);
+        if (!less && !between) A.haspos[ig.slot0 + best_gt] = 1;
+      }
     }
   }
 }
@@ -551,66 +566,82 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass2_fused_kernel(const E
     s.best = 0.f; s.best_gt = 0; s.ov0 = 0.f;
     s.claimed = false; s.cbest = 0.f; s.cbest_gt = 0;
     s.owner = -1; s.owner_ov = 0.f;
+    if (W.valid) {
+      const int64_t row = (int64_t)b * A.n + W.a;
+      s.best = A.rowbest[row];
+      s.best_gt = A.rowgt[row];
+    }
+    // An anchor can tie with / be claimed by GT k only if its overlap reaches the column maximum cm[k] (to within
+    // FLT_EPSILON for the mining matcher).  No overlap of this warp exceeds the largest row maximum of its lanes, so
+    // GTs with cm[k] above that bound are skipped without evaluating a single IoU.
+    const float wbest = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(s.best)));
+    const float reach = MINING ? fadd(wbest, 2.f * FLT_EPSILON) : wbest;
     int match = -1;
     float score = 0.f;
-    bool push = false;
-    for (int round = 0; round < 2; ++round) {
-      for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
-        const int k = k0 + lane;
-        bool test = false;
-        if (k < ig.m_eff) {
-          const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + k));
-          const bool wide = MINING ? (cm < FLT_EPSILON) : (cm == 0.f);
-          test = may_hit(W.wb, gt_box(A, ig, k)) || (round == 0 && wide);
-        }
-        unsigned hits = __ballot_sync(0xffffffffu, test);
-        while (hits) {
-          const int kk = k0 + __ffs(hits) - 1;
-          hits &= hits - 1;
-          const float4 g = gt_box(A, ig, kk);
-          bool hit = false;
-          float ov = 0.f;
-          if (W.active) ov = pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g.x, g.y, g.z, g.w,
-                                      box_area(g.x, g.y, g.z, g.w), hit);
-          if (round == 0) {
-            const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + kk));
-            const bool claimable = !need_haspos || __ldg(A.haspos + ig.slot0 + kk) == 0;
-            row_update<MINING>(s, kk, ov, cm, claimable);
-          } else if (MINING && push && ov > A.stop) {
-            const int pos = atomicAdd(A.fill + ig.slot0 + kk, 1);
-            if (pos < kBucketCap) A.bucket[(int64_t)(ig.slot0 + kk) * kBucketCap + pos] = HeapItem{ov, W.a};
+    for (int k0 = 0; k0 < (A.dbg_skip ? 0 : ig.m_eff); k0 += 32) {
+      const int k = k0 + lane;
+      bool test = false;
+      if (k < ig.m_eff) {
+        const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + k));
+        const bool wide = MINING ? (cm < FLT_EPSILON) : (cm == 0.f);
+        test = (cm <= reach && may_hit(W.wb, gt_box(A, ig, k))) || wide;
+      }
+      unsigned hits = __ballot_sync(0xffffffffu, test);
+      while (hits) {
+        const int kk = k0 + __ffs(hits) - 1;
+        hits &= hits - 1;
+        const float4 g = gt_box(A, ig, kk);
+        bool hit = false;
+        float ov = 0.f;
+        if (W.active) ov = pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g.x, g.y, g.z, g.w,
+                                    box_area(g.x, g.y, g.z, g.w), hit);
+        const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + kk));
+        if (MINING) {
+          // stage 2 tie band, small_mining_match.cc:171,179; ascending GT index => the last GT wins
+          if (fabsf(fsub(ov, cm)) < FLT_EPSILON) { s.owner = kk; s.owner_ov = ov; }
+        } else {
+          // anchor_manipulator.py:88 exact equality with the column maximum
+          const bool claimable = !need_haspos || __ldg(A.haspos + ig.slot0 + kk) == 0;
+          if (claimable && ov == cm) {
+            s.claimed = true;
+            if (ov > s.cbest) { s.cbest = ov; s.cbest_gt = kk; }
           }
         }
       }
-      if (round == 1) break;
-      if (MINING) {
-        // stage 1, small_mining_match.cc:85-93
-        if (s.best >= A.neg_low && s.best < A.low) match = -1;
-        else if (s.best >= A.high) match = s.best_gt;
-        else match = -2;
-        score = s.best;
-        // stage 2, :178-186
-        if (s.owner >= 0) { match = s.owner; score = s.owner_ov; }
-        if (W.valid && match >= 0) atomicAdd(A.cnt + ig.slot0 + match, 1);
-        push = W.valid && match < 0 && s.best > A.stop;
-      } else {
-        // anchor_manipulator.py:67-76
-        const bool less = s.best < A.low;
-        const bool between = (s.best < A.high) && (s.best >= A.low);
-        const bool neg = A.ignore_between ? less : between;
-        const bool ign = A.ignore_between ? between : less;
-        match = s.best_gt;
-        if (neg) match = -1;
-        if (ign) match = -2;
-        score = s.best;
-        // :95-104 GT-side claim has priority; argmax over (overlap * claim mask)
-        if (s.claimed) {
-          if (s.cbest > 0.f) { match = s.cbest_gt; score = s.cbest; }
-          else { match = 0; score = s.ov0; }
+    }
+    if (MINING) {
+      // stage 1, small_mining_match.cc:85-93
+      if (s.best >= A.neg_low && s.best < A.low) match = -1;
+      else if (s.best >= A.high) match = s.best_gt;
+      else match = -2;
+      score = s.best;
+      // stage 2, :178-186
+      if (s.owner >= 0) { match = s.owner; score = s.owner_ov; }
+      if (W.valid && match >= 0) atomicAdd(A.cnt + ig.slot0 + match, 1);
+    } else {
+      // anchor_manipulator.py:67-76
+      const bool less = s.best < A.low;
+      const bool between = (s.best < A.high) && (s.best >= A.low);
+      const bool neg = A.ignore_between ? less : between;
+      const bool ign = A.ignore_between ? between : less;
+      match = s.best_gt;
+      if (neg) match = -1;
+      if (ign) match = -2;
+      score = s.best;
+      // :95-104 GT-side claim has priority; argmax over (overlap * claim mask)
+      if (s.claimed) {
+        if (s.cbest > 0.f) {
+          match = s.cbest_gt;
+          score = s.cbest;
+        } else {
+          // claimed only through zero-overlap ties: argmax of an all-zero row is GT 0, the score is its overlap
+          const float4 g0 = gt_box(A, ig, 0);
+          bool hit0 = false;
+          match = 0;
+          score = W.active ? pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g0.x, g0.y, g0.z, g0.w,
+                                      box_area(g0.x, g0.y, g0.z, g0.w), hit0) : 0.f;
         }
       }
-      // compensation candidates are pushed in a second sweep, only by warps that have one (warp-uniform decision)
-      if (!MINING || !__any_sync(0xffffffffu, push)) break;
     }
     if (W.valid) {
       const int64_t row = (int64_t)b * A.n + W.a;
@@ -867,7 +898,13 @@ __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) 
       for (int e = tid; e < ng * kBucketCap; e += kP3Threads) {
         const int g = e / kBucketCap, k = e % kBucketCap;
         const int f = s_needy_fill[g0 + g];
-        if (f <= kBucketCap && k < f) s_group[g][k] = A.bucket[(int64_t)(ig.slot0 + s_needy_j[g0 + g]) * kBucketCap + k];
+        if (f <= kBucketCap && k < f) {
+          HeapItem it = A.bucket[(int64_t)(ig.slot0 + s_needy_j[g0 + g]) * kBucketCap + k];
+          // buckets hold every anchor with overlap > stop; only those still unmatched after stage 2 (and after the
+          // patches of the previous groups, already in HBM) are candidates
+          if (!still_unmatched<DENSE>(A, (int64_t)b * A.n + it.id)) it.key = 0.f;
+          s_group[g][k] = it;
+        }
       }
       __syncthreads();
       // ---- the stage is order dependent: warp 0 walks the GTs in ascending order
@@ -950,7 +987,7 @@ __global__ void fill_empty_match_kernel(int32_t* match, float* scores, int n) {
 // host side
 // ---------------------------------------------------------------------------
 struct WsLayout {
-  size_t colmax, cnt, haspos, fill, zero_bytes, bucket, spill, total;
+  size_t colmax, cnt, haspos, fill, zero_bytes, bucket, spill, rowbest, rowgt, total;
 };
 
 static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
@@ -963,6 +1000,8 @@ static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
   w.zero_bytes = off;
   w.bucket = off; off += align_up(slots * kBucketCap * sizeof(HeapItem), 256);
   w.spill = off;  off += align_up(batch * 3 * n * sizeof(HeapItem), 256);
+  w.rowbest = off; off += align_up(batch * n * 4, 256);
+  w.rowgt = off;   off += align_up(batch * n * 4, 256);
   w.total = off;
   return w;
 }
@@ -986,6 +1025,8 @@ static void bind_workspace(EncArgs& A, void* workspace, const WsLayout& w) {
   A.fill = reinterpret_cast<int32_t*>(base + w.fill);
   A.bucket = reinterpret_cast<HeapItem*>(base + w.bucket);
   A.spill = reinterpret_cast<HeapItem*>(base + w.spill);
+  A.rowbest = reinterpret_cast<float*>(base + w.rowbest);
+  A.rowgt = reinterpret_cast<int32_t*>(base + w.rowgt);
 }
 
 // ev (optional, 4 events): recorded before pass 1 and after each pass, for the profile entry point
@@ -994,14 +1035,16 @@ static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, c
   const dim3 grid((A.n + kEncThreads - 1) / kEncThreads, batch);
   static const int ipw_env = []() { const char* e = getenv("DAN_ENC_IMAGES_PER_WARP"); const int v = e ? atoi(e) : 1; return v >= 1 ? v : 1; }();
   const int ipw = ipw_env;
-  const dim3 fgrid((A.n + kEncThreads - 1) / kEncThreads, (batch + ipw - 1) / ipw);
+  static const int fthreads = []() { const char* e = getenv("DAN_ENC_THREADS"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
+  const dim3 fgrid((A.n + fthreads - 1) / fthreads, (batch + ipw - 1) / ipw);
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   if (DENSE) {
     if (need_row) enc_pass1_kernel<true, true><<<grid, kEncThreads, 0, st>>>(A);
     else enc_pass1_kernel<true, false><<<grid, kEncThreads, 0, st>>>(A);
   } else {
-    if (need_row) enc_pass1_fused_kernel<true><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
-    else enc_pass1_fused_kernel<false><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
+    if (mining) enc_pass1_fused_kernel<false, true><<<fgrid, fthreads, 0, st>>>(A, batch, ipw);
+    else if (need_row) enc_pass1_fused_kernel<true, false><<<fgrid, fthreads, 0, st>>>(A, batch, ipw);
+    else enc_pass1_fused_kernel<false, false><<<fgrid, fthreads, 0, st>>>(A, batch, ipw);
   }
   DAN_LAUNCH_CHECK("enc_pass1_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
@@ -1009,8 +1052,8 @@ static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, c
     if (mining) enc_pass2_kernel<true, true><<<grid, kEncThreads, 0, st>>>(A);
     else enc_pass2_kernel<true, false><<<grid, kEncThreads, 0, st>>>(A);
   } else {
-    if (mining) enc_pass2_fused_kernel<true><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
-    else enc_pass2_fused_kernel<false><<<fgrid, kEncThreads, 0, st>>>(A, batch, ipw);
+    if (mining) enc_pass2_fused_kernel<true><<<fgrid, fthreads, 0, st>>>(A, batch, ipw);
+    else enc_pass2_fused_kernel<false><<<fgrid, fthreads, 0, st>>>(A, batch, ipw);
   }
   DAN_LAUNCH_CHECK("enc_pass2_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
@@ -1159,6 +1202,7 @@ static int encode_core(const dan_encode_params* p, const float* a_ymin, const fl
   A.ps0 = p->prior_scaling[0]; A.ps1 = p->prior_scaling[1]; A.ps2 = p->prior_scaling[2]; A.ps3 = p->prior_scaling[3];
   A.pa_scale = p->pa_scale;
   A.debug = p->debug;
+  { static const int dbg = []() { const char* e = getenv("DAN_DEBUG_SKIP"); return e ? atoi(e) : 0; }(); A.dbg_skip = dbg; }
   A.targets = reinterpret_cast<float4*>(out_targets);
   A.labels = out_labels;
   A.scores = out_scores;
