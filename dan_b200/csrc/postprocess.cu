@@ -19,11 +19,21 @@
 //                      part is a register-resident shuffle sweep over the diagonal
 //                      word, the kept rows are OR-ed into the removed set by all
 //                      lanes; writes the zero padded outputs (bbox_util.py:80-90).
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace dan {
+
+// phase timestamps (SM cycles) of the per-list kernels, written by thread 0 of the CTA of the longest list when the
+// library is built with -DDAN_PHASE_TIMING (tools/phase_timing.py); otherwise the macro is empty
+#ifdef DAN_PHASE_TIMING
+__device__ long long g_phase[32];
+#define DAN_PHASE(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_phase[slot] = clock64(); } while (0)
+#else
+#define DAN_PHASE(slot) do { } while (0)
+#endif
 
 constexpr int kSortCap = 8192;      // keys sorted in shared memory (64 KB)
 constexpr int kSortThreads = 1024;
@@ -44,6 +54,7 @@ struct PpArgs {
   int n, batch, num_classes;
   float img_h, img_w;
   float select_thr, min_size_p1;
+  float reject_below;         // 2 classes: logit difference below which softmax <= threshold for sure (-inf: off)
   float ps0, ps1, ps2, ps3;
   int keep_topk, nms_topk;
   int nms_cap;                // kept-list capacity in shared memory = min(nms_topk, keep_topk)
@@ -118,17 +129,15 @@ DAN_D float4 pp_box(const PpArgs& A, int b, int a) { return pp_finish(A, pp_load
 // ---------------------------------------------------------------------------
 // K3: filter + compaction.  grid (ceil(N/256), B)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
-  const int b = blockIdx.y;
-  const int a = blockIdx.x * 256 + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const bool valid = a < A.n;
-  const int C = A.num_classes;
-  const float* x = A.cls + ((int64_t)b * A.n + (valid ? a : 0)) * C;
+constexpr int kFilterPerThread = 4;     // anchors per thread: 4 independent logit loads in flight (memory-level parallelism)
 
+// exact per-anchor path: softmax, threshold, decode + clip, min-size, warp-aggregated append of the survivors
+DAN_D void filter_one(const PpArgs& A, int b, int a, bool live, int lane) {
+  const int C = A.num_classes;
+  const float* x = A.cls + ((int64_t)b * A.n + (live ? a : 0)) * C;
   // tf.nn.softmax: exp(x - max) * (1 / sum(exp(x - max))), sum in class order
   float mx = 0.f, inv = 0.f;
-  if (valid) {
+  if (live) {
     mx = x[0];
     for (int k = 1; k < C; ++k) mx = fmaxf(mx, x[k]);
     float s = 0.f;
@@ -143,7 +152,7 @@ __global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
   for (int c = 1; c < C; ++c) {
     bool pass = false;
     float p = 0.f;
-    if (valid) {
+    if (live) {
       p = fmul(cephes_expf(fsub(x[c], mx)), inv);
       if (p > A.select_thr) {                       // select_bboxes :24-36
         if (!have_box) { box = pp_box(A, b, a); have_box = true; }
@@ -163,6 +172,47 @@ __global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
         A.keys[(int64_t)list * A.n + pos] = ((unsigned long long)score_to_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int a0 = blockIdx.x * (256 * kFilterPerThread) + threadIdx.x;
+  // Two classes: softmax_1 = sigmoid(x1 - x0).  An anchor whose logit difference is more than 0.05 below
+  // logit(threshold) cannot pass (the fp32 evaluation is accurate to ~1e-6 relative), so the ~98 % background anchors
+  // leave after one subtraction.  The exact path runs per 32-anchor group when any of its lanes may pass.
+  bool maybe[kFilterPerThread];
+  if (A.num_classes == 2) {
+    float2 xx[kFilterPerThread];
+#pragma unroll
+    for (int u = 0; u < kFilterPerThread; ++u) {
+      const int a = a0 + u * 256;
+      xx[u] = (a < A.n) ? *reinterpret_cast<const float2*>(A.cls + ((int64_t)b * A.n + a) * 2) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kFilterPerThread; ++u)
+      maybe[u] = (a0 + u * 256 < A.n) &&
+                 (!(fsub(xx[u].y, xx[u].x) < A.reject_below) || fabsf(xx[u].x) > 1e5f || fabsf(xx[u].y) > 1e5f);
+  } else {
+#pragma unroll
+    for (int u = 0; u < kFilterPerThread; ++u) maybe[u] = a0 + u * 256 < A.n;
+  }
+  // compact the warp's few possibly-passing anchors (out of its 128) into dense lanes, then run the exact path on
+  // full warps: without this ~60 % of the 32-anchor groups would run it for one or two live lanes
+  __shared__ int s_list[8][32 * kFilterPerThread];
+  int* mylist = s_list[threadIdx.x >> 5];
+  int total = 0;
+#pragma unroll
+  for (int u = 0; u < kFilterPerThread; ++u) {
+    const unsigned m = __ballot_sync(0xffffffffu, maybe[u]);
+    if (maybe[u]) mylist[total + __popc(m & ((1u << lane) - 1u))] = a0 + u * 256;
+    total += __popc(m);
+  }
+  __syncwarp();
+  for (int j = 0; j < total; j += 32) {
+    const bool live = j + lane < total;
+    filter_one(A, b, live ? mylist[j + lane] : 0, live, lane);
   }
 }
 
@@ -229,7 +279,7 @@ DAN_D void bitonic_sort_regs(unsigned long long* s_keys, int lp2) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const unsigned long long o = s_keys[e * T + partner];
-            r[e] = keep_max ? (r[e] > o ? r[e] : o) : (r[e] < o ? r[e] : o);
+            r[e] = ((r[e] < o) == keep_max) ? o : r[e];      // keys are unique: max takes o iff r < o, min iff r > o
           }
         }
       } else if (!active) {
@@ -240,7 +290,7 @@ DAN_D void bitonic_sort_regs(unsigned long long* s_keys, int lp2) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const unsigned long long o = __shfl_xor_sync(0xffffffffu, r[e], lmask);
-          r[e] = keep_max ? (r[e] > o ? r[e] : o) : (r[e] < o ? r[e] : o);
+          r[e] = ((r[e] < o) == keep_max) ? o : r[e];
         }
       } else if (ls == 2) {
         reg_stage<4>(r, lsize, desc_t);
@@ -298,6 +348,7 @@ DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, 
     }
     m = k;
   }
+  DAN_PHASE(8);
   // pad to a power of two with 0 (smaller than any real key: the low word of a real key is ~index != 0)
   int lp2 = 0;
   while ((1 << lp2) < m) ++lp2;
@@ -623,7 +674,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
   const int cnt = min(A.key_count[list], A.n);
   const int64_t o = (int64_t)list * A.keep_topk;
 
+  DAN_PHASE(0);
   const int K = min(select_and_sort(A.keys + (int64_t)list * A.n, cnt, min(A.keep_topk, cnt), keys, sc), A.keep_topk);
+  DAN_PHASE(1);
   float ylo = 3.0e38f, yhi = -3.0e38f, xlo = 3.0e38f, xhi = -3.0e38f;
   for (int r = tid; r < K; r += kSortThreads) {
     const unsigned long long key = keys[r];
@@ -644,6 +697,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
   block_minmax(ylo, yhi, g.oy, ey);      // (contains barriers: the keys are dead from here on)
   block_minmax(xlo, xhi, g.ox, ex);
   g.extent = fmaxf(fmaxf(ey - g.oy, ex - g.ox), 1.f);
+  DAN_PHASE(2);
 
   for (int i = tid; i < kTotalCells; i += kSortThreads) cell_cnt[i] = 0;
   __syncthreads();
@@ -668,6 +722,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
     box_cell[i] = (uint16_t)cid;
   }
   __syncthreads();
+  DAN_PHASE(3);
   uint16_t* cell_start = A.cell_start + (int64_t)list * (kTotalCells + 1);
   {  // exclusive scan of the cell counters: consecutive cells per thread
     constexpr int per = (kTotalCells + kSortThreads - 1) / kSortThreads;
@@ -707,6 +762,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
     const int cid = box_cell[i];
     if (cid != 0xffff) cell_items[atomicAdd(&cell_cnt[cid], 1)] = (uint16_t)i;
   }
+  DAN_PHASE(4);
   if (tid == 0) {
     A.s_len[list] = K;
     A.grid_info[list] = make_float4(g.oy, g.ox, g.extent, __int_as_float(s_class_mask));
@@ -855,20 +911,42 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
   const int64_t o = (int64_t)list * A.keep_topk;
   int kept_n = 0;
 
+  DAN_PHASE(16);
   if (A.ovf[list] == 0) {
     const int n_edges = min(A.edge_n[list], kEdgeCap);
     const uint32_t* edges = A.edges + (int64_t)list * kEdgeCap;
+    // the relaxation sweeps the edge list several times: keep it in shared memory when it fits (the fallback's
+    // candidate array is unused on this path)
+    const int smem_edges = A.keep_topk * 4;          // 16 B per candidate slot
+    if (n_edges <= smem_edges) {
+      uint32_t* se = reinterpret_cast<uint32_t*>(m.cand_box);
+      for (int e = tid; e < n_edges; e += kSortThreads) se[e] = edges[e];
+      edges = se;
+    }
     for (int i = tid; i < K; i += kSortThreads) m.status[i] = 0;
     while (true) {
       for (int i = tid; i < K; i += kSortThreads) m.pending[i] = 0;
       __syncthreads();
-      for (int e = tid; e < n_edges; e += kSortThreads) {
-        const uint32_t ed = edges[e];
-        const int hi = (int)(ed >> 16), lo = (int)(ed & 0xffffu);
-        if (m.status[hi] == 0) {
-          const int sl = m.status[lo];
-          if (sl == 1) m.status[hi] = 2;
-          else if (sl == 0) m.pending[hi] = 1;
+      for (int e0 = tid; e0 < n_edges; e0 += 4 * kSortThreads) {
+        uint32_t ed[4];
+        int sh[4], sl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                    // independent lookups in flight
+          const int e = e0 + u * kSortThreads;
+          ed[u] = (e < n_edges) ? edges[e] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = ed[u] != 0xffffffffu;
+          sh[u] = ok ? m.status[ed[u] >> 16] : 1;
+          sl[u] = ok ? m.status[ed[u] & 0xffffu] : 2;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (sh[u] == 0) {
+            if (sl[u] == 1) m.status[ed[u] >> 16] = 2;
+            else if (sl[u] == 0) m.pending[ed[u] >> 16] = 1;
+          }
         }
       }
       __syncthreads();
@@ -881,6 +959,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
       }
       if (!__syncthreads_or(any ? 1 : 0)) break;
     }
+    DAN_PHASE(17);
     // ordered compaction of the kept boxes: thread t owns ranks [t*E, (t+1)*E)
     const int E = (K + kSortThreads - 1) / kSortThreads;
     int mine_cnt = 0;
@@ -920,6 +999,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
     kept_n = nms_rounds(m, K, A.nms_topk, A.nms_thr);
   }
 
+  DAN_PHASE(18);
   // ---- outputs, zero padded to nms_topk
   for (int t = tid; t < A.nms_topk; t += kSortThreads) {
     const int64_t oo = (int64_t)list * A.nms_topk + t;
@@ -944,6 +1024,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
     }
   }
   if (tid == 0 && A.out_counts != nullptr) A.out_counts[list] = kept_n;
+  DAN_PHASE(19);
 }
 
 // ---------------------------------------------------------------------------
@@ -1039,6 +1120,10 @@ using namespace dan;
 
 extern "C" {
 
+#ifdef DAN_PHASE_TIMING
+int dan_debug_phases(long long* h_out32) { return cudaMemcpyFromSymbol(h_out32, g_phase, sizeof(long long) * 32) == cudaSuccess ? 0 : -3; }
+#endif
+
 size_t dan_postprocess_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t num_classes, int32_t keep_topk) {
   if (num_anchors < 0 || batch < 0 || num_classes < 2 || keep_topk < 1) return 0;
   return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1), keep_topk, true).total;
@@ -1093,6 +1178,10 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   A.img_w = (float)p->image_w;
   A.select_thr = p->select_threshold;
   A.min_size_p1 = (float)((double)p->min_size + 1.0);   // python: min_size + 1. then fp32
+  {
+    const double t = (double)p->select_threshold;
+    A.reject_below = (p->num_classes == 2 && t > 0.0 && t <= 0.99) ? (float)(log(t / (1.0 - t)) - 0.05) : -INFINITY;
+  }
   A.ps0 = p->prior_scaling[0]; A.ps1 = p->prior_scaling[1]; A.ps2 = p->prior_scaling[2]; A.ps3 = p->prior_scaling[3];
   A.keep_topk = p->keep_topk;
   A.nms_topk = p->nms_topk;
@@ -1108,7 +1197,7 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   DAN_CUDA(cudaMemsetAsync(A.key_count, 0, (size_t)lists * 4, st));
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   if (num_anchors > 0) {
-    pp_filter_kernel<<<dim3((num_anchors + 255) / 256, batch), 256, 0, st>>>(A);
+    pp_filter_kernel<<<dim3((num_anchors + 256 * kFilterPerThread - 1) / (256 * kFilterPerThread), batch), 256, 0, st>>>(A);
     DAN_LAUNCH_CHECK("pp_filter_kernel");
   }
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
