@@ -30,7 +30,7 @@ namespace dan {
 // library is built with -DDAN_PHASE_TIMING (tools/phase_timing.py); otherwise the macro is empty
 #ifdef DAN_PHASE_TIMING
 __device__ long long g_phase[32];
-#define DAN_PHASE(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_phase[slot] = clock64(); } while (0)
+#define DAN_PHASE(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_phase[slot] = clock64(); } while (0)
 #else
 #define DAN_PHASE(slot) do { } while (0)
 #endif
@@ -461,7 +461,7 @@ DAN_D bool pair_suppresses(const float4& a, float a_area, const float4& b, float
 }
 
 constexpr int kNmsClasses = 10;                                    // class 9: max side >= 512, one cell
-constexpr int kGridDim = 24;                                       // cells per dimension and class
+constexpr int kGridDim = 32;                                       // cells per dimension and class
 constexpr int kCellsPerClass = kGridDim * kGridDim;
 constexpr int kTotalCells = kNmsClasses * kCellsPerClass;
 constexpr int kEdgeCap = 1 << 18;                                  // suppression edges per list (1 MB)
@@ -469,7 +469,9 @@ constexpr int kEdgeCap = 1 << 18;                                  // suppressio
 // geometry of the per-class grids of one list
 struct GridGeom {
   float oy, ox, extent;
-  DAN_D float cell_size(int c) const { return fmaxf((float)(2 << c), extent * (1.f / (kGridDim - 1))); }
+  // cell = half the class's largest side (a window of <= 6x6 cells then covers box + reach tightly), but never
+  // more than kGridDim cells per dimension
+  DAN_D float cell_size(int c) const { return fmaxf((float)(1 << c), extent * (1.f / (kGridDim - 1))); }
   DAN_D static int cell_of(float v, float org, float inv) {
     const int q = (int)((v - org) * inv);
     return min(max(q, 0), kGridDim - 1);
@@ -491,7 +493,7 @@ static size_t nms_smem_bytes(int nms_cap, int keep_topk) {
   return (size_t)nms_cap * 20 + (size_t)keep_topk * 20 + align_up((size_t)keep_topk, 16) * 2 + align_up((size_t)nms_cap * 4, 16);
 }
 constexpr size_t kNmsSmemMax = 227 * 1024 - 6 * 1024;   // dynamic part; a few KB of static shared memory on top
-constexpr size_t kSortSmem = (size_t)kSortCap * 8;       // sort kernel: keys, then (aliased) the cell counters
+constexpr size_t kSortSmem = (size_t)kSortCap * 8 > (size_t)kTotalCells * 4 ? (size_t)kSortCap * 8 : (size_t)kTotalCells * 4;   // sort kernel: keys, then (aliased) the cell counters
 
 DAN_D NmsSmem nms_carve(unsigned char* base, int nms_cap, int keep_topk) {
   NmsSmem m;
@@ -749,13 +751,14 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
     for (int e = 0; e < per; ++e) {
       const int cidx = tid * per + e;
       if (cidx < kTotalCells) {
-        cell_start[cidx] = (uint16_t)run;
-        cell_cnt[cidx] = run;          // becomes the scatter cursor
+        cell_cnt[cidx] = run;          // start of the cell; becomes the scatter cursor below
         run += local[e];
       }
     }
     if (tid == kSortThreads - 1) cell_start[kTotalCells] = (uint16_t)run;
   }
+  __syncthreads();
+  for (int i = tid; i < kTotalCells; i += kSortThreads) cell_start[i] = (uint16_t)cell_cnt[i];   // coalesced copy to HBM
   __syncthreads();
   uint16_t* cell_items = A.cell_items + o;
   for (int i = tid; i < K; i += kSortThreads) {
@@ -788,8 +791,7 @@ static size_t pairs_smem_bytes(int keep_topk) {
 
 __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs A) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ int s_e_n, s_base;
-  __shared__ float s_amin[kNmsClasses];
+  __shared__ float s_prune[kNmsClasses], s_inv[kNmsClasses];
   const int list = blockIdx.y;
   if (A.ovf[list] != 0) return;
   const int K = A.s_len[list];
@@ -797,6 +799,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   // is set by the longest list
   const int my_ctas = min((int)gridDim.x, max(1, K / 160));
   if ((int)blockIdx.x >= my_ctas) return;
+  DAN_PHASE(24);
   const int tid = threadIdx.x;
   const int64_t o = (int64_t)list * A.keep_topk;
   unsigned char* p = dyn_smem;
@@ -815,13 +818,16 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   }
   const uint16_t* g_start = A.cell_start + (int64_t)list * (kTotalCells + 1);
   for (int i = tid; i <= kTotalCells; i += kSortThreads) cell_start[i] = g_start[i];
-  if (tid == 0) s_e_n = 0;
-  if (tid < kNmsClasses) s_amin[tid] = A.class_amin[list * 16 + tid];
-  __syncthreads();
-
   const float4 gi = A.grid_info[list];
   GridGeom g;
   g.oy = gi.x; g.ox = gi.y; g.extent = gi.z;
+  if (tid < kNmsClasses) {
+    s_prune[tid] = A.nms_thr * A.class_amin[list * 16 + tid] * 0.999f;   // area below which class `tid` cannot suppress
+    s_inv[tid] = 1.f / g.cell_size(tid);
+  }
+  __syncthreads();
+  DAN_PHASE(25);
+
   const int class_mask = __float_as_int(gi.w);
   uint32_t* edges = A.edges + (int64_t)list * kEdgeCap;
   const float thr = A.nms_thr;
@@ -830,69 +836,125 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   // (A thread-per-query loop is SIMT-hostile here: the windows hold anything from 0 to hundreds of boxes.)
   const int lane = tid & 31;
   const int warps_total = my_ctas * (kSortThreads / 32);
+  // every warp collects its edges in a private slice of shared memory (no atomics in the search loop) and appends
+  // the slice to the list's edge array with one atomic when it is full and at the end
+  constexpr int kWarpEdgeBuf = kPairEdgeBuf / (kSortThreads / 32);
+  uint32_t* wbuf = ebuf + (tid >> 5) * kWarpEdgeBuf;
+  int wcount = 0;                                            // warp-uniform
+  auto flush_warp = [&]() {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(A.edge_n + list, wcount);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + wcount > kEdgeCap) {
+      if (lane == 0) A.ovf[list] = 1;
+    } else {
+      for (int e = lane; e < wcount; e += 32) edges[base + e] = wbuf[e];
+    }
+    __syncwarp();
+    wcount = 0;
+  };
+#ifdef DAN_PHASE_TIMING
+  long long acc_setup = 0, acc_loop = 0, acc_n = 0, acc_boxes = 0, t_a = 0;
+#define DAN_TICK() (t_a = clock64())
+#define DAN_TOCK(acc) (acc += clock64() - t_a)
+#else
+#define DAN_TICK() do { } while (0)
+#define DAN_TOCK(acc) do { } while (0)
+#endif
   for (int i = blockIdx.x * (kSortThreads / 32) + (tid >> 5); i < K; i += warps_total) {
     const int my_cid = box_cell[i];
     if (my_cid == 0xffff) continue;                       // warp-uniform
     const int c = my_cid / kCellsPerClass;
     const float4 me = box[i];
     const float my_area = area[i];
-    for (int d = c; d < kNmsClasses; ++d) {
-      if (!((class_mask >> d) & 1)) continue;
-      // IoU <= area_i / area_j: a class whose smallest box is already too large for the threshold cannot suppress i
-      if (d > c && my_area < thr * s_amin[d] * 0.999f) continue;
+    auto emit = [&](bool edge, int j) {       // append the edges found by this step to the warp's private buffer
+      const unsigned em = __ballot_sync(0xffffffffu, edge);
+      if (em != 0u) {
+        if (wcount + 32 > kWarpEdgeBuf) flush_warp();
+        if (edge) wbuf[wcount + __popc(em & ((1u << lane) - 1u))] = ((uint32_t)max(i, j) << 16) | (uint32_t)min(i, j);
+        wcount += __popc(em);
+      }
+    };
+    // classes to search: non-empty, d >= c, and not ruled out by the area ratio (IoU <= area_i / area_j: a class
+    // whose smallest box is already too large for the threshold cannot suppress i)
+    unsigned todo = __ballot_sync(0xffffffffu, lane >= c && lane < kNmsClasses && ((class_mask >> lane) & 1) &&
+                                                   (lane == c || !(my_area < s_prune[lane < kNmsClasses ? lane : 0])));
+    while (todo) {                                         // up to 4 classes per pass
+      DAN_TICK();
+      // lane = (class slot, window row): each lane finds the item range of ONE row of ONE class's window, so the
+      // window geometry of all classes is computed in parallel and all candidates of the box form one flat list
+      const int slot = lane >> 3, r = lane & 7;
+      const unsigned dd = __fns(todo, 0, slot + 1);        // position of the (slot+1)-th set bit, or 0xffffffff
+      const bool has = dd != 0xffffffffu;
+      const int d = has ? (int)dd : 0;
       int cy0 = 0, cy1 = 0, cx0 = 0, cx1 = 0;
-      if (d < kNmsClasses - 1) {
-        const float inv = 1.f / g.cell_size(d);
+      if (has && d < kNmsClasses - 1) {
+        const float inv = s_inv[d];
         const float reach = (float)(1 << d) + 1.f;
         cy0 = GridGeom::cell_of(me.x - reach - 1e-6f * fabsf(me.x), g.oy, inv);
         cy1 = GridGeom::cell_of(me.z + reach + 1e-6f * fabsf(me.z), g.oy, inv);
         cx0 = GridGeom::cell_of(me.y - reach - 1e-6f * fabsf(me.y), g.ox, inv);
         cx1 = GridGeom::cell_of(me.w + reach + 1e-6f * fabsf(me.w), g.ox, inv);
       }
-      for (int cy = cy0; cy <= cy1; ++cy) {
-        // the cells of one grid row are contiguous: one [begin, end) range of items per row
-        const int row = d * kCellsPerClass + cy * kGridDim;
-        const int p1 = cell_start[row + cx1 + 1];
-        for (int q0 = cell_start[row + cx0]; q0 < p1; q0 += 32) {      // warp-uniform trip count
+      // a window taller than 8 rows (possible only when the grid had to be coarsened) is walked in row blocks of 8
+      const int nrows = cy1 - cy0 + 1;
+      const int nblocks = __reduce_max_sync(0xffffffffu, has ? (nrows + 7) >> 3 : 0);
+      for (int rb = 0; rb < nblocks; ++rb) {
+        const int row_in_window = rb * 8 + r;
+        int p0 = 0, len = 0;
+        if (has && row_in_window < nrows) {
+          const int row = d * kCellsPerClass + (cy0 + row_in_window) * kGridDim;
+          p0 = cell_start[row + cx0];
+          len = cell_start[row + cx1 + 1] - p0;        // the cells of one grid row are contiguous
+        }
+        int incl = len;                                  // inclusive prefix over the 32 (class, row) ranges
+#pragma unroll
+        for (int sh = 1; sh < 32; sh <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, sh);
+          if (lane >= sh) incl += v;
+        }
+        const int n = __shfl_sync(0xffffffffu, incl, 31);
+        const int shift = p0 - (incl - len);             // item position = q + shift inside this lane's range
+        const int same = (d == c) ? 1 : 0;
+        DAN_TOCK(acc_setup);
+        DAN_TICK();
+#ifdef DAN_PHASE_TIMING
+        acc_n += n; acc_boxes += 1;
+#endif
+        for (int q0 = 0; q0 < n; q0 += 32) {              // warp-uniform trip count
           const int q = q0 + lane;
+          int lo = 0;                                      // first range whose inclusive prefix exceeds q
+#pragma unroll
+          for (int st = 16; st >= 1; st >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, lo + st - 1);
+            if (q >= v) lo += st;
+          }
+          lo = min(lo, 31);
+          const int pos = q + __shfl_sync(0xffffffffu, shift, lo);
+          const int sm = __shfl_sync(0xffffffffu, same, lo);
           bool edge = false;
           int j = 0;
-          if (q < p1) {
-            j = cell_items[q];
+          if (q < n) {
+            j = cell_items[pos];
             // same class: each unordered pair is met from both sides, keep the one seen from the lower rank
-            if (j != i && !(d == c && j > i)) edge = pair_suppresses(box[j], area[j], me, my_area, thr);
+            if (j != i && !(sm && j > i)) edge = pair_suppresses(box[j], area[j], me, my_area, thr);
           }
-          const unsigned em = __ballot_sync(0xffffffffu, edge);
-          if (em != 0u) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_e_n, __popc(em));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (edge) {
-              const uint32_t ed = ((uint32_t)max(i, j) << 16) | (uint32_t)min(i, j);
-              const int e = base + __popc(em & ((1u << lane) - 1u));
-              if (e < kPairEdgeBuf) {
-                ebuf[e] = ed;
-              } else {                                   // CTA buffer full: append directly
-                const int ge = atomicAdd(A.edge_n + list, 1);
-                if (ge < kEdgeCap) edges[ge] = ed;
-                else A.ovf[list] = 1;
-              }
-            }
-          }
+          emit(edge, j);
         }
+        DAN_TOCK(acc_loop);
+        DAN_TICK();
       }
+      // drop the (up to) 4 classes handled in this pass
+#pragma unroll
+      for (int k = 0; k < 4; ++k) todo &= todo - 1u;
     }
   }
-  __syncthreads();
-  const int n_local = min(s_e_n, kPairEdgeBuf);
-  if (tid == 0) s_base = atomicAdd(A.edge_n + list, n_local);
-  __syncthreads();
-  const int base = s_base;
-  if (base + n_local > kEdgeCap) {
-    if (tid == 0) A.ovf[list] = 1;
-  } else {
-    for (int e = tid; e < n_local; e += kSortThreads) edges[base + e] = ebuf[e];
-  }
+  DAN_PHASE(26);
+#ifdef DAN_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_phase[28] = acc_setup; g_phase[29] = acc_loop; g_phase[30] = acc_n; g_phase[31] = acc_boxes; }
+#endif
+  if (wcount > 0) flush_warp();
+  DAN_PHASE(27);
 }
 
 // ---- kernel R: one CTA per list: relaxation over the edges (step 5) and the outputs (step 6)
