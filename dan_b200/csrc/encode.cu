@@ -494,7 +494,10 @@ struct WarpAnchors {
 
 DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
   WarpAnchors w;
-  w.a = blockIdx.x * blockDim.x + threadIdx.x;
+  // grid = (image groups, anchor chunks): CTAs are dispatched x-fastest, so all images of one anchor chunk start
+  // together, and the chunks are walked from the END of the anchor array: the coarse pyramid levels live there, their
+  // warps see every GT and run the longest, so they must not be the tail of the launch
+  w.a = (gridDim.y - 1 - blockIdx.y) * blockDim.x + threadIdx.x;
   w.valid = w.a < A.n;
   w.ab = AnchorBox{};
   w.active = false;
@@ -510,8 +513,8 @@ template <bool NEED_ROW, bool MINING>
 __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
   const WarpAnchors W = load_warp_anchors(A);
-  const int b_end = min(batch, (int)(blockIdx.y + 1) * ipw);
-  for (int b = blockIdx.y * ipw; b < b_end; ++b) {
+  const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
+  for (int b = blockIdx.x * ipw; b < b_end; ++b) {
     const ImageGt ig = image_gt<false>(A, b);
     float best = 0.f;
     int best_gt = 0;
@@ -559,8 +562,8 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass2_fused_kernel(const E
   const int lane = threadIdx.x & 31;
   const WarpAnchors W = load_warp_anchors(A);
   const bool need_haspos = !MINING && !A.gt_max_first;
-  const int b_end = min(batch, (int)(blockIdx.y + 1) * ipw);
-  for (int b = blockIdx.y * ipw; b < b_end; ++b) {
+  const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
+  for (int b = blockIdx.x * ipw; b < b_end; ++b) {
     const ImageGt ig = image_gt<false>(A, b);
     RowState s;
     s.best = 0.f; s.best_gt = 0; s.ov0 = 0.f;
@@ -1036,7 +1039,7 @@ static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, c
   static const int ipw_env = []() { const char* e = getenv("DAN_ENC_IMAGES_PER_WARP"); const int v = e ? atoi(e) : 1; return v >= 1 ? v : 1; }();
   const int ipw = ipw_env;
   static const int fthreads = []() { const char* e = getenv("DAN_ENC_THREADS"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
-  const dim3 fgrid((A.n + fthreads - 1) / fthreads, (batch + ipw - 1) / ipw);
+  const dim3 fgrid((batch + ipw - 1) / ipw, (A.n + fthreads - 1) / fthreads);
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   if (DENSE) {
     if (need_row) enc_pass1_kernel<true, true><<<grid, kEncThreads, 0, st>>>(A);
@@ -1170,6 +1173,7 @@ static int encode_core(const dan_encode_params* p, const float* a_ymin, const fl
   DAN_REQUIRE(p->matcher == DAN_MATCH_DUAL || p->matcher == DAN_MATCH_MINING, DAN_ERR_INVALID_ARGUMENT, "unknown matcher %d", p->matcher);
   DAN_REQUIRE(num_anchors >= 0 && batch >= 0 && total_gt >= 0, DAN_ERR_INVALID_ARGUMENT, "negative size");
   DAN_REQUIRE(batch <= 65535, DAN_ERR_UNSUPPORTED, "batch > 65535");
+  DAN_REQUIRE(num_anchors <= 4000000, DAN_ERR_UNSUPPORTED, "more than 4,000,000 anchors per image");
   const bool mining = p->matcher == DAN_MATCH_MINING;
   if (mining) {
     int rc = check_mining_attrs(p->negative_low_thres, p->ignore_threshold, p->positive_threshold, p->min_match, p->stop_positive_thres);

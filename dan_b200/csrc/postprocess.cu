@@ -73,6 +73,7 @@ struct PpArgs {
   float4* grid_info;          // [L] (origin y, origin x, extent, bit mask of the non-empty size classes)
   float* class_amin;          // [L, 16] smallest box area per size class (IoU <= area ratio: whole classes are skipped)
   uint16_t* box_cell;         // [L, keep_topk] flattened (class, cy, cx) of each box, 0xffff = not binned
+  uint16_t* box_pos;          // [L, keep_topk] position of each box inside cell_items
   uint16_t* cell_start;       // [L, kTotalCells + 1]
   uint16_t* cell_items;       // [L, keep_topk] ranks grouped by cell
   uint32_t* edges;            // [L, kEdgeCap] (hi << 16 | lo): lo suppresses hi when lo is kept
@@ -763,7 +764,11 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
   uint16_t* cell_items = A.cell_items + o;
   for (int i = tid; i < K; i += kSortThreads) {
     const int cid = box_cell[i];
-    if (cid != 0xffff) cell_items[atomicAdd(&cell_cnt[cid], 1)] = (uint16_t)i;
+    if (cid != 0xffff) {
+      const int pos = atomicAdd(&cell_cnt[cid], 1);
+      cell_items[pos] = (uint16_t)i;
+      A.box_pos[o + i] = (uint16_t)pos;
+    }
   }
   DAN_PHASE(4);
   if (tid == 0) {
@@ -775,17 +780,18 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
   if (tid < kNmsClasses) A.class_amin[list * 16 + tid] = __int_as_float(s_class_amin[tid]);
 }
 
-// ---- kernel P: narrow phase (step 4), kPairCtas CTAs per list.  Every CTA stages the list's boxes and grid in shared
-// memory (the searches are chains of dependent lookups: ~30 cycles there instead of an L2 round trip) and handles a
-// slice of the (box i, size class d >= class(i)) work items, one per thread.  A box j of class d that overlaps box i
-// has its centre within 2^d (half its largest possible side) of i (+1 px and 1e-6 relative for fp32 rounding), i.e.
-// in a window of at most 4x4 cells of class d's grid.  Edges are collected in shared memory and appended to the
-// list's edge array with one atomic per CTA.
+// ---- kernel P: narrow phase (step 4), up to kPairCtas CTAs per list.  Every CTA stages the list's boxes and grid in
+// shared memory (the searches are chains of dependent lookups: ~30 cycles there instead of an L2 round trip) and its
+// warps take the boxes round-robin.  A box j of class d that overlaps box i has its centre within 2^d (half its largest
+// possible side) of i (+1 px and 1e-6 relative for fp32 rounding), i.e. in a window of at most 4x4 cells of class d's
+// grid (more when the grid had to be coarsened).  Box i searches the classes d > class(i) in full and only the half
+// of its own class's window that follows it (each same-class pair is met exactly once).  Edges are collected in
+// warp-private shared-memory buffers and appended to the list's edge array with one atomic per flush.
 constexpr int kPairCtas = 16;         // upper bound of CTAs per list
 constexpr int kPairEdgeBuf = 8192;
 
 static size_t pairs_smem_bytes(int keep_topk) {
-  return (size_t)keep_topk * 16 + (size_t)keep_topk * 4 + align_up((size_t)keep_topk * 2, 16) * 2 +
+  return (size_t)keep_topk * 16 + (size_t)keep_topk * 4 + align_up((size_t)keep_topk * 2, 16) * 3 +
          align_up((size_t)(kTotalCells + 1) * 2, 16) + (size_t)kPairEdgeBuf * 4;
 }
 
@@ -806,6 +812,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   float4* box = reinterpret_cast<float4*>(p); p += (size_t)A.keep_topk * 16;
   float* area = reinterpret_cast<float*>(p); p += (size_t)A.keep_topk * 4;
   uint16_t* box_cell = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
+  uint16_t* box_pos = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
   uint16_t* cell_items = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
   uint16_t* cell_start = reinterpret_cast<uint16_t*>(p); p += ((size_t)(kTotalCells + 1) * 2 + 15) / 16 * 16;
   uint32_t* ebuf = reinterpret_cast<uint32_t*>(p);
@@ -814,6 +821,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
     box[i] = A.s_box[o + i];
     area[i] = A.s_area[o + i];
     box_cell[i] = A.box_cell[o + i];
+    box_pos[i] = A.box_pos[o + i];
     cell_items[i] = A.cell_items[o + i];
   }
   const uint16_t* g_start = A.cell_start + (int64_t)list * (kTotalCells + 1);
@@ -865,6 +873,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
     const int my_cid = box_cell[i];
     if (my_cid == 0xffff) continue;                       // warp-uniform
     const int c = my_cid / kCellsPerClass;
+    const int own_row = (my_cid - c * kCellsPerClass) / kGridDim;    // grid row of the box's own cell (0 for the last class)
+    const int after_me = box_pos[i] + 1;
     const float4 me = box[i];
     const float my_area = area[i];
     auto emit = [&](bool edge, int j) {       // append the edges found by this step to the warp's private buffer
@@ -905,7 +915,14 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
         if (has && row_in_window < nrows) {
           const int row = d * kCellsPerClass + (cy0 + row_in_window) * kGridDim;
           p0 = cell_start[row + cx0];
-          len = cell_start[row + cx1 + 1] - p0;        // the cells of one grid row are contiguous
+          // Own class: both boxes of an overlapping pair have each other in their windows, so only the HALF window
+          // after the box is searched: the rest of its own cell, the cells to the right in its own row, and the
+          // rows below.  (The items of a grid row are contiguous, and so are those of a cell.)
+          if (d == c) {
+            if (cy0 + row_in_window < own_row) p0 = 0x7fffffff;
+            else if (cy0 + row_in_window == own_row) p0 = after_me;
+          }
+          len = max((int)cell_start[row + cx1 + 1] - p0, 0);
         }
         int incl = len;                                  // inclusive prefix over the 32 (class, row) ranges
 #pragma unroll
@@ -915,7 +932,6 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
         }
         const int n = __shfl_sync(0xffffffffu, incl, 31);
         const int shift = p0 - (incl - len);             // item position = q + shift inside this lane's range
-        const int same = (d == c) ? 1 : 0;
         DAN_TOCK(acc_setup);
         DAN_TICK();
 #ifdef DAN_PHASE_TIMING
@@ -931,13 +947,11 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
           }
           lo = min(lo, 31);
           const int pos = q + __shfl_sync(0xffffffffu, shift, lo);
-          const int sm = __shfl_sync(0xffffffffu, same, lo);
           bool edge = false;
           int j = 0;
           if (q < n) {
             j = cell_items[pos];
-            // same class: each unordered pair is met from both sides, keep the one seen from the lower rank
-            if (j != i && !(sm && j > i)) edge = pair_suppresses(box[j], area[j], me, my_area, thr);
+            edge = pair_suppresses(box[j], area[j], me, my_area, thr);
           }
           emit(edge, j);
         }
@@ -1094,7 +1108,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
 // ---------------------------------------------------------------------------
 
 struct PpLayout {
-  size_t key_count, s_len, edge_n, ovf, grid_info, class_amin, keys, s_key, s_box, s_area, box_cell, cell_start, cell_items, edges, total;
+  size_t key_count, s_len, edge_n, ovf, grid_info, class_amin, keys, s_key, s_box, s_area, box_cell, box_pos, cell_start, cell_items, edges, total;
 };
 
 static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms) {
@@ -1112,6 +1126,7 @@ static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms)
   w.s_box = take(nms ? lists * keep_topk * 16 : 0);
   w.s_area = take(nms ? lists * keep_topk * 4 : 0);
   w.box_cell = take(nms ? lists * keep_topk * 2 : 0);
+  w.box_pos = take(nms ? lists * keep_topk * 2 : 0);
   w.cell_start = take(nms ? lists * (size_t)(kTotalCells + 1) * 2 : 0);
   w.cell_items = take(nms ? lists * keep_topk * 2 : 0);
   w.edges = take(nms ? lists * (size_t)kEdgeCap * 4 : 0);
@@ -1132,6 +1147,7 @@ static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
   A.s_box = reinterpret_cast<float4*>(base + w.s_box);
   A.s_area = reinterpret_cast<float*>(base + w.s_area);
   A.box_cell = reinterpret_cast<uint16_t*>(base + w.box_cell);
+  A.box_pos = reinterpret_cast<uint16_t*>(base + w.box_pos);
   A.cell_start = reinterpret_cast<uint16_t*>(base + w.cell_start);
   A.cell_items = reinterpret_cast<uint16_t*>(base + w.cell_items);
   A.edges = reinterpret_cast<uint32_t*>(base + w.edges);
