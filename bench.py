@@ -216,7 +216,12 @@ def run_cuda(args):
     preds = [synthetic.gen_predictions(base + i, an, max_faces=300) for i in range(B)]
     per_set = B * N * (8 + 16 + 44)          # cls + loc in, encode outputs out
     R = args.sets if args.sets > 0 else max(4, int(np.ceil(3.0 * 126e6 / per_set)))
-    ws = (_lib.Workspace(), _lib.Workspace())
+    # `inflight` consecutive steps are in flight at a time, each on its own stream with its own workspaces (different
+    # buffer sets, no shared state): the top-k sort, the NMS resolve and the compensation pass run one CTA per image,
+    # i.e. on 32 of the 148 SMs, and their latency chain would otherwise leave most of the GPU idle
+    L = max(1, args.inflight)
+    R = (R + L - 1) // L * L                  # a set always runs on the same lane
+    ws_lanes = [(_lib.Workspace(), _lib.Workspace()) for _ in range(L)]
     sets = []
     for r in range(R):
         order = [(i + r) % B for i in range(B)]
@@ -225,8 +230,8 @@ def run_cuda(args):
              "cls": torch.from_numpy(np.stack([preds[i][0] for i in order])).pin_memory(),
              "loc": torch.from_numpy(np.stack([preds[i][1] for i in order])).pin_memory()}
         d = {k: v.to(dev) for k, v in h.items()}
-        hp = pipeline.HotPath(a_train[:4], a_train[4], enc_params, pp_params, anchors_eval=a_eval[:4], workspaces=ws,
-                              overlap=not args.no_overlap)
+        hp = pipeline.HotPath(a_train[:4], a_train[4], enc_params, pp_params, anchors_eval=a_eval[:4],
+                              workspaces=ws_lanes[r % L], overlap=not args.no_overlap)
         sets.append({"host": h, "dev": d, "hp": hp, "total_gt": int(offs[-1])})
     total_gt_mean = float(np.mean([s["total_gt"] for s in sets]))
 
@@ -254,16 +259,23 @@ def run_cuda(args):
     # a set is not replayed again before its previous gather has finished
     comm = torch.cuda.Stream() if world > 1 else None
     ev_comm = [torch.cuda.Event() for _ in range(R)]
+    main = torch.cuda.current_stream()
+    lanes = [torch.cuda.Stream() for _ in range(L)]
 
-    def step(k, gather=True):
+    def lane_of(k, serial=False):
+        return lanes[0] if serial else lanes[(k % R) % L]
+
+    def step(k, gather=True, serial=False):
+        """Enqueue step k on its lane's stream (serial=True: every step on lane 0, one after the other)."""
         s = sets[k % R]
-        cur = torch.cuda.current_stream()
+        cur = lane_of(k, serial)
         if comm is not None:
             cur.wait_event(ev_comm[k % R])
-        if graphs:
-            graphs[k % R].replay()
-        else:
-            run_set(s)
+        with torch.cuda.stream(cur):
+            if graphs:
+                graphs[k % R].replay()
+            else:
+                run_set(s)
         if comm is not None and gather:
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):
@@ -272,9 +284,15 @@ def run_cuda(args):
             return out
         return None
 
+    def fork():
+        for ln in lanes:
+            ln.wait_stream(main)
+
     def drain():
+        for ln in lanes:
+            main.wait_stream(ln)
         if comm is not None:
-            torch.cuda.current_stream().wait_stream(comm)
+            main.wait_stream(comm)
 
     def barrier():
         if world > 1:
@@ -285,6 +303,7 @@ def run_cuda(args):
     # warm-up: at least W steps AND at least ~0.5 s of load so that the SM clocks have ramped up from idle
     # (the time-based part runs without the collective: ranks may do different numbers of those)
     W, K = max(args.warmup, 3), args.steps
+    fork()
     for k in range(W):
         step(k)
     t_warm = time.time() + 0.5
@@ -299,15 +318,21 @@ def run_cuda(args):
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(K):
-        step(W + k)
-    drain()
-    e1.record()
-    barrier()
-    elapsed_ms = e0.elapsed_time(e1)
+    def timed(serial):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        drain()
+        barrier()
+        e0.record()
+        fork()
+        for k in range(K):
+            step(W + k, serial=serial)
+        drain()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    serial_ms = timed(True) if L > 1 else None       # one step at a time: the latency of a step
+    elapsed_ms = timed(False)
     # keep the GPU busy a little longer so that the clock sampler sees the loaded state
     t_end = time.time() + (1.0 if sampler else 0.0)
     k = 0
@@ -316,11 +341,36 @@ def run_cuda(args):
         k += 1
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    drain()
+    t = torch.tensor([elapsed_ms, serial_ms if serial_ms is not None else elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms, serial_ms = float(t[0].item()), float(t[1].item())
     value = world * B * K / (elapsed_ms * 1e-3)
+
+    # ---- the steps in flight must not disturb each other: every set's outputs after a pipelined run are compared
+    # bit for bit with the outputs of the same set run alone
+    def outputs(s):
+        return list(s["hp"]._enc_out[:4]) + [s["hp"]._slab.buf]
+    for r in range(R):
+        step(r, gather=False, serial=True)
+    drain()
+    torch.cuda.synchronize()
+    alone = [[t.clone() for t in outputs(s)] for s in sets]
+    for s in sets:
+        for t in outputs(s):
+            t.fill_(-7)
+    torch.cuda.synchronize()
+    fork()
+    for k in range(2 * R):
+        step(k, gather=False)
+    drain()
+    torch.cuda.synchronize()
+    for r, s in enumerate(sets):
+        for a, b in zip(alone[r], outputs(s)):
+            if not torch.equal(a, b):
+                raise RuntimeError("set %d: outputs with %d steps in flight differ from the serial run" % (r, L))
+    del alone
 
     # ---- end to end: host buffers in, detections out, every step -------------------------------------------------
     # Software pipeline of depth 2 over three streams: while step k computes, the inputs of step k+1 cross PCIe on the
@@ -329,7 +379,6 @@ def run_cuda(args):
     slab_words = sets[0]["hp"]._slab.words
     h_out = [torch.empty(slab_words, dtype=torch.float32).pin_memory() for _ in range(2)]
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    main = torch.cuda.current_stream()
     ev_in = [torch.cuda.Event() for _ in range(R)]
     ev_done = [torch.cuda.Event() for _ in range(R)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
@@ -342,15 +391,17 @@ def run_cuda(args):
                 for name in ("gt", "offs", "cls", "loc"):
                     s["dev"][name].copy_(s["host"][name], non_blocking=True)
                 ev_in[k % R].record(s_in)
+        drain()
         for r in range(R):
             ev_done[r].record(main)
+        fork()
         copy_in(0)
         for k in range(n_steps):
             if k + 1 < n_steps:
                 copy_in(k + 1)
-            main.wait_event(ev_in[k % R])
+            lane_of(k).wait_event(ev_in[k % R])
             step(k)
-            ev_done[k % R].record(main)
+            ev_done[k % R].record(lane_of(k))
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[k % R])
                 ev_out[k % 2].synchronize()                   # the host consumed this pinned buffer two steps ago
@@ -408,10 +459,13 @@ def run_cuda(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": workload_config(B, world, {"l2_policy": "%d rotating input/output buffer sets (%.0f MB) > 126 MB L2" %
                                                                   (R, R * per_set / 1e6),
-                                                     "cuda_graph": not args.no_graph, "two_stream_overlap": not args.no_overlap, "mean_gt_per_image": total_gt_mean / B}),
+                                                     "cuda_graph": not args.no_graph, "two_stream_overlap": not args.no_overlap,
+                                                     "steps_in_flight": L, "inflight_outputs": "bit-identical to the serial run (checked on all sets)", "mean_gt_per_image": total_gt_mean / B}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * K,
                 "roofline": roofline, "cpu_baseline": cpu_base,
-                "kernel_ms": kernel_ms, "step_kernel_ms_sum": step_kernel_sum}
+                "kernel_ms": kernel_ms, "step_kernel_ms_sum": step_kernel_sum,
+                "serial": {"ms_per_step": serial_ms / K, "value": world * B * K / (serial_ms * 1e-3), "unit": UNIT,
+                           "note": "same K steps with one step in flight (step latency); `value` has %d steps in flight" % L}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -426,6 +480,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough for 3x L2)")
+    ap.add_argument("--inflight", type=int, default=3, help="steps in flight (each on its own stream and workspaces)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run encode and postprocess on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -894,9 +894,16 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
       // lane = (class slot, window row): each lane finds the item range of ONE row of ONE class's window, so the
       // window geometry of all classes is computed in parallel and all candidates of the box form one flat list
       const int slot = lane >> 3, r = lane & 7;
-      const unsigned dd = __fns(todo, 0, slot + 1);        // position of the (slot+1)-th set bit, or 0xffffffff
-      const bool has = dd != 0xffffffffu;
-      const int d = has ? (int)dd : 0;
+      unsigned rest = todo;                                // (slot+1)-th set bit of todo (no __fns: it is a software loop)
+      int dsel = -1;
+#pragma unroll
+      for (int sidx = 0; sidx < 4; ++sidx) {
+        const int dd = rest ? (__ffs(rest) - 1) : -1;
+        if (slot == sidx) dsel = dd;
+        rest &= rest - 1u;
+      }
+      const bool has = dsel >= 0;
+      const int d = has ? dsel : 0;
       int cy0 = 0, cy1 = 0, cx0 = 0, cx1 = 0;
       if (has && d < kNmsClasses - 1) {
         const float inv = s_inv[d];
@@ -958,9 +965,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
         DAN_TOCK(acc_loop);
         DAN_TICK();
       }
-      // drop the (up to) 4 classes handled in this pass
-#pragma unroll
-      for (int k = 0; k < 4; ++k) todo &= todo - 1u;
+      todo = rest;                                         // the (up to) 4 classes of this pass are done
     }
   }
   DAN_PHASE(26);
@@ -1000,7 +1005,13 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
       edges = se;
     }
     for (int i = tid; i < K; i += kSortThreads) m.status[i] = 0;
+#ifdef DAN_PHASE_TIMING
+    int dbg_rounds = 0;
+#endif
     while (true) {
+#ifdef DAN_PHASE_TIMING
+      ++dbg_rounds;
+#endif
       for (int i = tid; i < K; i += kSortThreads) m.pending[i] = 0;
       __syncthreads();
       for (int e0 = tid; e0 < n_edges; e0 += 4 * kSortThreads) {
@@ -1036,6 +1047,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
       if (!__syncthreads_or(any ? 1 : 0)) break;
     }
     DAN_PHASE(17);
+#ifdef DAN_PHASE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) { g_phase[20] = n_edges; g_phase[21] = dbg_rounds; }
+#endif
     // ordered compaction of the kept boxes: thread t owns ranks [t*E, (t+1)*E)
     const int E = (K + kSortThreads - 1) / kSortThreads;
     int mine_cnt = 0;

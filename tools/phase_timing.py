@@ -32,6 +32,7 @@ for faces, seed in ((60, 1420), (300, 3100), (450, 4150)):
     print("K=%d kept=%d  kernel ms: %s" % (k, int(det.counts[0, 0]), [round(1e3 * v, 1) for v in ms]))
     print("  sort kernel: load+select %.1f | bitonic %.1f | decode+minmax %.1f | cell count %.1f | scan+scatter %.1f" %
           (t[8] - t[0], t[1] - t[8], t[2] - t[1], t[3] - t[2], t[4] - t[3]))
-    print("  resolve kernel: relaxation %.1f | compaction %.1f | outputs %.1f" % (t[17] - t[16], t[18] - t[17], t[19] - t[18]))
+    print("  resolve kernel: relaxation %.1f (%d edges, %d rounds) | compaction %.1f | outputs %.1f" %
+          (t[17] - t[16], buf[20], buf[21], t[18] - t[17], t[19] - t[18]))
     print("  pairs kernel (CTA 0): staging %.1f | search %.1f | flush %.1f" % (t[25] - t[24], t[26] - t[25], t[27] - t[26]))
     print("     warp 0: window setup %.1f us, item loops %.1f us, %d candidates in %d (box, class) searches" % (t[28], t[29], buf[30], buf[31]))
