@@ -61,7 +61,6 @@ struct EncArgs {
   float ps0, ps1, ps2, ps3;
   float pa_scale;
   int debug;
-  int dbg_skip;          // experiment switch (DAN_DEBUG_SKIP): 1 = pass 2 skips the GT sweep
   // workspace
   uint32_t* colmax;      // [G] fp32 bit patterns (>= 0)
   int32_t* cnt;          // [G] anchors matched per GT after stage 2
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass2_fused_kernel(const E
     const float reach = MINING ? fadd(wbest, 2.f * FLT_EPSILON) : wbest;
     int match = -1;
     float score = 0.f;
-    for (int k0 = 0; k0 < (A.dbg_skip ? 0 : ig.m_eff); k0 += 32) {
+    for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
       const int k = k0 + lane;
       bool test = false;
       if (k < ig.m_eff) {
@@ -1036,9 +1035,10 @@ static void bind_workspace(EncArgs& A, void* workspace, const WsLayout& w) {
 template <bool DENSE>
 static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, cudaStream_t st, cudaEvent_t* ev = nullptr) {
   const dim3 grid((A.n + kEncThreads - 1) / kEncThreads, batch);
-  static const int ipw_env = []() { const char* e = getenv("DAN_ENC_IMAGES_PER_WARP"); const int v = e ? atoi(e) : 1; return v >= 1 ? v : 1; }();
-  const int ipw = ipw_env;
-  static const int fthreads = []() { const char* e = getenv("DAN_ENC_THREADS"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
+  // sparse path: 128-thread CTAs, one image per CTA (sweeps on B200: 64/256 threads and 2-8 images per warp are
+  // within 2 % of this)
+  const int ipw = 1;
+  const int fthreads = 128;
   const dim3 fgrid((batch + ipw - 1) / ipw, (A.n + fthreads - 1) / fthreads);
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   if (DENSE) {
@@ -1206,7 +1206,6 @@ static int encode_core(const dan_encode_params* p, const float* a_ymin, const fl
   A.ps0 = p->prior_scaling[0]; A.ps1 = p->prior_scaling[1]; A.ps2 = p->prior_scaling[2]; A.ps3 = p->prior_scaling[3];
   A.pa_scale = p->pa_scale;
   A.debug = p->debug;
-  { static const int dbg = []() { const char* e = getenv("DAN_DEBUG_SKIP"); return e ? atoi(e) : 0; }(); A.dbg_skip = dbg; }
   A.targets = reinterpret_cast<float4*>(out_targets);
   A.labels = out_labels;
   A.scores = out_scores;

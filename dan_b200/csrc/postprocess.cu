@@ -1194,10 +1194,7 @@ static int run_sort_nms(const PpArgs& A, int lists, const float* src_scores, con
   DAN_LAUNCH_CHECK("pp_sort_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   // up to kPairCtas CTAs per list; a CTA exits at once when its list is short (see the kernel)
-  static const int ctas_env = []() { const char* e = getenv("DAN_PAIR_CTAS"); return e ? atoi(e) : 0; }();
-  int ctas = ctas_env > 0 ? ctas_env : kPairCtas;
-  ctas = ctas < 1 ? 1 : (ctas > kPairCtas ? kPairCtas : ctas);
-  nms_pairs_kernel<<<dim3(ctas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
+  nms_pairs_kernel<<<dim3(kPairCtas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
   DAN_LAUNCH_CHECK("nms_pairs_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
   nms_resolve_kernel<DECODE><<<lists, kSortThreads, nms_smem_bytes(A.nms_cap, A.keep_topk), st>>>(A, src_scores, src_boxes);
