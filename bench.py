@@ -446,8 +446,8 @@ def run_cuda(args):
     traffic = ncu_traffic()
     roof_kernel = "enc_pass2"
     achieved = alg[roof_kernel] / (kernel_ms[roof_kernel] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "enc_pass2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": (traffic or {}).get("enc_pass2_kernel"), "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "enc_pass2_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": (traffic or {}).get("enc_pass2_fused_kernel"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[roof_kernel], "kernel_ms": kernel_ms[roof_kernel],
                 "share_of_step_kernel_time": kernel_ms[roof_kernel] / step_kernel_sum,
                 "longest_kernel": dom,

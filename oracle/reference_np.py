@@ -485,3 +485,70 @@ def parse_by_class(image_shape, cls_pred, bboxes_pred, num_classes, select_thres
     if return_indices:
         return selected_bboxes, selected_scores, indices
     return selected_bboxes, selected_scores
+
+
+# --------------------------------------------------------------------------
+# per-image hard-negative mining, train_dan.py:286-324 (and the inline copy train_sfd.py:349-384)
+# --------------------------------------------------------------------------
+def mining_hard_neg(batch_size, cls_pred, location_pred, cls_targets, match_scores, loc_targets,
+                    negative_ratio=3., num_classes=2, at_least_one=True):
+    """train_dan.py:286-324 (``at_least_one=True``: the ``tf.maximum(..., 1)`` of :302) and train_sfd.py:349-384
+    (``at_least_one=False``: no such clamp; an image without positives then indexes position -1 of the sorted row,
+    which ``tf.gather_nd`` rejects on the CPU -> ValueError here).
+
+    cls_pred [B*N, C] or [B, N, C] logits, location_pred [B*N, 4], cls_targets [B, N] int64, loc_targets [B, N, 4].
+    Returns (cls_pred[final_mask], location_pred[positive_mask], clip(cls_targets)[final_mask], loc_targets[positive_mask])
+    plus the dict of intermediates the tests compare (final_mask, n_neg_select, score_at_k)."""
+    cls_targets = np.asarray(cls_targets, dtype=np.int64)
+    B, N = cls_targets.shape
+    assert B == batch_size
+    cls_flat = np.asarray(cls_pred, dtype=f32).reshape(B * N, -1)
+    loc_flat = np.asarray(location_pred, dtype=f32).reshape(B * N, 4)
+    flat_targets = cls_targets.reshape(-1)                                   # :288
+    flat_loc_targets = np.asarray(loc_targets, dtype=f32).reshape(-1, 4)     # :290
+    positive_mask = flat_targets > 0                                         # :293
+    batch_n_positives = np.count_nonzero(cls_targets > 0, axis=-1)           # :296
+    batch_negative_mask = cls_targets == 0                                   # :298
+    batch_n_negatives = np.count_nonzero(batch_negative_mask, axis=-1)       # :299
+    n_sel = (f32(negative_ratio) * batch_n_positives.astype(f32)).astype(f32).astype(i32)   # :301 to_int32 truncates
+    n_sel = np.minimum(n_sel, batch_n_negatives.astype(i32))
+    if at_least_one:
+        n_sel = np.maximum(n_sel, 1)                                         # :302
+    elif (n_sel < 1).any():
+        raise ValueError("indices[%d] = [%d, -1] does not index into param" % (int(np.argmax(n_sel < 1)), int(np.argmax(n_sel < 1))))
+    bg = softmax(cls_flat.reshape(B, N, -1))[:, :, 0]                        # :305
+    prob = np.where(batch_negative_mask, f32(0.) - bg, f32(0.) - np.ones_like(bg))   # :306-309
+    score_at_k = np.empty(B, dtype=f32)
+    for b in range(B):
+        vals, _ = tf_top_k(prob[b], N)                                       # :310 full descending sort
+        score_at_k[b] = vals[n_sel[b] - 1]                                   # :311
+    selected = prob >= score_at_k[:, None]                                   # :313
+    final_mask = np.logical_or(np.logical_and(batch_negative_mask, selected).reshape(-1), positive_mask)   # :316
+    out = (cls_flat[final_mask], loc_flat[positive_mask],
+           np.clip(flat_targets, 0, num_classes)[final_mask], flat_loc_targets[positive_mask])    # :319-322
+    return out, {"final_mask": final_mask, "n_neg_select": n_sel.astype(i32), "score_at_k": score_at_k}
+
+
+def mining_hard_neg_across_batch(batch_size, cls_pred, location_pred, cls_targets, match_scores, loc_targets,
+                                 negative_ratio=3., num_classes=2):
+    """train_dan.py:247-284: ONE selection over the flattened batch, strict ``>`` against the k-th value (:274)."""
+    flat_targets = np.asarray(cls_targets, dtype=np.int64).reshape(-1)
+    T = flat_targets.shape[0]
+    cls_flat = np.asarray(cls_pred, dtype=f32).reshape(T, -1)
+    loc_flat = np.asarray(location_pred, dtype=f32).reshape(T, 4)
+    flat_loc_targets = np.asarray(loc_targets, dtype=f32).reshape(-1, 4)
+    positive_mask = flat_targets > 0
+    negative_mask = flat_targets == 0
+    n_sel = int(np.minimum((f32(negative_ratio) * f32(np.count_nonzero(positive_mask))).astype(i32),
+                           i32(np.count_nonzero(negative_mask))))
+    if n_sel < 1:
+        raise ValueError("slice index -1 of dimension 0 out of bounds")       # topk[-1] of an empty vector
+    bg = softmax(cls_flat)[:, 0]
+    prob = np.where(negative_mask, f32(0.) - bg, f32(0.) - np.ones_like(bg))
+    vals, _ = tf_top_k(prob, n_sel)
+    selected = prob > vals[-1]
+    final_mask = np.logical_or(np.logical_and(negative_mask, selected), positive_mask)
+    out = (cls_flat[final_mask], loc_flat[positive_mask], np.clip(flat_targets, 0, num_classes)[final_mask],
+           flat_loc_targets[positive_mask])
+    return out, {"final_mask": final_mask, "n_neg_select": np.array([n_sel], dtype=i32),
+                 "score_at_k": np.array([vals[-1]], dtype=f32)}
