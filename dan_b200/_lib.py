@@ -96,6 +96,9 @@ _SIGNATURES = {
     "dan_postprocess_batch_profile": (ctypes.c_int, [ctypes.POINTER(PostprocessParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                                      c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp,
                                                      ctypes.POINTER(c_f32)]),
+    "dan_hard_negative_workspace_bytes": (c_sz, [c_i32, c_i64]),
+    "dan_hard_negative_mining": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_f32, c_i32, c_i32, c_i32,
+                                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -16,6 +16,8 @@ _ws = L.Workspace()
 
 EncodeResult = namedtuple("EncodeResult", ["targets", "labels", "scores", "matched_gt", "match"])
 Detections = namedtuple("Detections", ["boxes", "scores", "counts", "anchor_index", "keep_pos"])
+HardNegatives = namedtuple("HardNegatives", ["cls_pred", "loc_pred", "cls_targets", "loc_targets", "counts", "final_mask",
+                                             "n_neg_select", "score_at_k"])
 
 
 def _dev(t):
@@ -402,3 +404,46 @@ def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=
             return Detections(boxes, scores, counts, aidx, kpos), list(ms)
         L.check(L.lib().dan_postprocess_batch(*args))
     return Detections(boxes, scores, counts, aidx, kpos)
+
+
+# ----------------------------------------------------------------------------------
+# hard-negative mining
+# ----------------------------------------------------------------------------------
+def hard_negative_mining(cls_pred, loc_pred, cls_targets, loc_targets, rows, negative_ratio, num_classes,
+                         at_least_one=True, strict_greater=False, out=None, workspace=None):
+    """dan_hard_negative_mining: everything stays on the device and nothing synchronises.
+
+    cls_pred [rows*n, C] (or [rows, n, C]), loc_pred / loc_targets [rows*n, 4], cls_targets [rows, n] int64.
+    Returns HardNegatives whose four compacted tensors have CAPACITY rows*n; their valid lengths are
+    counts = int32 [2] = (selected rows, positive rows) on the device."""
+    L.require_device()
+    dev = _dev(cls_pred)
+    total = cls_targets.numel()
+    rows = int(rows)
+    n = total // rows if rows > 0 else 0
+    if rows * n != total:
+        raise ValueError("cls_targets has %d elements, not a multiple of rows=%d" % (total, rows))
+    c = cls_pred.numel() // total if total else int(cls_pred.shape[-1])
+    cp = cls_pred.contiguous()
+    lp = loc_pred.contiguous()
+    tg = cls_targets.contiguous()
+    lt = loc_targets.contiguous()
+    if out is None:
+        out = (torch.empty((total, c), dtype=torch.float32, device=dev), torch.empty((total, 4), dtype=torch.float32, device=dev),
+               torch.empty(total, dtype=torch.int64, device=dev), torch.empty((total, 4), dtype=torch.float32, device=dev),
+               torch.empty(2, dtype=torch.int32, device=dev), torch.empty(total, dtype=torch.uint8, device=dev),
+               torch.empty(rows, dtype=torch.int32, device=dev), torch.empty(rows, dtype=torch.float32, device=dev))
+    o_cls, o_lp, o_tg, o_lt, o_cnt, o_mask, o_nsel, o_cut = out
+    nbytes = L.lib().dan_hard_negative_workspace_bytes(rows, n)
+    ws = (workspace or _ws).get(nbytes, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_hard_negative_mining(
+            L.dev_ptr(cp, torch.float32, "cls_pred"), int(c), L.dev_ptr(tg, torch.int64, "cls_targets"),
+            L.dev_ptr(lp, torch.float32, "location_pred"), L.dev_ptr(lt, torch.float32, "loc_targets"), rows, n,
+            float(negative_ratio), int(num_classes), int(bool(at_least_one)), int(bool(strict_greater)),
+            L.dev_ptr(o_mask, torch.uint8, "final_mask"), L.dev_ptr(o_nsel, torch.int32, "n_neg_select"),
+            L.dev_ptr(o_cut, torch.float32, "score_at_k"), L.dev_ptr(o_cls, torch.float32, "out cls_pred"),
+            L.dev_ptr(o_tg, torch.int64, "out cls_targets"), L.dev_ptr(o_lp, torch.float32, "out location_pred"),
+            L.dev_ptr(o_lt, torch.float32, "out loc_targets"), L.dev_ptr(o_cnt, torch.int32, "counts"),
+            L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return HardNegatives(o_cls, o_lp, o_tg, o_lt, o_cnt, o_mask, o_nsel, o_cut)

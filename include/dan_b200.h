@@ -255,6 +255,32 @@ int dan_postprocess_batch_profile(const dan_postprocess_params* h_params, const 
                                   int32_t* out_anchor_index, int32_t* out_keep_pos, void* workspace,
                                   size_t workspace_bytes, void* stream, float* h_kernel_ms);
 
+/* ------------------------------------------------------------------------- *
+ * (f3) per-image hard-negative mining, the step after encode on the
+ * training side: mining_hard_neg, train_dan.py:286-324 (inline copy
+ * train_sfd.py:349-384) and mining_hard_neg_across_batch, train_dan.py:247-284.
+ *   cls_pred [rows*row_len, num_logits] logits; cls_targets [rows*row_len] int64
+ *   (the labels dan_encode_batch writes: 1 positive, 0 negative, -1 ignore);
+ *   loc_pred / loc_targets [rows*row_len, 4].
+ * rows = batch and row_len = anchors for the per-image rule; rows = 1 and
+ * row_len = batch*anchors with strict_greater = 1 for the across-batch rule.
+ * at_least_one: the tf.maximum(., 1) of train_dan.py:302 (0 for train_sfd.py).
+ * Outputs: out_final_mask [rows*row_len] (train_dan.py:316), out_n_neg_select
+ * [rows] int32 (:301-302), out_score_at_k [rows] (:311; NaN where n_neg_select < 1,
+ * which the reference cannot index), and the four boolean_mask results (:319-322)
+ * compacted in order into caller buffers of capacity rows*row_len rows, their
+ * lengths in out_counts[2] = {selected rows, positive rows}.
+ * ------------------------------------------------------------------------- */
+size_t dan_hard_negative_workspace_bytes(int32_t rows, int64_t row_len);
+int dan_hard_negative_mining(const float* cls_pred, int32_t num_logits, const int64_t* cls_targets,
+                             const float* loc_pred, const float* loc_targets, int32_t rows,
+                             int64_t row_len, float negative_ratio, int32_t num_classes,
+                             int32_t at_least_one, int32_t strict_greater, uint8_t* out_final_mask,
+                             int32_t* out_n_neg_select, float* out_score_at_k, float* out_cls_pred,
+                             int64_t* out_cls_targets, float* out_loc_pred, float* out_loc_targets,
+                             int32_t* out_counts, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -566,3 +566,77 @@ def test_postprocess_errors(cuda):
         bu.parse_by_class_batch([64, 64], cls.cpu(), 2, 0.1, 0, 100, 10, 0.3, bboxes_pred=box)      # no CPU fallback
     det = bu.parse_by_class_batch([64, 64], cls, 2, 0.9, 0, 100, 10, 0.3, bboxes_pred=box)
     assert int(det.counts.sum()) == 0 and not det.scores.any()
+
+
+# ------------------------------------------------------------------------------------------------
+# hard-negative mining
+# ------------------------------------------------------------------------------------------------
+def _hnm_inputs(seed, B, N, C=2, quantise=False, pos_rate=0.02):
+    rng = np.random.default_rng(seed)
+    cls = rng.normal(0., 3., size=(B, N, C)).astype(np.float32)
+    if quantise:
+        cls = np.round(cls)
+    tg = rng.choice([-1, 0, 1], p=[0.05, 0.95 - pos_rate, pos_rate], size=(B, N)).astype(np.int64)
+    loc = rng.normal(size=(B * N, 4)).astype(np.float32)
+    lt = rng.normal(size=(B, N, 4)).astype(np.float32)
+    return cls, loc, tg, lt
+
+
+def _check_hnm(ref, aux, got, det):
+    for name, r, g in zip(("cls_pred", "location_pred", "cls_targets", "loc_targets"), ref, got):
+        assert tuple(g.shape) == r.shape, name
+        np.testing.assert_array_equal(_np(g), r, err_msg=name)
+    np.testing.assert_array_equal(_np(det.final_mask).astype(bool), aux["final_mask"])
+    np.testing.assert_array_equal(_np(det.n_neg_select), aux["n_neg_select"])
+    np.testing.assert_array_equal(_np(det.score_at_k).view(np.uint32), aux["score_at_k"].view(np.uint32))
+
+
+@pytest.mark.parametrize("B,N,C,quantise", [(4, 3000, 2, False), (3, 34125, 2, False), (2, 5000, 3, True), (5, 777, 2, True)])
+def test_hard_negative_mining_vs_oracle(cuda, oracle, B, N, C, quantise):
+    from dan_b200.utility import hard_negative_mining as hnm
+    cls, loc, tg, lt = _hnm_inputs(70 + B, B, N, C, quantise)
+    tg[-1] = np.where(tg[-1] > 0, 0, tg[-1])                # one image without positives: the max(., 1) clamp
+    ref, aux = oracle.mining_hard_neg(B, cls, loc, tg, None, lt, negative_ratio=3., num_classes=C)
+    got, det = hnm.mining_hard_neg(B, to_dev(cls.reshape(B * N, C), cuda), to_dev(loc, cuda), to_dev(tg, cuda), None,
+                                   to_dev(lt, cuda), negative_ratio=3., num_classes=C, return_details=True)
+    _check_hnm(ref, aux, got, det)
+    with pytest.raises(ValueError):                         # train_sfd.py rule: no clamp -> position -1
+        hnm.mining_hard_neg(B, to_dev(cls, cuda), to_dev(loc, cuda), to_dev(tg, cuda), None, to_dev(lt, cuda),
+                            at_least_one=False)
+
+
+def test_hard_negative_mining_across_batch_vs_oracle(cuda, oracle):
+    from dan_b200.utility import hard_negative_mining as hnm
+    # the last case is one row of 477 750 keys: slices beyond the shared-memory staging capacity (keys re-read from L2)
+    for quantise, B, N in ((False, 3, 4000), (True, 3, 4000), (False, 14, 34125)):
+        cls, loc, tg, lt = _hnm_inputs(80, B, N, 2, quantise)
+        ref, aux = oracle.mining_hard_neg_across_batch(B, cls, loc, tg, None, lt)
+        got, det = hnm.mining_hard_neg_across_batch(B, to_dev(cls, cuda), to_dev(loc, cuda), to_dev(tg, cuda), None,
+                                                    to_dev(lt, cuda), return_details=True)
+        _check_hnm(ref, aux, got, det)
+
+
+def test_hard_negative_mining_after_encode_full_size(cuda, s3fd_anchors_np):
+    """config 2 shape (batch 32 x 34 125 anchors): labels straight from encode_all_anchors; size-independent properties."""
+    import torch
+    from dan_b200.utility import anchor_manipulator as am, hard_negative_mining as hnm
+    enc = am.AnchorEncoder(0.4, 0.4, PS)
+    anchors = [to_dev(v, cuda) for v in s3fd_anchors_np]
+    B, N = 32, s3fd_anchors_np[0].shape[0]
+    cat, offs = synthetic.to_csr([synthetic.gen_faces(300 + i, 50) for i in range(B)])
+    res = enc.encode_all_anchors(to_dev(cat, cuda), to_dev(offs, cuda), *anchors, match_mining=True)
+    g = torch.Generator(device=cuda).manual_seed(3)
+    cls = torch.randn((B, N, 2), device=cuda, generator=g) * 3.
+    loc = torch.randn((B * N, 4), device=cuda, generator=g)
+    (c, l, t, lt), det = hnm.mining_hard_neg(B, cls, loc, res.labels, res.scores, res.targets, return_details=True)
+    labels = res.labels
+    n_pos = (labels > 0).sum(-1)
+    n_neg = (labels == 0).sum(-1)
+    want = torch.clamp(torch.minimum(3 * n_pos, n_neg), min=1).to(torch.int32)
+    assert torch.equal(det.n_neg_select, want)
+    fm = det.final_mask.view(B, N).bool()
+    assert torch.equal((fm & (labels == 0)).sum(-1).to(torch.int32), want)            # continuous logits: no ties
+    assert bool(fm[labels > 0].all()) and not bool(fm[labels < 0].any())
+    assert c.shape[0] == int(fm.sum()) and l.shape[0] == int(n_pos.sum())
+    assert torch.equal(c, cls.view(-1, 2)[fm.view(-1)]) and torch.equal(t, labels.view(-1)[fm.view(-1)].clamp(0, 2))
+    assert torch.equal(l, loc[labels.view(-1) > 0]) and torch.equal(lt, res.targets.view(-1, 4)[labels.view(-1) > 0])
