@@ -59,6 +59,7 @@ struct PpArgs {
   int keep_topk, nms_topk;
   int nms_cap;                // kept-list capacity in shared memory = min(nms_topk, keep_topk)
   float nms_thr;
+  int force_rounds;           // 1: the pair kernel's staging does not fit shared memory -> round-based NMS for every list
   // workspace
   unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
   int32_t* key_count;         // [L]
@@ -775,7 +776,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
     A.s_len[list] = K;
     A.grid_info[list] = make_float4(g.oy, g.ox, g.extent, __int_as_float(s_class_mask));
     A.edge_n[list] = 0;
-    A.ovf[list] = (A.nms_thr < 0.f) ? 1 : 0;     // disjoint boxes suppress too: no spatial pruning possible
+    A.ovf[list] = (A.nms_thr < 0.f || A.force_rounds) ? 1 : 0;     // thr < 0: disjoint boxes suppress too, no spatial pruning
   }
   if (tid < kNmsClasses) A.class_amin[list * 16 + tid] = __int_as_float(s_class_amin[tid]);
 }
@@ -1168,7 +1169,7 @@ static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
 }
 
 static bool nms_fits(int nms_cap, int keep_topk) {
-  return nms_smem_bytes(nms_cap, keep_topk) <= kNmsSmemMax && pairs_smem_bytes(keep_topk) <= kNmsSmemMax;
+  return nms_smem_bytes(nms_cap, keep_topk) <= kNmsSmemMax;   // (the pair kernel is skipped when ITS staging does not fit)
 }
 
 static int enable_big_smem() {
@@ -1188,14 +1189,18 @@ static int enable_big_smem() {
 // sort+grid -> pairs -> resolve for `lists` lists whose keys are in the workspace; ev (optional): 3 events, one after
 // each kernel
 template <bool DECODE>
-static int run_sort_nms(const PpArgs& A, int lists, const float* src_scores, const float4* src_boxes, cudaStream_t st,
+static int run_sort_nms(const PpArgs& A_in, int lists, const float* src_scores, const float4* src_boxes, cudaStream_t st,
                         cudaEvent_t* ev = nullptr) {
+  PpArgs A = A_in;
+  A.force_rounds = pairs_smem_bytes(A.keep_topk) > kNmsSmemMax ? 1 : 0;     // very long lists (> ~6 500 candidates)
   pp_sort_kernel<DECODE><<<lists, kSortThreads, kSortSmem, st>>>(A, src_boxes);
   DAN_LAUNCH_CHECK("pp_sort_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   // up to kPairCtas CTAs per list; a CTA exits at once when its list is short (see the kernel)
-  nms_pairs_kernel<<<dim3(kPairCtas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
-  DAN_LAUNCH_CHECK("nms_pairs_kernel");
+  if (!A.force_rounds) {
+    nms_pairs_kernel<<<dim3(kPairCtas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
+    DAN_LAUNCH_CHECK("nms_pairs_kernel");
+  }
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
   nms_resolve_kernel<DECODE><<<lists, kSortThreads, nms_smem_bytes(A.nms_cap, A.keep_topk), st>>>(A, src_scores, src_boxes);
   DAN_LAUNCH_CHECK("nms_resolve_kernel");
