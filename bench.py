@@ -222,6 +222,11 @@ def run_cuda(args):
     L = max(1, args.inflight)
     R = (R + L - 1) // L * L                  # a set always runs on the same lane
     ws_lanes = [(_lib.Workspace(), _lib.Workspace()) for _ in range(L)]
+    # the detection slabs of the L sets of a group are contiguous: at N > 1 ONE all-gather moves the detections of L steps
+    # (a collective per step costs ~50 us of host time in torch.distributed, more than a step takes on the GPU)
+    slab_words = pipeline.DetectionSlab.words_for(B, pp_params.num_classes - 1, pp_params.nms_topk)
+    group_send = [torch.zeros(L * slab_words, dtype=torch.float32, device=dev) for _ in range(R // L)]
+    group_recv = [torch.empty(world * L * slab_words, dtype=torch.float32, device=dev) for _ in range(R // L)] if world > 1 else None
     sets = []
     for r in range(R):
         order = [(i + r) % B for i in range(B)]
@@ -231,7 +236,8 @@ def run_cuda(args):
              "loc": torch.from_numpy(np.stack([preds[i][1] for i in order])).pin_memory()}
         d = {k: v.to(dev) for k, v in h.items()}
         hp = pipeline.HotPath(a_train[:4], a_train[4], enc_params, pp_params, anchors_eval=a_eval[:4],
-                              workspaces=ws_lanes[r % L], overlap=not args.no_overlap)
+                              workspaces=ws_lanes[r % L], overlap=not args.no_overlap,
+                              slab_buffer=group_send[r // L][(r % L) * slab_words:(r % L + 1) * slab_words])
         sets.append({"host": h, "dev": d, "hp": hp, "total_gt": int(offs[-1])})
     total_gt_mean = float(np.mean([s["total_gt"] for s in sets]))
 
@@ -258,37 +264,48 @@ def run_cuda(args):
     # the all-gather of step k runs on its own stream and overlaps the compute of step k+1 (different buffer set);
     # a set is not replayed again before its previous gather has finished
     comm = torch.cuda.Stream() if world > 1 else None
-    ev_comm = [torch.cuda.Event() for _ in range(R)]
+    ev_comm = [torch.cuda.Event() for _ in range(R // L)]
     main = torch.cuda.current_stream()
     lanes = [torch.cuda.Stream() for _ in range(L)]
+    pending = []                 # streams holding steps whose detections have not been gathered yet
 
     def lane_of(k, serial=False):
         return lanes[0] if serial else lanes[(k % R) % L]
 
+    def flush_gather(g):
+        """All-gather of group g's slabs on the communication stream; overlaps the compute of the following steps
+        (other buffer sets).  A set is not replayed again before the gather that reads its slab has finished."""
+        for ln in set(pending):
+            comm.wait_stream(ln)
+        del pending[:]
+        with torch.cuda.stream(comm):
+            pipeline.gather_slab_group(group_send[g], group_recv[g])
+            ev_comm[g].record(comm)
+
     def step(k, gather=True, serial=False):
         """Enqueue step k on its lane's stream (serial=True: every step on lane 0, one after the other)."""
-        s = sets[k % R]
+        r = k % R
+        s = sets[r]
         cur = lane_of(k, serial)
         if comm is not None:
-            cur.wait_event(ev_comm[k % R])
+            cur.wait_event(ev_comm[r // L])
         with torch.cuda.stream(cur):
             if graphs:
-                graphs[k % R].replay()
+                graphs[r].replay()
             else:
                 run_set(s)
         if comm is not None and gather:
-            comm.wait_stream(cur)
-            with torch.cuda.stream(comm):
-                out = s["hp"].gather(world)
-                ev_comm[k % R].record(comm)
-            return out
-        return None
+            pending.append(cur)
+            if r % L == L - 1:
+                flush_gather(r // L)
 
     def fork():
         for ln in lanes:
             ln.wait_stream(main)
 
-    def drain():
+    def drain(last_k=None):
+        if comm is not None and pending and last_k is not None:
+            flush_gather((last_k % R) // L)          # the last, incomplete group
         for ln in lanes:
             main.wait_stream(ln)
         if comm is not None:
@@ -306,6 +323,8 @@ def run_cuda(args):
     fork()
     for k in range(W):
         step(k)
+    drain(W - 1)
+    fork()
     t_warm = time.time() + 0.5
     k = 0
     while time.time() < t_warm:
@@ -326,7 +345,7 @@ def run_cuda(args):
         fork()
         for k in range(K):
             step(W + k, serial=serial)
-        drain()
+        drain(W + K - 1)
         e1.record()
         barrier()
         return e0.elapsed_time(e1)

@@ -40,7 +40,9 @@ class DetectionSlab(object):
     with L = num_classes - 1 and K = nms_topk.  ``views()`` returns typed views that the NMS kernel
     writes in place, so the slab needs no packing step before the collective."""
 
-    def __init__(self, images, lists, nms_topk, device):
+    def __init__(self, images, lists, nms_topk, device, buf=None):
+        """``buf``: optional caller-owned fp32 storage of exactly words_for(...) words (e.g. a slice of a larger send
+        buffer, so that the slabs of several steps travel in one collective)."""
         self.images, self.lists, self.k = int(images), int(lists), int(nms_topk)
         self.n_counts = self.images * self.lists
         self.n_scores = self.n_counts * self.k
@@ -48,7 +50,11 @@ class DetectionSlab(object):
         # counts region padded to 4 words so that the box region stays 16-byte aligned
         self.counts_words = (self.n_counts + 3) // 4 * 4
         self.words = self.counts_words + self.n_scores + self.n_boxes
-        self.buf = torch.zeros(self.words, dtype=torch.float32, device=device)
+        if buf is None:
+            buf = torch.zeros(self.words, dtype=torch.float32, device=device)
+        if buf.numel() != self.words or buf.dtype != torch.float32 or not buf.is_contiguous():
+            raise ValueError("slab buffer must be %d contiguous fp32 words" % self.words)
+        self.buf = buf
 
     @staticmethod
     def words_for(images, lists, nms_topk):
@@ -78,6 +84,14 @@ def gather_detections(slab, world_size, group=None):
     return [slab.views(out[r * slab.words:(r + 1) * slab.words]) for r in range(world_size)]
 
 
+def gather_slab_group(send, recv, group=None):
+    """ONE collective for the slabs of several consecutive steps: ``send`` is a contiguous buffer holding their
+    DetectionSlabs back to back, ``recv`` has world_size times its size (rank-major)."""
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv
+
+
 def flatten_detections(gathered, image_counts=None):
     """Ragged result for the host: list over images (global order) of dict(class -> (boxes [n,4], scores [n])).
     `image_counts[r]` = number of real images of rank r (ranks may own fewer images than the slab capacity)."""
@@ -101,7 +115,7 @@ class HotPath(object):
     (inside a CUDA-graph capture this becomes two parallel branches); each half has its own workspace."""
 
     def __init__(self, anchors_train, inside_mask, encode_params, postprocess_params, anchors_eval=None,
-                 images_per_rank=None, workspaces=None, overlap=True):
+                 images_per_rank=None, workspaces=None, overlap=True, slab_buffer=None):
         from . import _lib
         self.anchors_train = anchors_train          # (ymin, xmin, ymax, xmax)
         self.inside_mask = inside_mask
@@ -113,6 +127,7 @@ class HotPath(object):
         self.ws_enc, self.ws_pp = workspaces if workspaces is not None else (_lib.Workspace(), _lib.Workspace())
         self.overlap = overlap
         self._side = None
+        self._slab_buffer = slab_buffer             # optional caller-owned storage of the detection slab
         self._slab = None
         self._enc_out = None
         self._aux = None
@@ -122,7 +137,7 @@ class HotPath(object):
         k, lists = self.pp_params.nms_topk, self.pp_params.num_classes - 1
         cap = images if self.images_per_rank is None else self.images_per_rank
         if self._slab is None or self._slab.images != cap:
-            self._slab = DetectionSlab(cap, lists, k, self.device)
+            self._slab = DetectionSlab(cap, lists, k, self.device, buf=self._slab_buffer)
             self._aux = (torch.empty((cap, lists, k), dtype=torch.int32, device=self.device),
                          torch.empty((cap, lists, k), dtype=torch.int32, device=self.device))
         if self._enc_out is None or self._enc_out[0].shape[0] != images:
