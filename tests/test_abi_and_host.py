@@ -171,6 +171,18 @@ def _gather_worker(rank, world, port, q):
     for g, det in enumerate(flat):
         b, s = det[1]
         ok = ok and b.shape[0] == g % 5 and bool((s == float(g)).all()) and bool((b == float(g) + 0.5).all())
+    # the slabs of several steps in one send buffer -> ONE collective for the group (bench.py's steps in flight)
+    import torch
+    words = pipeline.DetectionSlab.words_for(cap, 1, 8)
+    send = torch.zeros(3 * words)
+    slabs = [pipeline.DetectionSlab(cap, 1, 8, "cpu", buf=send[j * words:(j + 1) * words]) for j in range(3)]
+    for j, sl in enumerate(slabs):
+        sl.views()[0][:] = 100 * rank + j
+    recv = pipeline.gather_slab_group(send, torch.empty(world * 3 * words))
+    for r in range(world):
+        for j, sl in enumerate(slabs):
+            c = sl.views(recv[(r * 3 + j) * words:(r * 3 + j + 1) * words])[0]
+            ok = ok and bool((c == 100 * r + j).all())
     q.put((rank, ok))
     dist.destroy_process_group()
 
