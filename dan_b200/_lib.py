@@ -62,6 +62,12 @@ class PostprocessParams(ctypes.Structure):
     ]
 
 
+class RoutingLayers(ctypes.Structure):
+    """dan_routing_layers of include/dan_b200.h."""
+    _fields_ = [("num_layers", c_i32), ("feat_height", c_i32 * 16), ("feat_width", c_i32 * 16), ("anchor_depth", c_i32 * 16),
+                ("feat_strides", c_i32 * 16)]
+
+
 _SIGNATURES = {
     "dan_version": (ctypes.c_int, []),
     "dan_last_error": (ctypes.c_char_p, []),
@@ -99,6 +105,9 @@ _SIGNATURES = {
     "dan_hard_negative_workspace_bytes": (c_sz, [c_i32, c_i64]),
     "dan_hard_negative_mining": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_f32, c_i32, c_i32, c_i32,
                                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_routing_workspace_bytes": (c_sz, [c_i64, c_i32]),
+    "dan_dynamic_anchor_routing_eval": (ctypes.c_int, [ctypes.POINTER(RoutingLayers), c_vp, c_vp, c_vp, c_vp, c_i64, c_i32,
+                                                       c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -447,3 +447,49 @@ def hard_negative_mining(cls_pred, loc_pred, cls_targets, loc_targets, rows, neg
             L.dev_ptr(o_lt, torch.float32, "out loc_targets"), L.dev_ptr(o_cnt, torch.int32, "counts"),
             L.dev_ptr(ws), nbytes, L.stream_ptr()))
     return HardNegatives(o_cls, o_lp, o_tg, o_lt, o_cnt, o_mask, o_nsel, o_cut)
+
+
+# ----------------------------------------------------------------------------------
+# DynamicAnchorRouting, evaluation branch
+# ----------------------------------------------------------------------------------
+def routing_layers(feat_heights, feat_widths, anchor_depths, feat_strides):
+    n = len(feat_heights)
+    if not (len(feat_widths) == len(anchor_depths) == len(feat_strides) == n):
+        raise ValueError("per-layer lists must have the same length")
+    if not 1 <= n <= 16:
+        raise ValueError("1..16 layers")
+    lay = L.RoutingLayers()
+    lay.num_layers = n
+    for i in range(n):
+        lay.feat_height[i], lay.feat_width[i] = int(feat_heights[i]), int(feat_widths[i])
+        lay.anchor_depth[i], lay.feat_strides[i] = int(anchor_depths[i]), int(feat_strides[i])
+    return lay
+
+
+def dynamic_anchor_routing_eval(layers, anchors, gt_targets, labels, mask_in, workspace=None):
+    """dan_dynamic_anchor_routing_eval: anchors / gt_targets [B, N, 4] (or [N, 4]), labels / mask_in [B, N] (or [N]).
+    -> (mask_out int32, decode_out fp32) shaped like the inputs."""
+    Lib = L.lib()
+    L.require_device()
+    dev = _dev(anchors)
+    a = anchors.contiguous()
+    t = gt_targets.contiguous()
+    lb = labels.contiguous()
+    m = mask_in.contiguous()
+    n = sum(layers.feat_height[i] * layers.feat_width[i] * layers.anchor_depth[i] for i in range(layers.num_layers))
+    total = lb.numel()
+    if n <= 0 or total % n != 0:
+        raise ValueError("labels has %d elements, the layers hold %d anchors" % (total, n))
+    batch = total // n
+    if a.numel() != total * 4 or t.numel() != total * 4 or m.numel() != total:
+        raise ValueError("anchors and gt_targets must be [.., 4] and mask_in like labels")
+    mask_out = torch.empty(lb.shape, dtype=torch.int32, device=dev)
+    decode_out = torch.empty(a.shape, dtype=torch.float32, device=dev)
+    nbytes = Lib.dan_routing_workspace_bytes(n, batch)
+    ws = (workspace or _ws).get(nbytes, dev)
+    with torch.cuda.device(dev):
+        L.check(Lib.dan_dynamic_anchor_routing_eval(
+            ctypes.byref(layers), L.dev_ptr(a, torch.float32, "anchors"), L.dev_ptr(t, torch.float32, "gt_targets"),
+            L.dev_ptr(lb, torch.float32, "labels"), L.dev_ptr(m, torch.int32, "mask_in"), n, batch, L.dev_ptr(mask_out),
+            L.dev_ptr(decode_out), L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return mask_out, decode_out

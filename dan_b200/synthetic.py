@@ -183,3 +183,33 @@ def gen_predictions(image_index, anchors, size=(640, 640), max_faces=300, prior_
         loc[fg] = enc + rng.normal(0.0, 0.3, (nf, 4))
         cls[fg] = np.stack([rng.normal(0.0, 1.0, nf), rng.normal(5.0, 1.0, nf)], axis=1)
     return cls.astype(f32), loc.astype(f32), faces
+
+
+def gen_routing(image_index, feat_heights, feat_widths, depths, strides, mode="plain"):
+    """Inputs of DynamicAnchorRouting's evaluation branch for one image, all layers concatenated (layer by layer,
+    (y, x, depth) inside a layer) -> (anchors [N,4], gt_targets [N,4], labels [N], mask_in [N] int32).
+
+    Decoded stage-1 boxes = a box centred near the anchor's cell (sigma 1.5 cells, so boxes really move to other
+    cells and some leave the feature map), stage-2 offsets already divided by 2 x prior scaling (eval_dan.py:384),
+    stage-2 probabilities, stage-1 mask (~60 % ones).  mode "ties": box centres snapped to half cells (std::round
+    sees exact .5 values), probabilities quantised to 1/8 (equal labels, exact zeros), some degenerate boxes."""
+    rng = np.random.default_rng(BASE_SEED + 400000 + image_index)
+    out = []
+    for H, W, D, S in zip(feat_heights, feat_widths, depths, strides):
+        n = H * W * D
+        yy, xx, _ = np.meshgrid(np.arange(H), np.arange(W), np.arange(D), indexing="ij")
+        cy = (yy.reshape(-1) + 0.5) * S + rng.normal(0, 1.5 * S, n)
+        cx = (xx.reshape(-1) + 0.5) * S + rng.normal(0, 1.5 * S, n)
+        h = np.abs(rng.normal(4 * S, 2 * S, n))
+        w = np.abs(rng.normal(4 * S, 2 * S, n))
+        lab = rng.uniform(0, 1, n)
+        if mode == "ties":
+            cy, cx = np.round(cy / (S / 2)) * (S / 2), np.round(cx / (S / 2)) * (S / 2)
+            h, w = np.round(h), np.round(w)
+            lab = np.round(lab * 8) / 8
+            h[::37] = 0.5                                  # narrower than one pixel: never a source
+        a = np.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], -1)
+        t = rng.normal(0, 1, (n, 4)) / np.array([20., 20., 10., 10.])
+        m = (rng.uniform(0, 1, n) > 0.4).astype(np.int32)
+        out.append((a.astype(f32), t.astype(f32), lab.astype(f32), m))
+    return tuple(np.concatenate([o[k] for o in out], 0) for k in range(4))

@@ -281,6 +281,37 @@ int dan_hard_negative_mining(const float* cls_pred, int32_t num_logits, const in
                              int32_t* out_counts, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * (f1) DynamicAnchorRouting, EVALUATION branch
+ * (cpp/ExtraLib/dynamic_anchor_routing.cc:328-408; op definition :31-59; called once
+ * per pyramid layer and image on /cpu:0 by eval_dan.py:383-391).  One call handles
+ * all layers of all images of a batch; a single layer with batch 1 is the op itself.
+ *   anchors    [B, N, 4] decoded stage-1 boxes (ymin, xmin, ymax, xmax)
+ *   gt_targets [B, N, 4] stage-2 offsets (cy, cx, h, w) already divided by the
+ *                        prior scaling (eval_dan.py:384)
+ *   labels     [B, N]    stage-2 probability;  mask_in [B, N] int32 (stage-1 score > thres)
+ * with N = sum over layers of feat_height*feat_width*anchor_depth, anchors ordered
+ * layer by layer, (y, x, depth) inside a layer.
+ *   mask_out [B, N] int32 in {0, 1};  decode_out [B, N, 4] the stage-2 boxes.
+ * The op's attrs `thres` / `ignore_thres` and inputs img_height / img_width are not
+ * used by the evaluation branch.  The training branch draws from an unseeded
+ * std::random_device and is not provided.
+ * ------------------------------------------------------------------------- */
+typedef struct dan_routing_layers {
+  int32_t num_layers;
+  int32_t feat_height[DAN_MAX_LAYERS];
+  int32_t feat_width[DAN_MAX_LAYERS];
+  int32_t anchor_depth[DAN_MAX_LAYERS];
+  int32_t feat_strides[DAN_MAX_LAYERS];
+} dan_routing_layers;
+
+size_t dan_routing_workspace_bytes(int64_t num_anchors, int32_t batch);
+int dan_dynamic_anchor_routing_eval(const dan_routing_layers* h_layers, const float* anchors,
+                                    const float* gt_targets, const float* labels,
+                                    const int32_t* mask_in, int64_t num_anchors, int32_t batch,
+                                    int32_t* mask_out, float* decode_out, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,4 +159,62 @@ int oracle_tf_nms(const float* boxes, const float* scores, int32_t num_boxes, in
   return static_cast<int32_t>(kept.size());
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// DynamicAnchorRouting, EVALUATION branch (cpp/ExtraLib/dynamic_anchor_routing.cc:328-408), one layer.
+// Our restatement, written as the two phases the CUDA path uses, so that the phase split itself is what gets pinned
+// against the reference's sequential loop (oracle/_ref/libdar_ref.so):
+//   phase 1  every source anchor i (mask_in >= 1, a box of at least 1x1 px that is not more than one cell outside the
+//            feature map) is re-binned to the cell of its rounded centre, same depth slot -> target t (:352-369).
+//            The reference keeps, per target, the running STRICT maximum of the label in index order (:370-381), but a
+//            target that is itself easy background (mask_in[t] < 1) turns to -1 when the loop reaches i == t (:331-334)
+//            and rejects every later source (:371): such a target only sees sources i < t.
+//            => winner(t) = max label, ties -> lowest index, over the admissible sources; labels <= 0 never win.
+//   phase 2  mask_out[t] = 1 iff mask_in[t] >= 1 and t has a winner (:384); the winner's box (or zeros) is the prior
+//            that the stage-2 offsets gt_targets[t] are decoded against, in the reference's mixed float/double
+//            arithmetic (:385-406); std::exp(float) is libm's expf.
+// ---------------------------------------------------------------------------------------------
+int oracle_dynamic_anchor_routing_eval(const float* anchors, const float* gt_targets, const float* labels,
+                                       const int32_t* mask_in, int64_t num_anchors, int32_t feat_height,
+                                       int32_t feat_width, int32_t anchor_depth, int32_t feat_strides,
+                                       int32_t* mask_out, float* decode_out) {
+  std::vector<int64_t> winner(num_anchors > 0 ? num_anchors : 1, -1);
+  for (int64_t i = 0; i < num_anchors; ++i) {
+    if (mask_in[i] < 1) continue;
+    const float ymin = anchors[i * 4], xmin = anchors[i * 4 + 1], ymax = anchors[i * 4 + 2], xmax = anchors[i * 4 + 3];
+    if (xmax - xmin < 1 || ymax - ymin < 1) continue;
+    if (xmin / feat_strides < -1 || xmax / feat_strides > feat_width + 1 - 1.) continue;
+    if (ymin / feat_strides < -1 || ymax / feat_strides > feat_height + 1 - 1.) continue;
+    int64_t cx = static_cast<int64_t>(std::round((xmin + xmax) / (2. * feat_strides)));
+    int64_t cy = static_cast<int64_t>(std::round((ymin + ymax) / (2. * feat_strides)));
+    cx = std::max<int64_t>(std::min<int64_t>(cx, feat_width - 1), 0);
+    cy = std::max<int64_t>(std::min<int64_t>(cy, feat_height - 1), 0);
+    const int64_t t = (cy * feat_width + cx) * anchor_depth + i % anchor_depth;
+    if (mask_in[t] < 1 && i > t) continue;                 // the target has already turned to -1
+    if (!(labels[i] > 0.f)) continue;
+    if (winner[t] < 0 || labels[i] > labels[winner[t]]) winner[t] = i;    // ascending i: ties keep the lowest index
+  }
+  for (int64_t t = 0; t < num_anchors; ++t) {
+    const int64_t w = winner[t];
+    mask_out[t] = (w >= 0 && mask_in[t] >= 1) ? 1 : 0;
+    const float ymin = w >= 0 ? anchors[w * 4] : 0.f, xmin = w >= 0 ? anchors[w * 4 + 1] : 0.f;
+    const float ymax = w >= 0 ? anchors[w * 4 + 2] : 0.f, xmax = w >= 0 ? anchors[w * 4 + 3] : 0.f;
+    const float prior_cy = (ymin + ymax) / 2.;
+    const float prior_cx = (xmin + xmax) / 2.;
+    const float prior_h = (ymax - ymin + 1.);
+    const float prior_w = (xmax - xmin + 1.);
+    float pred_cy = gt_targets[t * 4], pred_cx = gt_targets[t * 4 + 1];
+    float pred_h = gt_targets[t * 4 + 2], pred_w = gt_targets[t * 4 + 3];
+    pred_h = std::exp(pred_h) * prior_h;
+    pred_w = std::exp(pred_w) * prior_w;
+    pred_cy = pred_cy * prior_h + prior_cy;
+    pred_cx = pred_cx * prior_w + prior_cx;
+    decode_out[t * 4] = pred_cy - (pred_h - 1.) / 2.;
+    decode_out[t * 4 + 1] = pred_cx - (pred_w - 1.) / 2.;
+    decode_out[t * 4 + 2] = pred_cy + (pred_h - 1.) / 2.;
+    decode_out[t * 4 + 3] = pred_cx + (pred_w - 1.) / 2.;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -36,6 +36,9 @@ def _port():
         lib.oracle_tf_nms.restype = ctypes.c_int
         lib.oracle_tf_nms.argtypes = [_f32p, _f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
                                       ctypes.c_int32, _i32p]
+        lib.oracle_dynamic_anchor_routing_eval.restype = ctypes.c_int
+        lib.oracle_dynamic_anchor_routing_eval.argtypes = [_f32p, _f32p, _f32p, _i32p, ctypes.c_int64] + [ctypes.c_int32] * 4 + \
+                                                          [_i32p, _f32p]
         _PORT = lib
     return _PORT
 
@@ -79,3 +82,48 @@ def tf_non_max_suppression(boxes, scores, max_output_size, iou_threshold, tie="s
                                 int(max_output_size), float(iou_threshold),
                                 1 if tie == "std_sort" else 0, out.ctypes.data_as(_i32p))
     return out[:cnt].copy()
+
+
+_REF_DAR = None
+
+
+def have_reference_dar():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libdar_ref.so"))
+
+
+def _ref_dar():
+    global _REF_DAR
+    if _REF_DAR is None:
+        lib = ctypes.CDLL(os.path.join(_HERE, "_ref", "libdar_ref.so"))
+        lib.ref_dynamic_anchor_routing.restype = ctypes.c_int
+        lib.ref_dynamic_anchor_routing.argtypes = [_f32p, _f32p, _f32p, _i32p, ctypes.c_int64] + [ctypes.c_int32] * 7 + \
+                                                  [ctypes.c_float, ctypes.c_float, _i32p, _f32p]
+        _REF_DAR = lib
+    return _REF_DAR
+
+
+def dynamic_anchor_routing(anchors, gt_targets, labels, mask_in, feat_height, feat_width, anchor_depth, feat_strides,
+                           img_height, img_width, trainging=False, thres=0.03, ignore_thres=0.0, impl="port"):
+    """One layer of the DynamicAnchorRouting op (dynamic_anchor_routing.cc:31-59) -> (mask_out int32 [n], decode_out [n,4]).
+    impl="reference": the reference's own functor (both branches; the training branch draws from std::random_device);
+    impl="port": our restatement of the EVALUATION branch only."""
+    anchors = np.ascontiguousarray(anchors, dtype=np.float32).reshape(-1, 4)
+    gt_targets = np.ascontiguousarray(gt_targets, dtype=np.float32).reshape(-1, 4)
+    labels = np.ascontiguousarray(labels, dtype=np.float32).reshape(-1)
+    mask_in = np.ascontiguousarray(mask_in, dtype=np.int32).reshape(-1)
+    n = anchors.shape[0]
+    assert gt_targets.shape[0] == n and labels.shape[0] == n and mask_in.shape[0] == n
+    if not (0. <= thres < 1.) or not (0. <= ignore_thres < 1.):        # dynamic_anchor_routing.cc:527-529
+        raise ValueError("Need Attr 1 > thres >= 0. and 1 > ignore_thres >= 0.")
+    mask_out = np.zeros(n, dtype=np.int32)
+    decode_out = np.zeros((n, 4), dtype=np.float32)
+    a = (anchors.ctypes.data_as(_f32p), gt_targets.ctypes.data_as(_f32p), labels.ctypes.data_as(_f32p),
+         mask_in.ctypes.data_as(_i32p), n, int(feat_height), int(feat_width), int(anchor_depth), int(feat_strides))
+    if impl == "reference":
+        _ref_dar().ref_dynamic_anchor_routing(*a, int(img_height), int(img_width), int(bool(trainging)), float(thres),
+                                              float(ignore_thres), mask_out.ctypes.data_as(_i32p), decode_out.ctypes.data_as(_f32p))
+    else:
+        if trainging:
+            raise NotImplementedError("the training branch draws from std::random_device (unseeded): not restated")
+        _port().oracle_dynamic_anchor_routing_eval(*a, mask_out.ctypes.data_as(_i32p), decode_out.ctypes.data_as(_f32p))
+    return mask_out, decode_out

@@ -552,3 +552,44 @@ def mining_hard_neg_across_batch(batch_size, cls_pred, location_pred, cls_target
            flat_loc_targets[positive_mask])
     return out, {"final_mask": final_mask, "n_neg_select": np.array([n_sel], dtype=i32),
                  "score_at_k": np.array([vals[-1]], dtype=f32)}
+
+
+# --------------------------------------------------------------------------
+# DynamicAnchorRouting (C++ op) -- the oracle is native code (oracle/native.py); the only numpy piece
+# is the restatement of glibc's expf that the CUDA kernel evaluates (std::exp(float) in dynamic_anchor_routing.cc:399-400)
+# --------------------------------------------------------------------------
+_EXP2F_N = 32
+
+
+def _exp2f_table():
+    """T[i] = bits(2^(i/32)) - (i << 47), computed (not copied) from correctly rounded decimal powers."""
+    import struct
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    t = []
+    for i in range(_EXP2F_N):
+        d = float(Decimal(2) ** (Decimal(i) / Decimal(_EXP2F_N)))
+        t.append((struct.unpack("<Q", struct.pack("<d", d))[0] - (i << 47)) & 0xFFFFFFFFFFFFFFFF)
+    return np.array(t, dtype=np.uint64)
+
+
+def libm_expf(x):
+    """glibc >= 2.27 expf (the ARM optimized-routines algorithm, sysdeps/ieee754/flt-32/e_expf.c), restated: double
+    arithmetic, k = round(32 x / ln 2) by the 0x1.8p52 shift, table of 2^(i/32), degree-3 polynomial, one final rounding."""
+    x = np.asarray(x, dtype=f32)
+    with np.errstate(all="ignore"):
+        xd = x.astype(np.float64)
+        z = float.fromhex("0x1.71547652b82fep+5") * xd
+        kd = z + float.fromhex("0x1.8p52")
+        ki = kd.view(np.uint64)
+        kd = kd - float.fromhex("0x1.8p52")
+        r = z - kd
+        t = _exp2f_table()[(ki % np.uint64(_EXP2F_N)).astype(np.int64)] + (ki << np.uint64(47))
+        s = t.view(np.float64)
+        p = float.fromhex("0x1.c6af84b912394p-20") * r + float.fromhex("0x1.ebfce50fac4f3p-13")
+        y = float.fromhex("0x1.62e42ff0c52d6p-6") * r + 1.0
+        y = (p * (r * r) + y) * s
+        out = y.astype(f32)
+    out = np.where(x > f32(float.fromhex("0x1.62e42ep6")), f32(np.inf), out)
+    out = np.where(x < f32(float.fromhex("-0x1.9fe368p6")), f32(0.), out)
+    return np.where(np.isnan(x), x, out).astype(f32)

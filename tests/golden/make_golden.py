@@ -29,8 +29,44 @@ def pack_encode(res):
                 scores=scores, match=match.astype(np.int32))
 
 
+ROUTING_SMALL = dict(feat_heights=[40, 20, 10, 5], feat_widths=[40, 20, 10, 5], depths=[1, 1, 2, 3], strides=[4, 8, 16, 32])
+ROUTING_DAN640 = dict(feat_heights=[160, 80, 40, 20, 10, 5], feat_widths=[160, 80, 40, 20, 10, 5], depths=[1] * 6,
+                      strides=[4, 8, 16, 32, 64, 128])           # eval_dan.py:386 at 640 x 640
+
+
+def routing_reference(cfg, image_index, mode):
+    """The reference's own DynamicAnchorRouting functor (oracle/_ref/libdar_ref.so), evaluation branch, layer by layer
+    like eval_dan.py:387-393."""
+    a, t, lab, m = synthetic.gen_routing(image_index, cfg["feat_heights"], cfg["feat_widths"], cfg["depths"], cfg["strides"], mode)
+    masks, decs, off = [], [], 0
+    for H, W, D, S in zip(cfg["feat_heights"], cfg["feat_widths"], cfg["depths"], cfg["strides"]):
+        n = H * W * D
+        mo, do = native.dynamic_anchor_routing(a[off:off + n], t[off:off + n], lab[off:off + n], m[off:off + n], H, W, D, S,
+                                               640, 640, False, 0.03, 0.0, impl="reference")
+        masks.append(mo), decs.append(do)
+        off += n
+    return np.concatenate(masks), np.concatenate(decs)
+
+
+def make_routing():
+    assert native.have_reference_dar(), "oracle/_ref/libdar_ref.so missing: run `make -C oracle` where /root/reference exists"
+    out = {}
+    for name, mode in (("plain", "plain"), ("ties", "ties")):
+        mo, do = routing_reference(ROUTING_SMALL, 7, mode)
+        out["small_%s_mask" % name] = mo.astype(np.int8)
+        out["small_%s_decode" % name] = do
+    mo, do = routing_reference(ROUTING_DAN640, 11, "plain")
+    out["dan640_mask_bits"] = np.packbits(mo.astype(np.uint8))
+    out["dan640_decode_xor"] = np.bitwise_xor.reduce(do.view(np.uint32), axis=0)
+    out["dan640_decode_sum"] = do.view(np.uint32).astype(np.uint64).sum(axis=0)
+    np.savez_compressed(os.path.join(OUT, "routing_reference.npz"), **out)
+
+
 def main():
     native.build()
+    if len(sys.argv) > 1 and sys.argv[1] == "routing":
+        make_routing()
+        return
     assert native.have_reference(), "oracle/_ref/libsmm_ref.so missing: run `make -C oracle` where /root/reference exists"
 
     # ---- known-answer vectors for the custom op (cpp/ExtraLib/test_op.py:41,56) -------------
@@ -120,6 +156,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "postprocess_golden.npz"), image_index=np.int64(1), max_faces=np.int64(40),
                         boxes=sb[1], scores=ss[1], topk_index=idx[1][0][:int((ss[1] > 0).sum()) + 2000],
                         keep=idx[1][1])
+    make_routing()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

@@ -641,3 +641,73 @@ def test_hard_negative_mining_after_encode_full_size(cuda, s3fd_anchors_np):
     assert c.shape[0] == int(fm.sum()) and l.shape[0] == int(n_pos.sum())
     assert torch.equal(c, cls.view(-1, 2)[fm.view(-1)]) and torch.equal(t, labels.view(-1)[fm.view(-1)].clamp(0, 2))
     assert torch.equal(l, loc[labels.view(-1) > 0]) and torch.equal(lt, res.targets.view(-1, 4)[labels.view(-1) > 0])
+
+
+# ------------------------------------------------------------------------------------------------
+# DynamicAnchorRouting, evaluation branch
+# ------------------------------------------------------------------------------------------------
+def test_routing_goldens_from_reference_functor(cuda):
+    """CUDA path vs outputs of the reference's own compiled functor (tests/golden/routing_reference.npz)."""
+    from dan_b200.utility import custom_op
+    from test_oracle import ROUTING_DAN640, ROUTING_SMALL
+    g = np.load(os.path.join(GOLD, "routing_reference.npz"))
+    for mode in ("plain", "ties"):
+        c = ROUTING_SMALL
+        a, t, lab, m = synthetic.gen_routing(7, c["feat_heights"], c["feat_widths"], c["depths"], c["strides"], mode)
+        mo, do = custom_op.dynamic_anchor_routing_layers(to_dev(a, cuda), to_dev(t, cuda), to_dev(lab, cuda), to_dev(m, cuda),
+                                                         c["feat_heights"], c["feat_widths"], c["depths"], c["strides"])
+        np.testing.assert_array_equal(_np(mo).astype(np.int8), g["small_%s_mask" % mode])
+        np.testing.assert_array_equal(_np(do).view(np.uint32), g["small_%s_decode" % mode].view(np.uint32))
+    c = ROUTING_DAN640
+    a, t, lab, m = synthetic.gen_routing(11, c["feat_heights"], c["feat_widths"], c["depths"], c["strides"], "plain")
+    mo, do = custom_op.dynamic_anchor_routing_layers(to_dev(a, cuda), to_dev(t, cuda), to_dev(lab, cuda), to_dev(m, cuda),
+                                                     c["feat_heights"], c["feat_widths"], c["depths"], c["strides"])
+    np.testing.assert_array_equal(np.packbits(_np(mo).astype(np.uint8)), g["dan640_mask_bits"])
+    np.testing.assert_array_equal(np.bitwise_xor.reduce(_np(do).view(np.uint32), axis=0), g["dan640_decode_xor"])
+
+
+@pytest.mark.parametrize("mode", ["plain", "ties"])
+def test_routing_batch_vs_oracle(cuda, oracle, mode):
+    """batch of 3 images x 6 DAN layers in ONE call == the op applied per image and layer (eval_dan.py:386-393)."""
+    from dan_b200.utility import custom_op
+    from test_oracle import ROUTING_DAN640, routing_port
+    c = ROUTING_DAN640
+    ins, refs = [], []
+    for i in range(3):
+        x, mo, do = routing_port(c, 40 + i, mode)
+        ins.append(x), refs.append((mo, do))
+    stack = [np.stack([x[k] for x in ins]) for k in range(4)]
+    mo, do = custom_op.dynamic_anchor_routing_layers(*[to_dev(v, cuda) for v in stack], c["feat_heights"], c["feat_widths"],
+                                                     c["depths"], c["strides"])
+    for i in range(3):
+        np.testing.assert_array_equal(_np(mo[i]), refs[i][0])
+        np.testing.assert_array_equal(_np(do[i]).view(np.uint32), refs[i][1].view(np.uint32))
+    assert 0 < int(mo.sum()) < mo.numel()
+
+
+def test_routing_single_layer_op_and_errors(cuda, oracle):
+    from oracle import native
+    from dan_b200 import _lib
+    from dan_b200.utility import custom_op
+    a, t, lab, m = synthetic.gen_routing(3, [12], [17], [3], [16], "ties")
+    rm, rd = native.dynamic_anchor_routing(a, t, lab, m, 12, 17, 3, 16, 192, 272)
+    gm, gd = custom_op.dynamic_anchor_routing(to_dev(a, cuda), to_dev(t, cuda), to_dev(lab, cuda), to_dev(m, cuda), 12, 17, 3, 16,
+                                              192, 272, False, 0.03, 0.0)
+    np.testing.assert_array_equal(_np(gm), rm)
+    np.testing.assert_array_equal(_np(gd).view(np.uint32), rd.view(np.uint32))
+    # extreme offsets: exp overflow / underflow follow libm
+    t2 = t.copy()
+    t2[::5, 2] = 100.
+    t2[1::5, 3] = -120.
+    rm, rd = native.dynamic_anchor_routing(a, t2, lab, m, 12, 17, 3, 16, 192, 272)
+    gm, gd = custom_op.dynamic_anchor_routing(to_dev(a, cuda), to_dev(t2, cuda), to_dev(lab, cuda), to_dev(m, cuda), 12, 17, 3, 16,
+                                              192, 272)
+    np.testing.assert_array_equal(_np(gd).view(np.uint32), rd.view(np.uint32))
+    with pytest.raises(_lib.DanError):                      # dynamic_anchor_routing.cc:527
+        custom_op.dynamic_anchor_routing(to_dev(a, cuda), to_dev(t, cuda), to_dev(lab, cuda), to_dev(m, cuda), 12, 17, 3, 16, 192, 272,
+                                         False, 1.0, 0.0)
+    with pytest.raises(NotImplementedError):
+        custom_op.dynamic_anchor_routing(to_dev(a, cuda), to_dev(t, cuda), to_dev(lab, cuda), to_dev(m, cuda), 12, 17, 3, 16, 192, 272,
+                                         True, 0.03, 0.0)
+    with pytest.raises(ValueError):                         # layer geometry does not match the number of anchors
+        custom_op.dynamic_anchor_routing(to_dev(a, cuda), to_dev(t, cuda), to_dev(lab, cuda), to_dev(m, cuda), 12, 16, 3, 16, 192, 272)
