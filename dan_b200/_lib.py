@@ -108,6 +108,9 @@ _SIGNATURES = {
     "dan_routing_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "dan_dynamic_anchor_routing_eval": (ctypes.c_int, [ctypes.POINTER(RoutingLayers), c_vp, c_vp, c_vp, c_vp, c_i64, c_i32,
                                                        c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_detect_face_workspace_bytes": (c_sz, [c_i64]),
+    "dan_detect_face_select": (ctypes.c_int, [c_vp, c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dan_bbox_vote": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

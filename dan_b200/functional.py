@@ -493,3 +493,46 @@ def dynamic_anchor_routing_eval(layers, anchors, gt_targets, labels, mask_in, wo
             L.dev_ptr(lb, torch.float32, "labels"), L.dev_ptr(m, torch.int32, "mask_in"), n, batch, L.dev_ptr(mask_out),
             L.dev_ptr(decode_out), L.dev_ptr(ws), nbytes, L.stream_ptr()))
     return mask_out, decode_out
+
+
+# ----------------------------------------------------------------------------------
+# evaluation merge: detect_face top-k + bbox_vote
+# ----------------------------------------------------------------------------------
+def detect_face_select(bboxes, scores, shrink, top):
+    """dan_detect_face_select -> (det [top, 5] zero padded, index int32 [top] (-1 padded), count int32 [1])."""
+    L.require_device()
+    dev = _dev(bboxes)
+    b = bboxes.contiguous()
+    s = scores.contiguous()
+    n = s.numel()
+    det = torch.empty((top, 5), dtype=torch.float32, device=dev)
+    idx = torch.empty(top, dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = L.lib().dan_detect_face_workspace_bytes(n)
+    ws = _ws.get(nbytes, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_detect_face_select(L.dev_ptr(b, torch.float32, "bboxes"), L.dev_ptr(s, torch.float32, "scores"), n,
+                                               float(shrink), int(top), L.dev_ptr(det), L.dev_ptr(idx), L.dev_ptr(cnt),
+                                               L.dev_ptr(ws), nbytes, L.stream_ptr()))
+    return det, idx, cnt
+
+
+def bbox_vote_batch(det, counts, nms_threshold, max_per_image, details=False):
+    """dan_bbox_vote: det [B, cap, 5], counts int32 [B] or None -> (out [B, max_per_image, 5], out_count int32 [B]
+    [, order int32 [B, cap], assign int32 [B, cap]])."""
+    L.require_device()
+    dev = _dev(det)
+    d = det.contiguous()
+    if d.dim() != 3 or d.shape[2] != 5:
+        raise ValueError("det must be [B, capacity, 5]")
+    batch, cap = int(d.shape[0]), int(d.shape[1])
+    out = torch.empty((batch, max_per_image, 5), dtype=torch.float32, device=dev)
+    cnt = torch.empty(batch, dtype=torch.int32, device=dev)
+    order = torch.full((batch, cap), -1, dtype=torch.int32, device=dev) if details else None
+    assign = torch.full((batch, cap), -1, dtype=torch.int32, device=dev) if details else None
+    c = counts.contiguous() if counts is not None else None
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_bbox_vote(L.dev_ptr(d, torch.float32, "det"), L.dev_ptr(c, torch.int32, "counts"), batch, cap,
+                                      float(nms_threshold), int(max_per_image), L.dev_ptr(out), L.dev_ptr(cnt),
+                                      L.dev_ptr(order), L.dev_ptr(assign), L.stream_ptr()))
+    return (out, cnt, order, assign) if details else (out, cnt)

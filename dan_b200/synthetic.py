@@ -213,3 +213,32 @@ def gen_routing(image_index, feat_heights, feat_widths, depths, strides, mode="p
         m = (rng.uniform(0, 1, n) > 0.4).astype(np.int32)
         out.append((a.astype(f32), t.astype(f32), lab.astype(f32), m))
     return tuple(np.concatenate([o[k] for o in out], 0) for k in range(4))
+
+
+def gen_vote_dets(image_index, n, faces=40, background=0.5):
+    """Input of bbox_vote for one image: the stack of multi-scale / flipped detections, rows (xmin, ymin, xmax, ymax,
+    score).  (1 - background) of the rows are jittered copies of `faces` true boxes (they vote for each other), the rest
+    are scattered low-score boxes (mostly singletons, which bbox_vote drops).  Scores are continuous and distinct (the
+    reference's argsort leaves ties unspecified); every 9th row is degenerate (zero width): it never merges."""
+    rng = np.random.default_rng(BASE_SEED + 500000 + image_index)
+    k = max(int(faces), 1)
+    side = np.exp(rng.uniform(np.log(10.), np.log(300.), k))
+    cx, cy = rng.uniform(0, 640, k), rng.uniform(0, 640, k)
+    nf = int(round(n * (1. - background)))
+    idx = rng.integers(0, k, nf)
+    jit = side[idx] * 0.08
+    fx, fy = cx[idx] + rng.normal(0, 1, nf) * jit, cy[idx] + rng.normal(0, 1, nf) * jit
+    fw, fh = side[idx] * np.exp(rng.normal(0, 0.08, nf)), side[idx] * 1.2 * np.exp(rng.normal(0, 0.08, nf))
+    fs = rng.uniform(0.3, 1.0, nf)
+    nb = n - nf
+    bs_ = np.exp(rng.uniform(np.log(8.), np.log(200.), nb))
+    bx, by = rng.uniform(0, 640, nb), rng.uniform(0, 640, nb)
+    bsc = rng.uniform(0.0, 0.3, nb)
+    x = np.concatenate([fx, bx]); y = np.concatenate([fy, by])
+    w = np.concatenate([fw, bs_]); h = np.concatenate([fh, bs_ * 1.2])
+    sc = np.concatenate([fs, bsc])
+    det = np.stack([x - w / 2, y - h / 2, x + w / 2, y + h / 2, sc], -1).astype(f32)
+    det = det[rng.permutation(n)]
+    det[::9, 2] = det[::9, 0] - 1                 # zero area under the +1 convention
+    _, first = np.unique(det[:, 4], return_index=True)
+    return det[np.sort(first)]                    # distinct scores

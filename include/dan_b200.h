@@ -312,6 +312,28 @@ int dan_dynamic_anchor_routing_eval(const dan_routing_layers* h_layers, const fl
                                     int32_t* mask_out, float* decode_out, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * (f2) the evaluation merge of the reference's scripts.
+ * dan_detect_face_select: detect_face after net.run (eval_sfd.py:101-112 =
+ *   eval_dan.py:101-118): bboxes [n,4] (ymin,xmin,ymax,xmax) / shrink -> rows
+ *   (xmin, ymin, xmax, ymax, score), the top min(n-1, top) by descending score
+ *   (top = int(1.5 * max_per_image) = 1125); equal scores: higher index first.
+ *   out_det [top,5] zero padded, out_index [top] (-1 padded, may be NULL), out_count [1].
+ * dan_bbox_vote: bbox_vote (eval_sfd.py:170-210 = eval_dan.py:201-241), batched:
+ *   det [B, capacity, 5] rows (xmin, ymin, xmax, ymax, score), counts [B] valid rows
+ *   per image (NULL = capacity); out_det [B, max_per_image, 5] zero padded,
+ *   out_count [B]; optional out_order / out_assign [B, capacity]: sorted position ->
+ *   input row / head position (-2 = head deleted alone), for inspection.
+ *   capacity <= 8192 (the stack of multi-scale detections is <= 6 x 1125).
+ * ------------------------------------------------------------------------- */
+size_t dan_detect_face_workspace_bytes(int64_t n);
+int dan_detect_face_select(const float* bboxes, const float* scores, int64_t n, float shrink,
+                           int32_t top, float* out_det, int32_t* out_index, int32_t* out_count,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int dan_bbox_vote(const float* det, const int32_t* counts, int32_t batch, int32_t capacity,
+                  float nms_threshold, int32_t max_per_image, float* out_det, int32_t* out_count,
+                  int32_t* out_order, int32_t* out_assign, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

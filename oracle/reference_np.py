@@ -593,3 +593,98 @@ def libm_expf(x):
     out = np.where(x > f32(float.fromhex("0x1.62e42ep6")), f32(np.inf), out)
     out = np.where(x < f32(float.fromhex("-0x1.9fe368p6")), f32(0.), out)
     return np.where(np.isnan(x), x, out).astype(f32)
+
+
+# --------------------------------------------------------------------------
+# the evaluation merge the scripts actually use: detect_face's top-k (eval_sfd.py:95-114) and
+# bbox_vote (eval_sfd.py:170-210; identical in eval_dan.py:201-241).  Boxes here are (xmin, ymin, xmax, ymax, score),
+# float32, +1 pixel convention.
+# --------------------------------------------------------------------------
+def detect_face_select(bboxes, scores, shrink, max_per_image=750):
+    """eval_sfd.py:101-112 (everything after net.run): boxes (ymin, xmin, ymax, xmax) / shrink -> columns
+    (xmin, ymin, xmax, ymax, score); keep the top min(N - 1, int(1.5 * max_per_image)) by descending score.
+    Tie policy: ``argsort()[::-1]`` with numpy's default (unstable, platform dependent) sort leaves equal scores
+    unspecified; this restatement uses the stable sort, i.e. among equal scores the HIGHER index comes first."""
+    bboxes = np.asarray(bboxes, dtype=f32).reshape(-1, 4)
+    scores = np.asarray(scores, dtype=f32).reshape(-1)
+    sh = f32(shrink)
+    det = np.column_stack((bboxes[:, 1] / sh, bboxes[:, 0] / sh, bboxes[:, 3] / sh, bboxes[:, 2] / sh, scores)).astype(f32)
+    top = min(det.shape[0] - 1, int(max_per_image * 1.5))
+    keep = np.argsort(det[:, 4], kind="stable")[::-1].astype(np.int64)[:top]     # note: [:-1] when N == 0
+    return det[keep, :], keep
+
+
+def numpy_pairwise_sum(a):
+    """numpy's float32 add-reduce over one axis (umath pairwise_sum): < 8 sequential; <= 128 eight interleaved
+    accumulators, tree-combined, tail sequential; beyond that split at n/2 rounded down to a multiple of 8."""
+    n = len(a)
+    if n < 8:
+        res = f32(0.)
+        for v in a:
+            res = f32(res + v)
+        return res
+    if n <= 128:
+        r = [f32(a[i]) for i in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for k in range(8):
+                r[k] = f32(r[k] + a[i + k])
+            i += 8
+        res = f32(f32(f32(r[0] + r[1]) + f32(r[2] + r[3])) + f32(f32(r[4] + r[5]) + f32(r[6] + r[7])))
+        while i < n:
+            res = f32(res + a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return f32(numpy_pairwise_sum(a[:n2]) + numpy_pairwise_sum(a[n2:]))
+
+
+def bbox_vote(det, nms_threshold=0.3, max_per_image=750, return_details=False):
+    """eval_sfd.py:170-210, restated without the shrinking array: sort by descending score; a detection that no
+    earlier HEAD overlaps with IoU >= thr becomes a head, every other one joins the FIRST head (in score order) that
+    overlaps it; clusters of fewer than two members are dropped (:191-197); a cluster becomes one box = score-weighted
+    mean of its members (float32, the box sums accumulate member by member in score order, the score sum is numpy's
+    pairwise sum) with the maximum score (:198-203); the first max_per_image clusters in head order are returned."""
+    det = np.asarray(det, dtype=f32).reshape(-1, 5)
+    order = np.argsort(det[:, 4], kind="stable")[::-1]
+    d = det[order]
+    n = d.shape[0]
+    area = (d[:, 2] - d[:, 0] + f32(1)) * (d[:, 3] - d[:, 1] + f32(1))
+    assign = np.full(n, -1, dtype=np.int64)          # head position (in sorted order) of each detection, -2 = dropped head
+    heads = []
+    thr = f32(nms_threshold)
+    for i in range(n):
+        if assign[i] != -1:
+            continue
+        rest = np.nonzero(assign == -1)[0]
+        rest = rest[rest >= i]
+        xx1, yy1 = np.maximum(d[i, 0], d[rest, 0]), np.maximum(d[i, 1], d[rest, 1])
+        xx2, yy2 = np.minimum(d[i, 2], d[rest, 2]), np.minimum(d[i, 3], d[rest, 3])
+        w, h = np.maximum(f32(0.), xx2 - xx1 + f32(1)), np.maximum(f32(0.), yy2 - yy1 + f32(1))
+        inter = w * h
+        with np.errstate(all="ignore"):
+            o = inter / (area[i] + area[rest] - inter)
+        merged = rest[o >= thr]
+        assign[merged] = i
+        if assign[i] == -1:
+            assign[i] = -2                            # the head does not even match itself (NaN IoU): deleted alone (:189-190)
+        heads.append(i)
+    out = []
+    for hpos in heads:
+        members = np.nonzero(assign == hpos)[0]
+        if members.shape[0] <= 1:
+            continue
+        acc = d[members]
+        weighted = acc[:, 0:4] * acc[:, 4:5]
+        box_sum = np.zeros(4, dtype=f32)
+        for r in weighted:                            # np.sum(axis=0) adds the rows one after the other
+            box_sum = (box_sum + r).astype(f32)
+        with np.errstate(all="ignore"):
+            box = box_sum / numpy_pairwise_sum(acc[:, 4])
+        out.append(np.concatenate([box, [np.max(acc[:, 4])]]).astype(f32))
+    res = np.stack(out).astype(f32) if out else np.zeros((0, 5), dtype=f32)
+    res = res[:min(max_per_image, res.shape[0])]
+    if return_details:
+        return res, {"order": order, "assign": assign}
+    return res

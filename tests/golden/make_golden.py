@@ -62,10 +62,44 @@ def make_routing():
     np.savez_compressed(os.path.join(OUT, "routing_reference.npz"), **out)
 
 
+def reference_bbox_vote(nms_threshold=0.3, max_per_image=750):
+    """The reference's OWN bbox_vote (eval_sfd.py:170-210): the function's source is parsed out of the script with `ast`
+    and executed here (the script itself imports TensorFlow and cannot be imported); FLAGS as in eval_sfd.py:62-66."""
+    import ast
+    import warnings
+    warnings.simplefilter("ignore")                   # np.row_stack is deprecated in numpy 2
+    tree = ast.parse(open("/root/reference/eval_sfd.py").read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "bbox_vote"][0]
+
+    class FLAGS(object):
+        pass
+    FLAGS.nms_threshold, FLAGS.max_per_image = nms_threshold, max_per_image
+    ns = {"np": np, "FLAGS": FLAGS}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "eval_sfd.py", "exec"), ns)
+    return ns["bbox_vote"]
+
+
+VOTE_CASES = [(1, 300, 12, 0.3), (2, 2500, 60, 0.5), (3, 6750, 150, 0.6), (4, 1, 1, 0.0), (5, 40, 1, 0.0), (6, 8000, 1500, 0.05)]
+
+
+def make_vote():
+    vote = reference_bbox_vote()
+    out = {}
+    for image_index, n, faces, bg in VOTE_CASES:
+        det = synthetic.gen_vote_dets(image_index, n, faces, bg)
+        out["vote_%d" % image_index] = vote(det.copy())
+    # other FLAGS: the cut after max_per_image groups, a stricter threshold
+    out["vote_3_top100_thr05"] = reference_bbox_vote(0.5, 100)(synthetic.gen_vote_dets(3, 6750, 150, 0.6))
+    np.savez_compressed(os.path.join(OUT, "vote_reference.npz"), **out)
+
+
 def main():
     native.build()
     if len(sys.argv) > 1 and sys.argv[1] == "routing":
         make_routing()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "vote":
+        make_vote()
         return
     assert native.have_reference(), "oracle/_ref/libsmm_ref.so missing: run `make -C oracle` where /root/reference exists"
 
@@ -157,6 +191,7 @@ def main():
                         boxes=sb[1], scores=ss[1], topk_index=idx[1][0][:int((ss[1] > 0).sum()) + 2000],
                         keep=idx[1][1])
     make_routing()
+    make_vote()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

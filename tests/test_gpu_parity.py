@@ -711,3 +711,58 @@ def test_routing_single_layer_op_and_errors(cuda, oracle):
                                          True, 0.03, 0.0)
     with pytest.raises(ValueError):                         # layer geometry does not match the number of anchors
         custom_op.dynamic_anchor_routing(to_dev(a, cuda), to_dev(t, cuda), to_dev(lab, cuda), to_dev(m, cuda), 12, 16, 3, 16, 192, 272)
+
+
+# ------------------------------------------------------------------------------------------------
+# detect_face top-k + bbox_vote
+# ------------------------------------------------------------------------------------------------
+def test_bbox_vote_goldens_from_reference_function(cuda):
+    """CUDA bbox_vote vs outputs of the reference's own function (tests/golden/vote_reference.npz)."""
+    from dan_b200.utility import eval_merge
+    from test_oracle import VOTE_CASES
+    g = np.load(os.path.join(GOLD, "vote_reference.npz"))
+    for image_index, n, faces, bg in VOTE_CASES:
+        det = synthetic.gen_vote_dets(image_index, n, faces, bg)
+        got = _np(eval_merge.bbox_vote(to_dev(det, cuda)))
+        ref = g["vote_%d" % image_index]
+        assert got.shape == ref.shape, (image_index, got.shape, ref.shape)
+        np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+    got = _np(eval_merge.bbox_vote(to_dev(synthetic.gen_vote_dets(3, 6750, 150, 0.6), cuda), nms_threshold=0.5, max_per_image=100))
+    np.testing.assert_array_equal(got.view(np.uint32), g["vote_3_top100_thr05"].view(np.uint32))
+
+
+def test_bbox_vote_batch_vs_oracle(cuda, oracle):
+    """ragged batch in one launch; also checks the sort order and the head assignment themselves."""
+    from dan_b200 import functional as F
+    sizes = [0, 1, 2, 17, 700, 3000, 8192]
+    cap = max(sizes)
+    dets = [synthetic.gen_vote_dets(60 + i, n, max(n // 25, 1), 0.5)[:n] if n else np.zeros((0, 5), np.float32)
+            for i, n in enumerate(sizes)]
+    batch = np.zeros((len(sizes), cap, 5), np.float32)
+    batch[:] = np.nan                                         # rows beyond counts[b] must never be read into a result
+    for i, d in enumerate(dets):
+        batch[i, :d.shape[0]] = d
+    counts = np.array([d.shape[0] for d in dets], np.int32)
+    out, cnt, order, assign = F.bbox_vote_batch(to_dev(batch, cuda), to_dev(counts, cuda), 0.3, 750, details=True)
+    for i, d in enumerate(dets):
+        ref, aux = oracle.bbox_vote(d, return_details=True)
+        k = int(cnt[i])
+        assert k == ref.shape[0], (i, k, ref.shape)
+        np.testing.assert_array_equal(_np(out[i, :k]).view(np.uint32), ref.view(np.uint32))
+        assert not _np(out[i, k:]).any()
+        n = d.shape[0]
+        np.testing.assert_array_equal(_np(order[i, :n]), aux["order"])
+        np.testing.assert_array_equal(_np(assign[i, :n]), aux["assign"])
+
+
+def test_detect_face_select_vs_oracle(cuda, oracle):
+    from dan_b200.utility import eval_merge
+    rng = np.random.default_rng(12)
+    for n, shrink in ((3000, 0.5), (20000, 1.75), (5, 1.0), (1, 2.0), (900, 3.0)):
+        b = rng.uniform(0, 640, (n, 4)).astype(np.float32)
+        s = rng.uniform(0, 1, n).astype(np.float32)
+        s[::10] = s[min(5, n - 1)]                                        # equal scores: higher index first
+        ref, _ = oracle.detect_face_select(b, s, shrink)
+        got = _np(eval_merge.detect_face_select(to_dev(b, cuda), to_dev(s, cuda), shrink))
+        assert got.shape == ref.shape
+        np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
