@@ -1,0 +1,142 @@
+// the input hand-off, i.e. the deterministic tail of the reference's training preprocessing that sits
+// between the sampled image patch and encode_anchors, for a whole batch:
+//   random_flip_left_right    sfd_preprocessing.py:482-493  boxes (ymin, W-1-xmax, ymax, W-1-xmin) when the image was mirrored
+//                                                            (the coin flip itself is an input here)
+//   rescale to the net input  sfd_preprocessing.py:529-533  ymin * target_h / patch_h, ... (two separately rounded fp32 ops)
+//   small-face filter         sfd_preprocessing.py:544-550  keep (ymax - ymin) > 6 and (xmax - xmin) > 3, order preserved
+//   keep_input                dataset_common.py:178,186     an image whose box list is empty afterwards is not batched
+// Output = the CSR batch dan_encode_batch consumes (gt_boxes of the kept images back to back, gt_offsets) plus the
+// indices of the kept images.  One 1024-thread CTA: a batch holds a few thousand boxes at most.
+#include "common.cuh"
+
+namespace dan {
+
+namespace {
+
+struct HandoffArgs {
+  const float4* boxes;        // [total] (ymin, xmin, ymax, xmax), pixels of the sampled patch
+  const int32_t* offsets;     // [B + 1]
+  const float* patch_hw;      // [B, 2] height, width of the patch before resizing
+  const uint8_t* mirror;      // [B] or NULL
+  int batch;
+  float target_h, target_w, min_h, min_w;
+  float4* out_boxes;          // [total]
+  int32_t* out_offsets;       // [B + 1]
+  int32_t* out_image;         // [B]
+  int32_t* out_counts;        // [2] kept images, kept boxes
+};
+
+DAN_D float4 handoff_box(const HandoffArgs& A, int b, int i, bool& keep) {
+  float4 g = A.boxes[i];
+  const float ph = A.patch_hw[2 * b], pw = A.patch_hw[2 * b + 1];
+  if (A.mirror != nullptr && A.mirror[b]) {
+    const float x0 = fsub(fsub(pw, 1.f), g.w), x1 = fsub(fsub(pw, 1.f), g.y);     // float_width - 1. - xmax / xmin
+    g.y = x0;
+    g.w = x1;
+  }
+  g.x = fdiv(fmul(g.x, A.target_h), ph);
+  g.z = fdiv(fmul(g.z, A.target_h), ph);
+  g.y = fdiv(fmul(g.y, A.target_w), pw);
+  g.w = fdiv(fmul(g.w, A.target_w), pw);
+  keep = (fsub(g.z, g.x) > A.min_h) && (fsub(g.w, g.y) > A.min_w);
+  return g;
+}
+
+__global__ void __launch_bounds__(1024, 1) gt_handoff_kernel(const HandoffArgs A) {
+  __shared__ int s_warp[32][2];
+  __shared__ int s_carry[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 2) s_carry[tid] = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < A.batch; b0 += 1024) {
+    const int b = b0 + tid;
+    int kept = 0, lo = 0, hi = 0;
+    if (b < A.batch) {
+      lo = A.offsets[b];
+      hi = A.offsets[b + 1];
+      for (int i = lo; i < hi; ++i) {
+        bool keep;
+        handoff_box(A, b, i, keep);
+        kept += keep ? 1 : 0;
+      }
+    }
+    // exclusive scan over the images of (image kept, boxes kept)
+    int v[2] = {kept > 0 ? 1 : 0, kept}, incl[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      incl[q] = v[q];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl[q], d);
+        if (lane >= d) incl[q] += o;
+      }
+      if (lane == 31) s_warp[warp][q] = incl[q];
+    }
+    __syncthreads();
+    int before[2] = {s_carry[0], s_carry[1]}, chunk[2] = {0, 0};
+    for (int w = 0; w < 32; ++w) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (w < warp) before[q] += s_warp[w][q];
+        chunk[q] += s_warp[w][q];
+      }
+    }
+    if (b < A.batch && kept > 0) {
+      const int slot = before[0] + incl[0] - 1;            // position of this image in the batch
+      int at = before[1] + incl[1] - kept;                 // its first box
+      A.out_image[slot] = b;
+      A.out_offsets[slot] = at;
+      for (int i = lo; i < hi; ++i) {
+        bool keep;
+        const float4 g = handoff_box(A, b, i, keep);
+        if (keep) A.out_boxes[at++] = g;
+      }
+    }
+    __syncthreads();
+    if (tid < 2) s_carry[tid] += chunk[tid];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    A.out_offsets[s_carry[0]] = s_carry[1];
+    A.out_counts[0] = s_carry[0];
+    A.out_counts[1] = s_carry[1];
+  }
+}
+
+}  // namespace
+
+}  // namespace dan
+
+using namespace dan;
+
+extern "C" {
+
+int dan_gt_handoff(const float* gt_boxes, const int32_t* gt_offsets, const float* patch_hw, const uint8_t* mirror,
+                   int32_t batch, int32_t total_gt, float target_height, float target_width, float min_height,
+                   float min_width, float* out_gt_boxes, int32_t* out_gt_offsets, int32_t* out_image_index,
+                   int32_t* out_counts, void* stream) {
+  DAN_REQUIRE(batch >= 0 && total_gt >= 0, DAN_ERR_INVALID_ARGUMENT, "negative size");
+  DAN_REQUIRE(out_gt_offsets && out_counts, DAN_ERR_INVALID_ARGUMENT, "NULL output");
+  DAN_REQUIRE(batch == 0 || (gt_offsets && patch_hw && out_image_index), DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
+  DAN_REQUIRE(total_gt == 0 || (gt_boxes && out_gt_boxes && aligned16(gt_boxes) && aligned16(out_gt_boxes)), DAN_ERR_INVALID_ARGUMENT,
+              "gt boxes NULL or not 16-byte aligned");
+  HandoffArgs A = {};
+  A.boxes = reinterpret_cast<const float4*>(gt_boxes);
+  A.offsets = gt_offsets;
+  A.patch_hw = patch_hw;
+  A.mirror = mirror;
+  A.batch = batch;
+  A.target_h = target_height;
+  A.target_w = target_width;
+  A.min_h = min_height;
+  A.min_w = min_width;
+  A.out_boxes = reinterpret_cast<float4*>(out_gt_boxes);
+  A.out_offsets = out_gt_offsets;
+  A.out_image = out_image_index;
+  A.out_counts = out_counts;
+  gt_handoff_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A);
+  DAN_LAUNCH_CHECK("gt_handoff_kernel");
+  return DAN_OK;
+}
+
+}  // extern "C"

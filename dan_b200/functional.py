@@ -536,3 +536,36 @@ def bbox_vote_batch(det, counts, nms_threshold, max_per_image, details=False):
                                       float(nms_threshold), int(max_per_image), L.dev_ptr(out), L.dev_ptr(cnt),
                                       L.dev_ptr(order), L.dev_ptr(assign), L.stream_ptr()))
     return (out, cnt, order, assign) if details else (out, cnt)
+
+
+# ----------------------------------------------------------------------------------
+# input hand-off
+# ----------------------------------------------------------------------------------
+def gt_handoff(gt_boxes, gt_offsets, patch_hw, out_shape, mirror=None, min_height=6., min_width=3.):
+    """dan_gt_handoff -> (gt_boxes [total,4] capacity, gt_offsets int32 [B+1] capacity, image_index int32 [B],
+    counts int32 [2] = (kept images, kept boxes)); nothing synchronises."""
+    L.require_device()
+    dev = _dev(gt_offsets)
+    g = gt_boxes.contiguous()
+    o = gt_offsets.contiguous()
+    hw = patch_hw.contiguous()
+    batch = o.numel() - 1
+    total = g.numel() // 4
+    m = None
+    if mirror is not None:
+        m = mirror.to(torch.uint8).contiguous()
+        if m.numel() != batch:
+            raise ValueError("mirror must have one entry per image")
+    if hw.numel() != 2 * batch:
+        raise ValueError("patch_hw must be [B, 2]")
+    ob = torch.empty((total, 4), dtype=torch.float32, device=dev)
+    oo = torch.zeros(batch + 1, dtype=torch.int32, device=dev)
+    oi = torch.full((batch,), -1, dtype=torch.int32, device=dev)
+    oc = torch.empty(2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dan_gt_handoff(L.dev_ptr(g, torch.float32, "gt_boxes") if total else ctypes.c_void_p(0),
+                                       L.dev_ptr(o, torch.int32, "gt_offsets"), L.dev_ptr(hw, torch.float32, "patch_hw"),
+                                       L.dev_ptr(m, torch.uint8, "mirror"), batch, total, float(out_shape[0]), float(out_shape[1]),
+                                       float(min_height), float(min_width), L.dev_ptr(ob) if total else ctypes.c_void_p(0),
+                                       L.dev_ptr(oo), L.dev_ptr(oi), L.dev_ptr(oc), L.stream_ptr()))
+    return ob, oo, oi, oc

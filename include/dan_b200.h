@@ -334,6 +334,24 @@ int dan_bbox_vote(const float* det, const int32_t* counts, int32_t batch, int32_
                   float nms_threshold, int32_t max_per_image, float* out_det, int32_t* out_count,
                   int32_t* out_order, int32_t* out_assign, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * (f4) input hand-off: the deterministic tail of the training
+ * preprocessing between the sampled patch and encode_anchors, for a batch:
+ * mirror (sfd_preprocessing.py:482-493, the coin flip is an input), rescale to the
+ * net input (:529-533), small-face filter `h > 6 & w > 3` (:544-550), and the
+ * keep_input rule that drops images left without boxes (dataset_common.py:178,186).
+ *   gt_boxes [total_gt,4] (ymin,xmin,ymax,xmax) in patch pixels, gt_offsets [B+1],
+ *   patch_hw [B,2] (height, width of the patch), mirror [B] uint8 or NULL.
+ * Outputs: the CSR batch dan_encode_batch consumes: out_gt_boxes [total_gt,4]
+ * capacity, out_gt_offsets [B+1] capacity, out_image_index [B] (source image of
+ * each kept image), out_counts[2] = {kept images, kept boxes}.
+ * ------------------------------------------------------------------------- */
+int dan_gt_handoff(const float* gt_boxes, const int32_t* gt_offsets, const float* patch_hw,
+                   const uint8_t* mirror, int32_t batch, int32_t total_gt, float target_height,
+                   float target_width, float min_height, float min_width, float* out_gt_boxes,
+                   int32_t* out_gt_offsets, int32_t* out_image_index, int32_t* out_counts,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

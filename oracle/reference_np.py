@@ -688,3 +688,30 @@ def bbox_vote(det, nms_threshold=0.3, max_per_image=750, return_details=False):
     if return_details:
         return res, {"order": order, "assign": assign}
     return res
+
+
+# --------------------------------------------------------------------------
+# input hand-off (TF graph code, restated op by op; the random coin of the flip is an input)
+# --------------------------------------------------------------------------
+def prepare_gt_batch(gt_list, patch_hw, out_shape, mirror=None, min_height=6., min_width=3.):
+    """gt_list: per-image [M,4] (ymin, xmin, ymax, xmax) in patch pixels.  sfd_preprocessing.py:482-493 (mirror),
+    :529-533 (rescale), :544-550 (small-face filter); dataset_common.py:178,186 (keep_input: images without boxes
+    are dropped).  -> (gt_concat [sum,4], gt_offsets int32 [kept+1], image_index int32 [kept])."""
+    boxes, offs, idx = [], [0], []
+    for b, g in enumerate(gt_list):
+        g = np.asarray(g, dtype=f32).reshape(-1, 4)
+        ph, pw = f32(patch_hw[b][0]), f32(patch_hw[b][1])
+        ymin, xmin, ymax, xmax = g[:, 0], g[:, 1], g[:, 2], g[:, 3]
+        if mirror is not None and mirror[b]:
+            xmin, xmax = pw - f32(1.) - xmax, pw - f32(1.) - xmin
+        th, tw = f32(out_shape[0]), f32(out_shape[1])
+        ymin, ymax = ymin * th / ph, ymax * th / ph
+        xmin, xmax = xmin * tw / pw, xmax * tw / pw
+        keep = ((ymax - ymin) > f32(min_height)) & ((xmax - xmin) > f32(min_width))
+        out = np.stack([ymin, xmin, ymax, xmax], -1).astype(f32)[keep]
+        if out.shape[0] > 0:
+            boxes.append(out)
+            offs.append(offs[-1] + out.shape[0])
+            idx.append(b)
+    cat = np.concatenate(boxes, 0) if boxes else np.zeros((0, 4), dtype=f32)
+    return cat, np.asarray(offs, dtype=i32), np.asarray(idx, dtype=i32)

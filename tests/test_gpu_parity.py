@@ -766,3 +766,40 @@ def test_detect_face_select_vs_oracle(cuda, oracle):
         got = _np(eval_merge.detect_face_select(to_dev(b, cuda), to_dev(s, cuda), shrink))
         assert got.shape == ref.shape
         np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------
+# input hand-off
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch,use_mirror", [(23, True), (1, False), (1500, True), (6, False)])
+def test_input_handoff_vs_oracle(cuda, oracle, batch, use_mirror):
+    from dan_b200.utility import input_handoff
+    from test_oracle import handoff_case
+    gts, hw, mirror = handoff_case(batch, batch)
+    if batch == 6:
+        gts = [g[:0] for g in gts]                                # nothing at all survives
+    cat, offs = synthetic.to_csr(gts)
+    ref = oracle.prepare_gt_batch(gts, hw, (640, 640), mirror if use_mirror else None)
+    got = input_handoff.prepare_gt_batch(to_dev(cat.reshape(-1, 4), cuda), to_dev(offs, cuda), to_dev(hw, cuda), (640, 640),
+                                         to_dev(mirror, cuda) if use_mirror else None)
+    np.testing.assert_array_equal(_np(got[0]).view(np.uint32), ref[0].view(np.uint32))
+    np.testing.assert_array_equal(_np(got[1]), ref[1])
+    np.testing.assert_array_equal(_np(got[2]), ref[2])
+
+
+def test_input_handoff_feeds_encode(cuda, oracle, s3fd_anchors_np):
+    """hand-off -> encode_all_anchors on the device == oracle hand-off -> oracle encode, image by image."""
+    from dan_b200.utility import anchor_manipulator as am, input_handoff
+    from test_oracle import handoff_case
+    gts, hw, mirror = handoff_case(77, 12)
+    cat, offs = synthetic.to_csr(gts)
+    g_boxes, g_offs, g_idx = input_handoff.prepare_gt_batch(to_dev(cat.reshape(-1, 4), cuda), to_dev(offs, cuda), to_dev(hw, cuda),
+                                                            (640, 640), to_dev(mirror, cuda))
+    r_boxes, r_offs, r_idx = oracle.prepare_gt_batch(gts, hw, (640, 640), mirror)
+    anchors = [to_dev(v, cuda) for v in s3fd_anchors_np]
+    res = am.AnchorEncoder(0.4, 0.4, PS).encode_all_anchors(g_boxes, g_offs, *anchors, match_mining=True)
+    e_ref = oracle.AnchorEncoder(0.4, 0.4, PS)
+    assert res.labels.shape[0] == len(r_idx)
+    for k in range(len(r_idx)):
+        ref = e_ref.encode_anchors(r_boxes[r_offs[k]:r_offs[k + 1]], *s3fd_anchors_np, match_mining=True)
+        _check_encode(ref, [res.targets[k], res.labels[k], res.scores[k], res.matched_gt[k]], "kept image %d" % k)
