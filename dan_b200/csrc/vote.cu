@@ -12,8 +12,8 @@
 // memory:
 //   1. 64-bit keys (score bits << 32 | index), bitonic sort (sort.cuh); equal scores: higher index first, i.e.
 //      numpy's argsort(kind="stable")[::-1] (the reference's default quicksort leaves ties unspecified)
-//   2. heads, one after the other: every warp finds the next unassigned position by itself (ballot scan, no
-//      broadcast), all 1024 threads test the remaining detections against the head -> two barriers per head
+//   2. heads, 32 candidates per round: the round's candidates are resolved against each other with 32x32 pair tests
+//      and bit masks, then every thread tests its own (register resident) detections against the round's heads
 //   3. the groups with >= 2 members are numbered in head order (block scan); thread q walks the members of group q in
 //      score order: box sums accumulate sequentially like np.sum(axis=0), the score sum reproduces numpy's pairwise
 //      summation (8 interleaved accumulators up to 128 elements, recursive halving beyond), all in fp32 without FMA.
@@ -73,31 +73,55 @@ struct MemberIter {
   }
 };
 
-// numpy's pairwise_sum (float32 add-reduce) over the next m member scores
-__device__ float numpy_pairwise(MemberIter& it, int m) {
+// numpy's pairwise_sum (float32 add-reduce) over the next m member scores.  The leaf (<= 128 elements) is inlined so
+// that the iterator stays in registers; the recursive halving above 128 elements runs on a small explicit stack.
+DAN_D float numpy_pairwise_leaf(MemberIter& it, int m) {
   if (m < 8) {
     float res = 0.f;
     for (int i = 0; i < m; ++i) res = fadd(res, it.next());
     return res;
   }
-  if (m <= 128) {
-    float r[8];
+  float r[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = it.next();
-    int i = 8;
-    for (; i < m - (m % 8); i += 8) {
+  for (int k = 0; k < 8; ++k) r[k] = it.next();
+  int i = 8;
+  for (; i < m - (m % 8); i += 8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = fadd(r[k], it.next());
-    }
-    float res = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
-    for (; i < m; ++i) res = fadd(res, it.next());
-    return res;
+    for (int k = 0; k < 8; ++k) r[k] = fadd(r[k], it.next());
   }
-  int m2 = m / 2;
-  m2 -= m2 % 8;
-  const float a = numpy_pairwise(it, m2);
-  const float b = numpy_pairwise(it, m - m2);
-  return fadd(a, b);
+  float res = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
+  for (; i < m; ++i) res = fadd(res, it.next());
+  return res;
+}
+
+DAN_D float numpy_pairwise(MemberIter& it, int m) {
+  int fm[8], stage[8];                  // depth <= log2(8192 / 128) + 1
+  float left[8];
+  int sp = 0;
+  fm[0] = m; stage[0] = 0; left[0] = 0.f;
+  float ret = 0.f;
+  while (sp >= 0) {
+    const int cm = fm[sp];
+    if (cm <= 128) {
+      ret = numpy_pairwise_leaf(it, cm);
+      --sp;
+      continue;
+    }
+    int m2 = cm / 2;
+    m2 -= m2 % 8;
+    if (stage[sp] == 0) {
+      stage[sp] = 1;
+      ++sp; fm[sp] = m2; stage[sp] = 0;
+    } else if (stage[sp] == 1) {
+      left[sp] = ret;
+      stage[sp] = 2;
+      ++sp; fm[sp] = cm - m2; stage[sp] = 0;
+    } else {
+      ret = fadd(left[sp], ret);
+      --sp;
+    }
+  }
+  return ret;
 }
 
 static size_t vote_smem_bytes(int cap) {
@@ -133,64 +157,132 @@ __global__ void __launch_bounds__(kSortThreads, 1) bbox_vote_kernel(const VoteAr
     keys[i] = ((unsigned long long)score_to_key(det[i * 5 + 4]) << 32) | (unsigned long long)(uint32_t)i;
   __syncthreads();
   sort_smem_keys(keys, n);
-  // gather through registers: the boxes overwrite the key storage
+  // gather through registers (the boxes overwrite the key storage); thread t keeps the boxes of the score ranks
+  // t, t + 1024, ... in registers for the sweeps below
   constexpr int kPer = kSortCap / kSortThreads;
   float4 rb[kPer];
   float rs[kPer];
-  int ri[kPer];
+  int rr[kPer];                                            // score rank of the box in rb[e], -1 = none
 #pragma unroll
   for (int e = 0; e < kPer; ++e) {
     const int r = tid + e * kSortThreads;
-    ri[e] = -1;
+    rr[e] = -1;
     if (r < n) {
       const int i = (int)(uint32_t)(keys[r] & 0xFFFFFFFFull);
-      ri[e] = i;
+      rr[e] = r;
       rb[e] = make_float4(det[i * 5], det[i * 5 + 1], det[i * 5 + 2], det[i * 5 + 3]);
       rs[e] = det[i * 5 + 4];
+      if (A.out_order) A.out_order[(int64_t)b * A.cap + r] = i;
     }
   }
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < kPer; ++e) {
-    const int r = tid + e * kSortThreads;
-    if (r < n) {
-      box[r] = rb[e];
-      score[r] = rs[e];
-      assign[r] = kFree;
-      count[r] = 0;
-      if (A.out_order) A.out_order[(int64_t)b * A.cap + r] = ri[e];
+    if (rr[e] >= 0) {
+      box[rr[e]] = rb[e];
+      score[rr[e]] = rs[e];
+      assign[rr[e]] = kFree;
+      count[rr[e]] = 0;
     }
   }
   __syncthreads();
 
-  // ---- 2. heads in score order (:173-190)
+  // ---- 2. heads in score order (:173-190), 32 candidate heads per round.
+  // Every thread keeps its 8 boxes in registers (rb[e], score rank rr[e]) with an `alive` bit each.
+  //   a. warp 0 lists the next (up to) 32 unassigned positions = the candidates of this round
+  //   b. thread (k = warp, m = lane) tests candidate k against the earlier candidate m  -> 32 row masks
+  //   c. every thread resolves the 32 candidates from the masks (bit operations): candidate k is a head unless an earlier
+  //      HEAD of the round overlaps it (then it joins the first such head)
+  //   d. every thread tests its own alive boxes behind the last candidate against the round's heads, in head order
+  // Three barriers per 32 heads.
+  __shared__ int s_cand[32];
+  __shared__ unsigned s_mask[32];
+  __shared__ unsigned s_selfok;
+  __shared__ int s_ncand;
+  unsigned alive = 0;
+#pragma unroll
+  for (int e = 0; e < kPer; ++e) alive |= (rr[e] >= 0) ? (1u << e) : 0u;
+  auto add_count = [&](int head, unsigned k) {
+    atomicAdd(reinterpret_cast<unsigned int*>(count) + (head >> 1), k << ((head & 1) * 16));
+  };
   int cur = 0;
   while (true) {
-    // next unassigned position >= cur, found by every warp on its own (all warps read the same state)
-    int p = cur;
-    while (p < n) {
-      const unsigned m = __ballot_sync(0xffffffffu, (p + lane < n) && assign[p + lane] == kFree);
-      if (m) { p += __ffs(m) - 1; break; }
-      p += 32;
+    if (warp == 0) {                                       // a.
+      int have = 0, p = cur;
+      while (p < n && have < 32) {
+        const bool un = (p + lane < n) && assign[p + lane] == kFree;
+        const unsigned m = __ballot_sync(0xffffffffu, un);
+        const int rank = have + __popc(m & ((1u << lane) - 1u));
+        if (un && rank < 32) s_cand[rank] = p + lane;
+        have += __popc(m);
+        p += 32;
+      }
+      if (lane == 0) s_ncand = min(have, 32);
     }
-    if (p >= n) break;
-    const float4 h = box[p];
-    const float area_h = vote_area(h);
-    __syncthreads();                                   // everybody has read assign[] before it changes
-    int mine = 0;
-    for (int j = p + tid; j < n; j += kSortThreads) {
-      if (assign[j] == kFree) {
-        if (vote_overlaps(h, area_h, box[j], A.thr)) {
-          assign[j] = (uint16_t)p;
-          ++mine;
-        } else if (j == p) {
-          assign[j] = kGone;
-        }
+    __syncthreads();
+    const int ncand = s_ncand;
+    if (ncand == 0) break;
+    const int last = s_cand[ncand - 1];
+    {                                                      // b.
+      const int k = warp, m = lane;
+      bool ov = false, self_ok = false;
+      if (k < ncand && m <= k && m < ncand) {
+        const float4 bm = box[s_cand[m]];
+        const bool hit = vote_overlaps(bm, vote_area(bm), box[s_cand[k]], A.thr);
+        ov = hit && m < k;
+        self_ok = hit && m == k;
+      }
+      const unsigned row = __ballot_sync(0xffffffffu, ov);
+      const unsigned so = __ballot_sync(0xffffffffu, self_ok);
+      if (lane == 0) s_mask[k] = row;
+      if (lane == 0 && k == 0) s_selfok = 0u;
+      __syncthreads();
+      if (lane == 0 && so) atomicOr(&s_selfok, 1u << k);
+    }
+    __syncthreads();
+    unsigned heads = 0u;                                   // c. (redundantly in every thread)
+    int joined = -1;                                       // lane k of warp 0 applies candidate k
+    for (int k = 0; k < ncand; ++k) {
+      const unsigned mk = s_mask[k] & heads;
+      if (mk == 0u) heads |= 1u << k;
+      if (warp == 0 && lane == k) joined = mk ? __ffs(mk) - 1 : -1;
+    }
+    if (warp == 0 && lane < ncand) {
+      const int pos = s_cand[lane];
+      if (joined >= 0) {
+        assign[pos] = (uint16_t)s_cand[joined];
+        add_count(s_cand[joined], 1u);
+      } else if ((s_selfok >> lane) & 1u) {
+        assign[pos] = (uint16_t)pos;
+        add_count(pos, 1u);
+      } else {
+        assign[pos] = kGone;                               // NaN self IoU: deleted alone (:189-190)
       }
     }
-    mine = __reduce_add_sync(0xffffffffu, mine);
-    if (lane == 0 && mine) atomicAdd(reinterpret_cast<unsigned int*>(count) + (p >> 1), (unsigned)mine << ((p & 1) * 16));
-    cur = p + 1;
+#pragma unroll
+    for (int e = 0; e < kPer; ++e)                         // the candidates themselves are settled
+      if (rr[e] <= last) alive &= ~(1u << e);
+    {                                                      // d. (warp-uniform loop: no per-lane exits)
+      unsigned hm = heads;
+      while (hm) {
+        const int m = __ffs(hm) - 1;
+        hm &= hm - 1u;
+        const int hp = s_cand[m];
+        const float4 h = box[hp];
+        const float area_h = vote_area(h);
+        unsigned got = 0u;
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) {
+          if (((alive >> e) & 1u) && vote_overlaps(h, area_h, rb[e], A.thr)) {
+            assign[rr[e]] = (uint16_t)hp;
+            alive &= ~(1u << e);
+            ++got;
+          }
+        }
+        if (got) add_count(hp, got);
+      }
+    }
+    cur = last + 1;
     __syncthreads();
   }
   __syncthreads();
