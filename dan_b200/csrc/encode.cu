@@ -511,10 +511,25 @@ DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
 template <bool NEED_ROW, bool MINING>
 __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
+  // the GT offsets are requested before the anchor loads: both arrive in one round trip
+  const int b_first = blockIdx.x * ipw;
+  int pre_off0 = 0, pre_off1 = 0;
+  if (b_first < batch) {
+    pre_off0 = __ldg(A.gt_off + b_first);
+    pre_off1 = __ldg(A.gt_off + b_first + 1);
+  }
   const WarpAnchors W = load_warp_anchors(A);
   const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
-  for (int b = blockIdx.x * ipw; b < b_end; ++b) {
-    const ImageGt ig = image_gt<false>(A, b);
+  for (int b = b_first; b < b_end; ++b) {
+    ImageGt ig;
+    if (b == b_first) {
+      ig.off0 = pre_off0;
+      ig.m_real = pre_off1 - pre_off0;
+      ig.m_eff = ig.m_real > 0 ? ig.m_real : 1;
+      ig.slot0 = pre_off0 + b;
+    } else {
+      ig = image_gt<false>(A, b);
+    }
     float best = 0.f;
     int best_gt = 0;
     for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
@@ -559,19 +574,46 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const E
 template <bool MINING>
 __global__ void __launch_bounds__(kEncThreads, 8) enc_pass2_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
+  // the kernel is a chain of dependent loads (ncu: long_scoreboard): everything that only depends on the thread's
+  // coordinates is requested first, so the cached row maximum, the GT offsets and the anchor arrive in ONE round trip
+  const int b_first = blockIdx.x * ipw;
+  const int a_first = (gridDim.y - 1 - blockIdx.y) * blockDim.x + threadIdx.x;     // = W.a below
+  float pre_best = 0.f;
+  int pre_gt = 0, pre_off0 = 0, pre_off1 = 0;
+  if (b_first < batch) {
+    if (a_first < A.n) {
+      pre_best = __ldg(A.rowbest + (int64_t)b_first * A.n + a_first);
+      pre_gt = __ldg(A.rowgt + (int64_t)b_first * A.n + a_first);
+    }
+    pre_off0 = __ldg(A.gt_off + b_first);
+    pre_off1 = __ldg(A.gt_off + b_first + 1);
+  }
   const WarpAnchors W = load_warp_anchors(A);
   const bool need_haspos = !MINING && !A.gt_max_first;
   const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
-  for (int b = blockIdx.x * ipw; b < b_end; ++b) {
-    const ImageGt ig = image_gt<false>(A, b);
+  for (int b = b_first; b < b_end; ++b) {
+    ImageGt ig;
+    if (b == b_first) {
+      ig.off0 = pre_off0;
+      ig.m_real = pre_off1 - pre_off0;
+      ig.m_eff = ig.m_real > 0 ? ig.m_real : 1;
+      ig.slot0 = pre_off0 + b;
+    } else {
+      ig = image_gt<false>(A, b);
+    }
     RowState s;
     s.best = 0.f; s.best_gt = 0; s.ov0 = 0.f;
     s.claimed = false; s.cbest = 0.f; s.cbest_gt = 0;
     s.owner = -1; s.owner_ov = 0.f;
     if (W.valid) {
-      const int64_t row = (int64_t)b * A.n + W.a;
-      s.best = A.rowbest[row];
-      s.best_gt = A.rowgt[row];
+      if (b == b_first) {
+        s.best = pre_best;
+        s.best_gt = pre_gt;
+      } else {
+        const int64_t row = (int64_t)b * A.n + W.a;
+        s.best = A.rowbest[row];
+        s.best_gt = A.rowgt[row];
+      }
     }
     // An anchor can tie with / be claimed by GT k only if its overlap reaches the column maximum cm[k] (to within
     // FLT_EPSILON for the mining matcher).  No overlap of this warp exceeds the largest row maximum of its lanes, so
