@@ -42,58 +42,57 @@ DAN_D float4 handoff_box(const HandoffArgs& A, int b, int i, bool& keep) {
   return g;
 }
 
+// One warp per image, 32 images per sweep of the CTA: the lanes take the image's boxes 32 at a time (ballot + prefix
+// popcount keep their order), warp 0 scans the 32 per-image counts, then every warp writes its survivors.
 __global__ void __launch_bounds__(1024, 1) gt_handoff_kernel(const HandoffArgs A) {
-  __shared__ int s_warp[32][2];
+  __shared__ int s_cnt[32], s_slot[32], s_at[32];
   __shared__ int s_carry[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 2) s_carry[tid] = 0;
   __syncthreads();
-  for (int b0 = 0; b0 < A.batch; b0 += 1024) {
-    const int b = b0 + tid;
-    int kept = 0, lo = 0, hi = 0;
+  for (int b0 = 0; b0 < A.batch; b0 += 32) {
+    const int b = b0 + warp;
+    int lo = 0, hi = 0, kept = 0;
     if (b < A.batch) {
       lo = A.offsets[b];
       hi = A.offsets[b + 1];
-      for (int i = lo; i < hi; ++i) {
-        bool keep;
-        handoff_box(A, b, i, keep);
-        kept += keep ? 1 : 0;
+      for (int i0 = lo; i0 < hi; i0 += 32) {
+        bool keep = false;
+        if (i0 + lane < hi) handoff_box(A, b, i0 + lane, keep);
+        kept += __popc(__ballot_sync(0xffffffffu, keep));
       }
     }
-    // exclusive scan over the images of (image kept, boxes kept)
-    int v[2] = {kept > 0 ? 1 : 0, kept}, incl[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      incl[q] = v[q];
+    if (lane == 0) s_cnt[warp] = kept;
+    __syncthreads();
+    if (warp == 0) {                                       // exclusive scan over the 32 images of (image kept, boxes kept)
+      const int c = s_cnt[lane];
+      int img = c > 0 ? 1 : 0, box = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl[q], d);
-        if (lane >= d) incl[q] += o;
+        const int o0 = __shfl_up_sync(0xffffffffu, img, d), o1 = __shfl_up_sync(0xffffffffu, box, d);
+        if (lane >= d) { img += o0; box += o1; }
       }
-      if (lane == 31) s_warp[warp][q] = incl[q];
+      s_slot[lane] = s_carry[0] + img - 1;                  // position of the image in the batch (if it is kept)
+      s_at[lane] = s_carry[1] + box - c;                    // its first box
+      __syncwarp();
+      if (lane == 31) { s_carry[0] += img; s_carry[1] += box; }
     }
     __syncthreads();
-    int before[2] = {s_carry[0], s_carry[1]}, chunk[2] = {0, 0};
-    for (int w = 0; w < 32; ++w) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (w < warp) before[q] += s_warp[w][q];
-        chunk[q] += s_warp[w][q];
-      }
-    }
     if (b < A.batch && kept > 0) {
-      const int slot = before[0] + incl[0] - 1;            // position of this image in the batch
-      int at = before[1] + incl[1] - kept;                 // its first box
-      A.out_image[slot] = b;
-      A.out_offsets[slot] = at;
-      for (int i = lo; i < hi; ++i) {
-        bool keep;
-        const float4 g = handoff_box(A, b, i, keep);
-        if (keep) A.out_boxes[at++] = g;
+      int at = s_at[warp];
+      if (lane == 0) {
+        A.out_image[s_slot[warp]] = b;
+        A.out_offsets[s_slot[warp]] = at;
+      }
+      for (int i0 = lo; i0 < hi; i0 += 32) {
+        bool keep = false;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i0 + lane < hi) g = handoff_box(A, b, i0 + lane, keep);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) A.out_boxes[at + __popc(m & ((1u << lane) - 1u))] = g;
+        at += __popc(m);
       }
     }
-    __syncthreads();
-    if (tid < 2) s_carry[tid] += chunk[tid];
     __syncthreads();
   }
   if (tid == 0) {
