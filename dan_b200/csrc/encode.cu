@@ -511,25 +511,10 @@ DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
 template <bool NEED_ROW, bool MINING>
 __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
-  // the GT offsets are requested before the anchor loads: both arrive in one round trip
-  const int b_first = blockIdx.x * ipw;
-  int pre_off0 = 0, pre_off1 = 0;
-  if (b_first < batch) {
-    pre_off0 = __ldg(A.gt_off + b_first);
-    pre_off1 = __ldg(A.gt_off + b_first + 1);
-  }
   const WarpAnchors W = load_warp_anchors(A);
   const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
-  for (int b = b_first; b < b_end; ++b) {
-    ImageGt ig;
-    if (b == b_first) {
-      ig.off0 = pre_off0;
-      ig.m_real = pre_off1 - pre_off0;
-      ig.m_eff = ig.m_real > 0 ? ig.m_real : 1;
-      ig.slot0 = pre_off0 + b;
-    } else {
-      ig = image_gt<false>(A, b);
-    }
+  for (int b = blockIdx.x * ipw; b < b_end; ++b) {
+    const ImageGt ig = image_gt<false>(A, b);
     float best = 0.f;
     int best_gt = 0;
     for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {

@@ -128,8 +128,11 @@ DAN_D float4 pp_box(const PpArgs& A, int b, int a) { return pp_finish(A, pp_load
 // ---------------------------------------------------------------------------
 constexpr int kFilterPerThread = 4;     // anchors per thread: 4 independent logit loads in flight (memory-level parallelism)
 
-// exact per-anchor path: softmax, threshold, decode + clip, min-size, warp-aggregated append of the survivors
-DAN_D void filter_one(const PpArgs& A, int b, int a, bool live, int lane) {
+// exact per-anchor path: softmax, threshold, decode + clip, min-size, warp-aggregated append of the survivors.
+// STAGED (two classes = one list per image): the keys are collected in the CTA's shared memory and appended to the list
+// with ONE global atomic per CTA; per-warp atomics on the same counter serialise in L2 (ncu: 20 % of the stall samples).
+template <bool STAGED>
+DAN_D void filter_one(const PpArgs& A, int b, int a, bool live, int lane, unsigned long long* s_keys, int* s_cnt) {
   const int C = A.num_classes;
   const float* x = A.cls + ((int64_t)b * A.n + (live ? a : 0)) * C;
   // tf.nn.softmax: exp(x - max) * (1 / sum(exp(x - max))), sum in class order
@@ -161,21 +164,28 @@ DAN_D void filter_one(const PpArgs& A, int b, int a, bool live, int lane) {
     const unsigned m = __ballot_sync(0xffffffffu, pass);
     if (m != 0u) {
       const int list = b * (C - 1) + (c - 1);
+      const unsigned long long key = ((unsigned long long)score_to_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
       int base = 0;
-      if (lane == 0) base = atomicAdd(A.key_count + list, __popc(m));
+      if (lane == 0) base = STAGED ? atomicAdd(s_cnt, __popc(m)) : atomicAdd(A.key_count + list, __popc(m));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (pass) {
         const int pos = base + __popc(m & ((1u << lane) - 1u));
-        A.keys[(int64_t)list * A.n + pos] = ((unsigned long long)score_to_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+        if (STAGED) s_keys[pos] = key;
+        else A.keys[(int64_t)list * A.n + pos] = key;
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
+  __shared__ unsigned long long s_keys[256 * kFilterPerThread];
+  __shared__ int s_cnt, s_base;
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int a0 = blockIdx.x * (256 * kFilterPerThread) + threadIdx.x;
+  const bool staged = A.num_classes == 2;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
   // Two classes: softmax_1 = sigmoid(x1 - x0).  An anchor whose logit difference is more than 0.05 below
   // logit(threshold) cannot pass (the fp32 evaluation is accurate to ~1e-6 relative), so the ~98 % background anchors
   // leave after one subtraction.  The exact path runs per 32-anchor group when any of its lanes may pass.
@@ -209,7 +219,15 @@ __global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
   __syncwarp();
   for (int j = 0; j < total; j += 32) {
     const bool live = j + lane < total;
-    filter_one(A, b, live ? mylist[j + lane] : 0, live, lane);
+    if (staged) filter_one<true>(A, b, live ? mylist[j + lane] : 0, live, lane, s_keys, &s_cnt);
+    else filter_one<false>(A, b, live ? mylist[j + lane] : 0, live, lane, s_keys, &s_cnt);
+  }
+  if (staged) {
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (threadIdx.x == 0 && cnt > 0) s_base = atomicAdd(A.key_count + b, cnt);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += 256) A.keys[(int64_t)b * A.n + s_base + i] = s_keys[i];
   }
 }
 
