@@ -443,10 +443,11 @@ def run_cuda(args):
     h2d = sum(int(sets[0]["host"][n].numel() * sets[0]["host"][n].element_size()) for n in ("gt", "offs", "cls", "loc"))
     d2h = slab_words * 4
     e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * e2e_s / K,
+           "ms_per_step": 1e3 * e2e_s / K, "h2d_gbs_per_gpu": h2d * K / e2e_s / 1e9,
            "note": "per step: pinned host GT + predictions copied in, hot path, detection slab copied out to pinned host memory; "
                    "copies of neighbouring steps overlap the compute (3 streams); encode targets stay on the device "
-                   "(consumed by the loss there)"}
+                   "(consumed by the loss there); bound by the host-to-device copy of the predictions over PCIe "
+                   "(h2d_gbs_per_gpu is what the link delivers)"}
 
     # ---- per-kernel CUDA-event durations (profile entry points), cold buffers --------------------------------------
     prof = {}
