@@ -712,6 +712,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   uint32_t* wbuf = ebuf + (tid >> 5) * kWarpEdgeBuf;
   int wcount = 0;                                            // warp-uniform
   auto flush_warp = [&]() {
+    __syncwarp();                                            // the buffer entries were written by other lanes
     int base = 0;
     if (lane == 0) base = atomicAdd(A.edge_n + list, wcount);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -870,6 +871,10 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
 #ifdef DAN_PHASE_TIMING
     int dbg_rounds = 0;
 #endif
+    // One sweep of the relaxation reads status[] while other threads set entries to 2 (suppressed) in the same sweep:
+    // an INTENDED race (compute-sanitizer racecheck reports it).  status only moves 0 -> 2 inside a sweep and 0 -> 1
+    // between sweeps (behind the barriers); a stale 0 merely postpones a decision to the next sweep, and the fixed
+    // point - the greedy NMS result - does not depend on the interleaving.  Byte stores do not tear.
     while (true) {
 #ifdef DAN_PHASE_TIMING
       ++dbg_rounds;
