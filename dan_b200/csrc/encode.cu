@@ -8,14 +8,13 @@
 //                                    op boundary, overlaps [N,M] given in HBM.
 //
 // Three launches per batch, all images of the batch in each launch:
-//   pass 1  per-GT column maximum (the only cross-anchor quantity of stage 2 /
-//           of the dual matcher's "GT side") -> atomicMax on fp32 bit patterns
-//   pass 2  per anchor: row max/argmax (stage 1), tie test against the column
-//           maxima (stage 2 / dual claim), labels, encode, all outputs; mining
-//           also histograms matches per GT and buckets compensation candidates
-//   pass 3  (mining only) stage 3 "hard face compensation": one warp per image
-//           walks the GTs in ascending order (the stage is order dependent,
-//           small_mining_match.cc:199-222) and patches the few affected anchors
+//   pass 1  per-GT column maximum (the only cross-anchor quantity of stage 2 / of the dual matcher's "GT side")
+//           -> atomicMax on fp32 bit patterns; the per-anchor row maximum / argmax found on the way are cached
+//           (8 B/anchor); mining: anchors above stop_positive_thres are pushed to per-GT candidate buckets
+//   pass 2  per anchor: stage 1 from the cached row maximum, tie test against the column maxima (stage 2 / dual
+//           claim) only for the GTs this warp can reach, labels, encode, ALL outputs (44 B/anchor)
+//   pass 3  (mining only) stage 3 "hard face compensation": one CTA per image walks the GTs in ascending order
+//           (the stage is order dependent, small_mining_match.cc:199-222) and patches the few affected anchors
 //
 // Culling (fused path): a warp owns 32 consecutive anchors; it reduces their
 // bounding box with redux.sync and tests 32 GT boxes per ballot against it.  Only

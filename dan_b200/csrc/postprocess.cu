@@ -7,18 +7,18 @@
 //                      instead multiplies by 0/1 masks and keeps all N rows
 //                      (bbox_util.py:24-59); rows it zeroes can never precede a
 //                      positive score in tf.nn.top_k, so dropping them is exact.
-//   topk_sort_kernel   per (image, class): block radix select of the keep_topk
-//                      largest keys when more survive, then an in-shared-memory
-//                      bitonic sort.  Keys are unique, descending key order ==
-//                      descending score with ties broken by LOWER index, which is
-//                      tf.nn.top_k's documented order (bbox_util.py:64).
-//   nms_mask_kernel    64x64 tiles of the upper-triangular suppression bit matrix
-//                      with tf.image.non_max_suppression's IoU (no +1, strict >,
-//                      area<=0 never suppresses).
-//   nms_sweep_kernel   one warp per (image, class): 64-wide chunks; the serial
-//                      part is a register-resident shuffle sweep over the diagonal
-//                      word, the kept rows are OR-ed into the removed set by all
-//                      lanes; writes the zero padded outputs (bbox_util.py:80-90).
+//   topk_sort_kernel   sort_bboxes alone (bbox_util.py:61-72): block radix select of the keep_topk largest keys
+//                      when more survive, then the bitonic sort of sort.cuh.  Keys are unique, descending key
+//                      order == descending score with ties broken by LOWER index, which is tf.nn.top_k's order.
+//   pp_sort_kernel     per (image, class): the same top-k + sort, then decode of the survivors and the broad phase of
+//                      the NMS: boxes binned by size class (power of two of the longer side) and centre cell.
+//   nms_pairs_kernel   narrow phase: tf.image.non_max_suppression's IoU test (no +1, corners min/max-normalised,
+//                      strict >, area <= 0 never suppresses) only for boxes whose grid windows meet -> a sparse list
+//                      of suppression EDGES (lower rank, higher rank).
+//   nms_resolve_kernel greedy NMS as a relaxation over the edges (kept(i) = no kept lower-ranked neighbour; the depth
+//                      of the dependency chains is a handful of sweeps), ordered compaction, zero padded outputs
+//                      (bbox_util.py:80-90).  Lists with too many edges, a negative threshold or more candidates
+//                      than the pair kernel can stage fall back to rounds of 64 candidates against the kept list.
 #include <math.h>
 #include <stdlib.h>
 
