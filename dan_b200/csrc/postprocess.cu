@@ -70,7 +70,7 @@ struct PpArgs {
   float* class_amin;          // [L, 16] smallest box area per size class (IoU <= area ratio: whole classes are skipped)
   uint16_t* box_cell;         // [L, keep_topk] flattened (class, cy, cx) of each box, 0xffff = not binned
   uint16_t* box_pos;          // [L, keep_topk] position of each box inside cell_items
-  uint16_t* cell_start;       // [L, kTotalCells + 1]
+  uint16_t* cell_start;       // [L, kCellStride] (kTotalCells + 1 entries used; the stride keeps every list 16-byte aligned)
   uint16_t* cell_items;       // [L, keep_topk] ranks grouped by cell
   uint32_t* edges;            // [L, kEdgeCap] (hi << 16 | lo): lo suppresses hi when lo is kept
   int32_t* edge_n;            // [L]
@@ -327,6 +327,7 @@ constexpr int kNmsClasses = 10;                                    // class 9: m
 constexpr int kGridDim = 32;                                       // cells per dimension and class
 constexpr int kCellsPerClass = kGridDim * kGridDim;
 constexpr int kTotalCells = kNmsClasses * kCellsPerClass;
+constexpr int kCellStride = (kTotalCells + 1 + 7) / 8 * 8;      // uint16 entries per list, a multiple of 16 bytes
 constexpr int kEdgeCap = 1 << 18;                                  // suppression edges per list (1 MB)
 
 // geometry of the per-class grids of one list
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
   }
   __syncthreads();
   DAN_PHASE(3);
-  uint16_t* cell_start = A.cell_start + (int64_t)list * (kTotalCells + 1);
+  uint16_t* cell_start = A.cell_start + (int64_t)list * kCellStride;
   {  // exclusive scan of the cell counters: consecutive cells per thread
     constexpr int per = (kTotalCells + kSortThreads - 1) / kSortThreads;
     int local[per];
@@ -653,8 +654,8 @@ constexpr int kPairCtas = 16;         // upper bound of CTAs per list
 constexpr int kPairEdgeBuf = 8192;
 
 static size_t pairs_smem_bytes(int keep_topk) {
-  return (size_t)keep_topk * 16 + (size_t)keep_topk * 4 + align_up((size_t)keep_topk * 2, 16) * 3 +
-         align_up((size_t)(kTotalCells + 1) * 2, 16) + (size_t)kPairEdgeBuf * 4;
+  return (size_t)keep_topk * 16 + align_up((size_t)keep_topk * 4, 16) + align_up((size_t)keep_topk * 2, 16) * 3 +
+         (size_t)kCellStride * 2 + (size_t)kPairEdgeBuf * 4;
 }
 
 __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs A) {
@@ -672,22 +673,38 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   const int64_t o = (int64_t)list * A.keep_topk;
   unsigned char* p = dyn_smem;
   float4* box = reinterpret_cast<float4*>(p); p += (size_t)A.keep_topk * 16;
-  float* area = reinterpret_cast<float*>(p); p += (size_t)A.keep_topk * 4;
+  float* area = reinterpret_cast<float*>(p); p += ((size_t)A.keep_topk * 4 + 15) / 16 * 16;
   uint16_t* box_cell = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
   uint16_t* box_pos = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
   uint16_t* cell_items = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
-  uint16_t* cell_start = reinterpret_cast<uint16_t*>(p); p += ((size_t)(kTotalCells + 1) * 2 + 15) / 16 * 16;
+  uint16_t* cell_start = reinterpret_cast<uint16_t*>(p); p += (size_t)kCellStride * 2;
   uint32_t* ebuf = reinterpret_cast<uint32_t*>(p);
 
-  for (int i = tid; i < K; i += kSortThreads) {
-    box[i] = A.s_box[o + i];
-    area[i] = A.s_area[o + i];
-    box_cell[i] = A.box_cell[o + i];
-    box_pos[i] = A.box_pos[o + i];
-    cell_items[i] = A.cell_items[o + i];
+  if ((A.keep_topk & 7) == 0) {
+    // every list starts 16-byte aligned: 16-byte copies (reading up to the next multiple of 8 <= keep_topk entries)
+    for (int i = tid; i < K; i += kSortThreads) box[i] = A.s_box[o + i];
+    const int n4 = (K + 3) / 4, n8 = (K + 7) / 8;
+    for (int i = tid; i < n4; i += kSortThreads)
+      reinterpret_cast<float4*>(area)[i] = reinterpret_cast<const float4*>(A.s_area + o)[i];
+    for (int i = tid; i < n8; i += kSortThreads) {
+      reinterpret_cast<uint4*>(box_cell)[i] = reinterpret_cast<const uint4*>(A.box_cell + o)[i];
+      reinterpret_cast<uint4*>(box_pos)[i] = reinterpret_cast<const uint4*>(A.box_pos + o)[i];
+      reinterpret_cast<uint4*>(cell_items)[i] = reinterpret_cast<const uint4*>(A.cell_items + o)[i];
+    }
+  } else {
+    for (int i = tid; i < K; i += kSortThreads) {
+      box[i] = A.s_box[o + i];
+      area[i] = A.s_area[o + i];
+      box_cell[i] = A.box_cell[o + i];
+      box_pos[i] = A.box_pos[o + i];
+      cell_items[i] = A.cell_items[o + i];
+    }
   }
-  const uint16_t* g_start = A.cell_start + (int64_t)list * (kTotalCells + 1);
-  for (int i = tid; i <= kTotalCells; i += kSortThreads) cell_start[i] = g_start[i];
+  {  // the grid: 16-byte copies (20 KB per CTA; two-byte loads made this the longest part of the staging)
+    const uint4* g_start = reinterpret_cast<const uint4*>(A.cell_start + (int64_t)list * kCellStride);
+    uint4* s_start = reinterpret_cast<uint4*>(cell_start);
+    for (int i = tid; i < kCellStride / 8; i += kSortThreads) s_start[i] = g_start[i];
+  }
   const float4 gi = A.grid_info[list];
   GridGeom g;
   g.oy = gi.x; g.ox = gi.y; g.extent = gi.z;
@@ -864,7 +881,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
     const int smem_edges = A.keep_topk * 4;          // 16 B per candidate slot
     if (n_edges <= smem_edges) {
       uint32_t* se = reinterpret_cast<uint32_t*>(m.cand_box);
-      for (int e = tid; e < n_edges; e += kSortThreads) se[e] = edges[e];
+      // 16-byte copies (the list's edge array is 16-byte aligned and kEdgeCap a multiple of 4)
+      for (int e = tid; e < (n_edges + 3) / 4; e += kSortThreads)
+        reinterpret_cast<uint4*>(se)[e] = reinterpret_cast<const uint4*>(edges)[e];
       edges = se;
     }
     for (int i = tid; i < K; i += kSortThreads) m.status[i] = 0;
@@ -1008,7 +1027,7 @@ static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms)
   w.s_area = take(nms ? lists * keep_topk * 4 : 0);
   w.box_cell = take(nms ? lists * keep_topk * 2 : 0);
   w.box_pos = take(nms ? lists * keep_topk * 2 : 0);
-  w.cell_start = take(nms ? lists * (size_t)(kTotalCells + 1) * 2 : 0);
+  w.cell_start = take(nms ? lists * (size_t)kCellStride * 2 : 0);
   w.cell_items = take(nms ? lists * keep_topk * 2 : 0);
   w.edges = take(nms ? lists * (size_t)kEdgeCap * 4 : 0);
   w.total = off;
