@@ -888,7 +888,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
         reinterpret_cast<uint4*>(se)[e] = reinterpret_cast<const uint4*>(edges)[e];
       edges = se;
     }
-    for (int i = tid; i < K; i += kSortThreads) m.status[i] = 0;
+    for (int i = tid; i < K; i += kSortThreads) { m.status[i] = 0; m.pending[i] = 0; }
+    __syncthreads();
 #ifdef DAN_PHASE_TIMING
     int dbg_rounds = 0;
 #endif
@@ -900,8 +901,6 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
 #ifdef DAN_PHASE_TIMING
       ++dbg_rounds;
 #endif
-      for (int i = tid; i < K; i += kSortThreads) m.pending[i] = 0;
-      __syncthreads();
       for (int e0 = tid; e0 < n_edges; e0 += 4 * kSortThreads) {
         uint32_t ed[4];
         int sh[4], sl[4];
@@ -929,7 +928,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
       for (int i = tid; i < K; i += kSortThreads) {
         if (m.status[i] == 0) {
           if (m.pending[i] == 0) m.status[i] = 1;
-          else any = true;
+          else { any = true; m.pending[i] = 0; }         // (cleared here for the next sweep: one barrier less per sweep)
         }
       }
       if (!__syncthreads_or(any ? 1 : 0)) break;
