@@ -634,6 +634,15 @@ __global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A
     }
   }
   DAN_PHASE(4);
+  // the pair kernel stages these arrays with 16-byte copies: define the few entries between K and the next multiple of 8,
+  // and the padding of the cell table
+  for (int i = K + tid; i < min(A.keep_topk, (K + 7) & ~7); i += kSortThreads) {
+    A.s_area[o + i] = 0.f;
+    box_cell[i] = 0xffff;
+    A.box_pos[o + i] = 0;
+    cell_items[i] = 0;
+  }
+  for (int i = kTotalCells + 1 + tid; i < kCellStride; i += kSortThreads) cell_start[i] = 0;
   if (tid == 0) {
     A.s_len[list] = K;
     A.grid_info[list] = make_float4(g.oy, g.ox, g.extent, __int_as_float(s_class_mask));
@@ -884,8 +893,13 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
     if (n_edges <= smem_edges) {
       uint32_t* se = reinterpret_cast<uint32_t*>(m.cand_box);
       // 16-byte copies (the list's edge array is 16-byte aligned and kEdgeCap a multiple of 4)
-      for (int e = tid; e < (n_edges + 3) / 4; e += kSortThreads)
-        reinterpret_cast<uint4*>(se)[e] = reinterpret_cast<const uint4*>(edges)[e];
+      for (int e = tid; e < (n_edges + 3) / 4; e += kSortThreads) {
+        if (4 * e + 3 < n_edges) {
+          reinterpret_cast<uint4*>(se)[e] = reinterpret_cast<const uint4*>(edges)[e];
+        } else {                                          // the last, partial vector: nothing beyond the list is read
+          for (int q = 4 * e; q < n_edges; ++q) se[q] = edges[q];
+        }
+      }
       edges = se;
     }
     for (int i = tid; i < K; i += kSortThreads) { m.status[i] = 0; m.pending[i] = 0; }
