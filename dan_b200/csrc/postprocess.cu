@@ -729,8 +729,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
   const int class_mask = __float_as_int(gi.w);
   uint32_t* edges = A.edges + (int64_t)list * kEdgeCap;
   const float thr = A.nms_thr;
-  // warp-cooperative search: a warp takes one box i at a time and walks its size classes d >= class(i); for every
-  // grid row of the class-d window the 32 lanes test 32 consecutive items of the row's contiguous item range.
+  // warp-cooperative search: a half-warp takes one box i at a time and walks its size classes d >= class(i); the item
+  // ranges of the grid rows of the class-d windows form one flat candidate list that its 16 lanes test 16 at a time.
   // (A thread-per-query loop is SIMT-hostile here: the windows hold anything from 0 to hundreds of boxes.)
   const int lane = tid & 31;
   const int warps_total = my_ctas * (kSortThreads / 32);
@@ -760,14 +760,19 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
 #define DAN_TICK() do { } while (0)
 #define DAN_TOCK(acc) do { } while (0)
 #endif
-  for (int i = blockIdx.x * (kSortThreads / 32) + (tid >> 5); i < K; i += warps_total) {
-    const int my_cid = box_cell[i];
-    if (my_cid == 0xffff) continue;                       // warp-uniform
-    const int c = my_cid / kCellsPerClass;
+  // TWO boxes per warp, one per half-warp (consecutive ranks): most boxes have fewer than 16 candidates and search two
+  // size classes, so a whole warp per box left half of its lanes idle and paid the window set-up once per box.
+  const int half = lane >> 4, hl = lane & 15;
+  for (int i0 = 2 * (blockIdx.x * (kSortThreads / 32) + (tid >> 5)); i0 < K; i0 += 2 * warps_total) {
+    const int i = i0 + half;
+    const int my_cid = (i < K) ? box_cell[i] : 0xffff;
+    const bool live_box = my_cid != 0xffff;
+    if (!__any_sync(0xffffffffu, live_box)) continue;      // warp-uniform
+    const int c = live_box ? my_cid / kCellsPerClass : 0;
     const int own_row = (my_cid - c * kCellsPerClass) / kGridDim;    // grid row of the box's own cell (0 for the last class)
-    const int after_me = box_pos[i] + 1;
-    const float4 me = box[i];
-    const float my_area = area[i];
+    const int after_me = live_box ? box_pos[i] + 1 : 0;
+    const float4 me = live_box ? box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float my_area = live_box ? area[i] : 0.f;
     auto emit = [&](bool edge, int j) {       // append the edges found by this step to the warp's private buffer
       const unsigned em = __ballot_sync(0xffffffffu, edge);
       if (em != 0u) {
@@ -776,19 +781,21 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
         wcount += __popc(em);
       }
     };
-    // classes to search: non-empty, d >= c, and not ruled out by the area ratio (IoU <= area_i / area_j: a class
-    // whose smallest box is already too large for the threshold cannot suppress i)
-    unsigned todo = __ballot_sync(0xffffffffu, lane >= c && lane < kNmsClasses && ((class_mask >> lane) & 1) &&
-                                                   (lane == c || !(my_area < s_prune[lane < kNmsClasses ? lane : 0])));
-    while (todo) {                                         // up to 4 classes per pass
+    // classes to search (lane hl of a half-warp speaks for class hl): non-empty, d >= c, and not ruled out by the area
+    // ratio (IoU <= area_i / area_j: a class whose smallest box is already too large for the threshold cannot
+    // suppress i)
+    const bool want = live_box && hl >= c && hl < kNmsClasses && ((class_mask >> hl) & 1) &&
+                      (hl == c || !(my_area < s_prune[hl < kNmsClasses ? hl : 0]));
+    unsigned todo = (__ballot_sync(0xffffffffu, want) >> (16 * half)) & 0xffffu;     // per half-warp
+    while (__any_sync(0xffffffffu, todo != 0u)) {          // up to 2 classes per pass and box
       DAN_TICK();
       // lane = (class slot, window row): each lane finds the item range of ONE row of ONE class's window, so the
-      // window geometry of all classes is computed in parallel and all candidates of the box form one flat list
-      const int slot = lane >> 3, r = lane & 7;
+      // window geometry of the classes is computed in parallel and all candidates of a box form one flat list
+      const int slot = hl >> 3, r = hl & 7;
       unsigned rest = todo;                                // (slot+1)-th set bit of todo (no __fns: it is a software loop)
       int dsel = -1;
 #pragma unroll
-      for (int sidx = 0; sidx < 4; ++sidx) {
+      for (int sidx = 0; sidx < 2; ++sidx) {
         const int dd = rest ? (__ffs(rest) - 1) : -1;
         if (slot == sidx) dsel = dd;
         rest &= rest - 1u;
@@ -822,29 +829,30 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
           }
           len = max((int)cell_start[row + cx1 + 1] - p0, 0);
         }
-        int incl = len;                                  // inclusive prefix over the 32 (class, row) ranges
+        int incl = len;                                  // inclusive prefix over the 16 (class, row) ranges of the half-warp
 #pragma unroll
-        for (int sh = 1; sh < 32; sh <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, sh);
-          if (lane >= sh) incl += v;
+        for (int sh = 1; sh < 16; sh <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, sh, 16);
+          if (hl >= sh) incl += v;
         }
-        const int n = __shfl_sync(0xffffffffu, incl, 31);
+        const int n = __shfl_sync(0xffffffffu, incl, 15, 16);          // candidates of this half-warp's box
+        const int n_max = __reduce_max_sync(0xffffffffu, n);
         const int shift = p0 - (incl - len);             // item position = q + shift inside this lane's range
         DAN_TOCK(acc_setup);
         DAN_TICK();
 #ifdef DAN_PHASE_TIMING
         acc_n += n; acc_boxes += 1;
 #endif
-        for (int q0 = 0; q0 < n; q0 += 32) {              // warp-uniform trip count
-          const int q = q0 + lane;
+        for (int q0 = 0; q0 < n_max; q0 += 16) {          // warp-uniform trip count
+          const int q = q0 + hl;
           int lo = 0;                                      // first range whose inclusive prefix exceeds q
 #pragma unroll
-          for (int st = 16; st >= 1; st >>= 1) {
-            const int v = __shfl_sync(0xffffffffu, incl, lo + st - 1);
+          for (int st = 8; st >= 1; st >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, lo + st - 1, 16);
             if (q >= v) lo += st;
           }
-          lo = min(lo, 31);
-          const int pos = q + __shfl_sync(0xffffffffu, shift, lo);
+          lo = min(lo, 15);
+          const int pos = q + __shfl_sync(0xffffffffu, shift, lo, 16);
           bool edge = false;
           int j = 0;
           if (q < n) {
@@ -856,7 +864,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs
         DAN_TOCK(acc_loop);
         DAN_TICK();
       }
-      todo = rest;                                         // the (up to) 4 classes of this pass are done
+      todo = rest;                                         // the (up to) 2 classes of this pass are done
     }
   }
   DAN_PHASE(26);
