@@ -520,15 +520,18 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const E
       const int k = k0 + lane;
       const float4 gk = (k < ig.m_eff) ? gt_box(A, ig, k) : make_float4(0.f, 0.f, 0.f, 0.f);
       unsigned hits = __ballot_sync(0xffffffffu, (k < ig.m_eff) && may_hit(W.wb, gk));
+      const float gk_area = box_area(gk.x, gk.y, gk.z, gk.w);      // once per GT, broadcast with the box below
       uint32_t my_colmax = 0u;            // column maximum of GT k over this warp's anchors
       while (hits) {
         const int kl = __ffs(hits) - 1;
         hits &= hits - 1;
-        const float4 g = gt_box(A, ig, k0 + kl);
+        // lane kl loaded this GT for the cull test above: broadcast it instead of fetching it again
+        const float4 g = make_float4(__shfl_sync(0xffffffffu, gk.x, kl), __shfl_sync(0xffffffffu, gk.y, kl),
+                                     __shfl_sync(0xffffffffu, gk.z, kl), __shfl_sync(0xffffffffu, gk.w, kl));
+        const float g_area = __shfl_sync(0xffffffffu, gk_area, kl);
         bool hit = false;
         float ov = 0.f;
-        if (W.active) ov = pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g.x, g.y, g.z, g.w,
-                                    box_area(g.x, g.y, g.z, g.w), hit);
+        if (W.active) ov = pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g.x, g.y, g.z, g.w, g_area, hit);
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, (ov > 0.f) ? __float_as_uint(ov) : 0u);
         if (lane == kl) my_colmax = wmax;
         if (ov > best) { best = ov; best_gt = k0 + kl; }      // first strictly-greatest GT wins (tf.argmax / :76-83)
