@@ -473,6 +473,18 @@ def run_cuda(args):
                 "longest_kernel": dom,
                 "pp_filter_achieved_gbs": alg["pp_filter"] / (kernel_ms["pp_filter"] * 1e-3) / 1e9}
 
+    # the match kernels against the non-FMA FP32 issue rate (calibrated: tools/fp32_peak.cu), as the DENSE
+    # evaluation figure N(20M+30) per image; pairs with an empty intersection are culled, so this is an equivalent rate
+    fp32_peak = 37.2e12
+    try:
+        fp32_peak = 1e12 * json.load(open(os.path.join(ROOT, "profiles", "r01_fp32_peak.json")))["fp32_nonfma_tinstr_s"]
+    except Exception:
+        pass
+    dense_flops = N * (20.0 * total_gt_mean + 30.0 * B)
+    match_ms = kernel_ms["enc_pass1"] + kernel_ms["enc_pass2"]
+    roofline["fp32_dense_equivalent"] = {"flops_per_step": dense_flops, "kernels": "enc_pass1 + enc_pass2", "kernel_ms": match_ms,
+                                         "achieved_tflops": dense_flops / (match_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak / 1e12,
+                                         "frac": dense_flops / (match_ms * 1e-3) / fp32_peak}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
