@@ -679,11 +679,12 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass2_fused_kernel(const E
       if (match >= 0) {
         write_positive(A, row, W.ab, gt_box(A, ig, match), score, match);
       } else {
-        A.targets[row] = make_float4(0.f, 0.f, 0.f, 0.f);
-        A.labels[row] = (match < -1) ? -1 : 0;   // anchor_manipulator.py:300-302
-        A.scores[row] = score;
-        if (A.matched != nullptr) A.matched[row] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (A.match32 != nullptr) A.match32[row] = match;
+        // streaming stores: the 44 B/anchor of a step are written once and not read again by this kernel
+        __stcs(A.targets + row, make_float4(0.f, 0.f, 0.f, 0.f));
+        __stcs(reinterpret_cast<long long*>(A.labels) + row, (long long)((match < -1) ? -1 : 0));   // anchor_manipulator.py:300-302
+        __stcs(A.scores + row, score);
+        if (A.matched != nullptr) __stcs(A.matched + row, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (A.match32 != nullptr) __stcs(A.match32 + row, match);
       }
     }
   }
