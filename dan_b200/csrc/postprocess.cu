@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) pp_filter_kernel(const PpArgs A) {
 #pragma unroll
     for (int u = 0; u < kFilterPerThread; ++u) {
       const int a = a0 + u * 256;
-      xx[u] = (a < A.n) ? *reinterpret_cast<const float2*>(A.cls + ((int64_t)b * A.n + a) * 2) : make_float2(0.f, 0.f);
+      xx[u] = (a < A.n) ? __ldcs(reinterpret_cast<const float2*>(A.cls + ((int64_t)b * A.n + a) * 2)) : make_float2(0.f, 0.f);   // read once: streaming
     }
 #pragma unroll
     for (int u = 0; u < kFilterPerThread; ++u)
