@@ -35,7 +35,7 @@ UNIT = "images/s"
 IMAGE = (640, 640)
 PP = (0.01, 0, 5000, 750, 0.3)      # select_threshold, min_size, keep_topk, nms_topk, nms_threshold
 CPU_CFG = dict(kind="s3fd", size=IMAGE, pos=0.4, ign=0.4, mining=True, max_gt=50, max_faces=300, pp=PP)
-KERNELS_PER_STEP = 7                # enc_pass1/2/3, pp_filter, pp_sort (+grid), nms_pairs, nms_resolve
+KERNELS_PER_STEP = 5                # enc_pass1/2/3, pp_filter, nms_greedy
 
 
 def workload_config(batch, n_gpus, extra=None):

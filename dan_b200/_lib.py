@@ -114,6 +114,12 @@ _SIGNATURES = {
     "dan_bbox_vote": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dan_gt_handoff": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp,
                                       c_vp]),
+    "dan_nccl_load": (ctypes.c_int, [ctypes.c_char_p]),
+    "dan_nccl_version": (ctypes.c_int, []),
+    "dan_comm_unique_id": (ctypes.c_int, [c_vp]),
+    "dan_comm_init": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp)]),
+    "dan_comm_destroy": (ctypes.c_int, [c_vp]),
+    "dan_gather_detections": (ctypes.c_int, [c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -176,7 +182,8 @@ def as_f32(t, device=None):
 
 
 class Workspace(object):
-    """Grow-only device scratch buffer owned by the caller side (the library never allocates)."""
+    """Grow-only device scratch buffer owned by the caller side (the library never allocates).  One buffer per
+    (device, stream): a workspace is only ever used by kernels of the stream it was requested on."""
 
     def __init__(self):
         self._buf = None
@@ -186,3 +193,20 @@ class Workspace(object):
         if self._buf is None or self._buf.numel() < nbytes or self._buf.device != device:
             self._buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
         return self._buf
+
+
+class StreamWorkspaces(object):
+    """Default scratch of the standalone entry points: one grow-only Workspace per (device, current stream), so that
+    calls issued on different streams or devices never share scratch memory.  Inside a CUDA-graph capture the key is
+    the capturing stream.  (Explicit Workspace objects, as pipeline.HotPath uses, bypass this.)"""
+
+    def __init__(self):
+        self._by_stream = {}
+
+    def get(self, nbytes, device):
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               int(torch.cuda.current_stream(device).cuda_stream))
+        ws = self._by_stream.get(key)
+        if ws is None:
+            ws = self._by_stream[key] = Workspace()
+        return ws.get(nbytes, device)

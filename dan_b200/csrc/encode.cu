@@ -66,9 +66,8 @@ struct EncArgs {
   int32_t* haspos;       // [G] GT has a positive anchor-side match (dual, gt_max_first=0)
   int32_t* fill;         // [G] candidates pushed per GT
   HeapItem* bucket;      // [G, kBucketCap]
-  HeapItem* spill;       // [B, 3, n] (candidate list, sort buffer, heap of the overflow path)
-  float* rowbest;        // [B, n] per-anchor row maximum, written by fused pass 1, read by fused pass 2
-  int32_t* rowgt;        // [B, n] its (first) argmax
+  HeapItem* spill;       // [B, 2, n] (candidate list and heap of the overflow path)
+  float* wbest;          // [B, ceil(n/32)] largest row maximum of each warp of fused pass 1 (read by the patch pass)
   // outputs
   float4* targets;
   int64_t* labels;
@@ -507,13 +506,90 @@ DAN_D WarpAnchors load_warp_anchors(const EncArgs& A) {
   return w;
 }
 
+// stage 1 of either matcher from the row maximum (small_mining_match.cc:85-93 / anchor_manipulator.py:67-76)
+template <bool MINING>
+DAN_D int stage1_match(const EncArgs& A, float best, int best_gt) {
+  if (MINING) {
+    if (best >= A.neg_low && best < A.low) return -1;
+    if (best >= A.high) return best_gt;
+    return -2;
+  }
+  const bool less = best < A.low;
+  const bool between = (best < A.high) && (best >= A.low);
+  const bool neg = A.ignore_between ? less : between;
+  const bool ign = A.ignore_between ? between : less;
+  int match = best_gt;
+  if (neg) match = -1;
+  if (ign) match = -2;
+  return match;
+}
+
+// Non-positive anchors.  The reference multiplies the encoded targets of EVERY anchor by float(positive)
+// (anchor_manipulator.py:324) and gathers GT clip(match, 0) = GT 0 for the non-positive ones (:297,306), so their
+// targets are 0 * t = a zero with the SIGN of t, and their matched box is 0 * GT 0.  NegCtx holds what is needed to
+// reproduce those signs without evaluating t: per image GT 0 in centre form (uniform over the warp).
+struct NegCtx {
+  float gcy, gcx, gh, gw;     // GT 0 (gh, gw already multiplied by pa_scale for encode_pa_anchors)
+  float4 mzero;               // 0 * GT 0
+  uint32_t ps_sign[4];        // sign bits of the prior scaling
+};
+
+DAN_D uint32_t sign_of(float v) { return __float_as_uint(v) & 0x80000000u; }
+
+DAN_D NegCtx neg_ctx(const EncArgs& A, const ImageGt& ig) {
+  NegCtx c;
+  const float4 g = gt_box(A, ig, 0);
+  point2center(g.x, g.y, g.z, g.w, c.gcy, c.gcx, c.gh, c.gw);
+  if (A.pa_scale > 0.f) { c.gh = fmul(c.gh, A.pa_scale); c.gw = fmul(c.gw, A.pa_scale); }
+  c.mzero = make_float4(__uint_as_float(sign_of(g.x)), __uint_as_float(sign_of(g.y)), __uint_as_float(sign_of(g.z)),
+                        __uint_as_float(sign_of(g.w)));
+  c.ps_sign[0] = sign_of(A.ps0); c.ps_sign[1] = sign_of(A.ps1); c.ps_sign[2] = sign_of(A.ps2); c.ps_sign[3] = sign_of(A.ps3);
+  return c;
+}
+
+// sign bit of log(num / den) for num >= 0: negative iff the quotient is below 1 (for den > 0 the correctly rounded quotient
+// is below 1 exactly when num < den)
+DAN_D uint32_t log_ratio_sign(float num, float den) {
+  const bool below = (den > 0.f) ? (num < den) : (fdiv(num, den) < 1.f);
+  return below ? 0x80000000u : 0u;
+}
+
+// every output row of a NON-positive anchor; the 44 B/anchor of a step are written once and not read again by the
+// encode kernels: streaming stores
+DAN_D void write_negative(const EncArgs& A, int64_t row, const AnchorBox& ab, const NegCtx& c, float score, int match) {
+  float4 t;
+  if (A.debug) {
+    t = make_float4(__uint_as_float(sign_of(ab.y0)), __uint_as_float(sign_of(ab.x0)), __uint_as_float(sign_of(ab.y1)),
+                    __uint_as_float(sign_of(ab.x1)));
+  } else {
+    float acy, acx, ah, aw;
+    point2center(ab.y0, ab.x0, ab.y1, ab.x1, acy, acx, ah, aw);
+    t.x = __uint_as_float(sign_of(fsub(c.gcy, acy)) ^ sign_of(ah) ^ c.ps_sign[0]);
+    t.y = __uint_as_float(sign_of(fsub(c.gcx, acx)) ^ sign_of(aw) ^ c.ps_sign[1]);
+    t.z = __uint_as_float(log_ratio_sign(c.gh, ah) ^ c.ps_sign[2]);
+    t.w = __uint_as_float(log_ratio_sign(c.gw, aw) ^ c.ps_sign[3]);
+  }
+  __stcs(A.targets + row, t);
+  __stcs(reinterpret_cast<long long*>(A.labels) + row, (long long)((match < -1) ? -1 : 0));   // anchor_manipulator.py:300-302
+  __stcs(A.scores + row, score);
+  if (A.matched != nullptr) __stcs(A.matched + row, c.mzero);
+  if (A.match32 != nullptr) __stcs(A.match32 + row, match);
+}
+
+// pass 1 (fused path): everything that depends on ONE anchor only - row maximum / argmax, stage 1 of the matcher,
+// labels, encode, ALL outputs - plus the two cross-anchor quantities the later passes need: the per-GT column maxima
+// (atomicMax) and, for the mining matcher, the stage-3 candidates (overlap > stop_positive_thres) and the per-GT
+// match counts.  What stage 2 / the GT-side claim of the dual matcher changes afterwards is a handful of anchors per
+// GT; pass 2 finds and patches them.
 template <bool NEED_ROW, bool MINING>
 __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const EncArgs A, int batch, int ipw) {
   const int lane = threadIdx.x & 31;
   const WarpAnchors W = load_warp_anchors(A);
+  const int nwarps = (A.n + 31) >> 5;
   const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
   for (int b = blockIdx.x * ipw; b < b_end; ++b) {
     const ImageGt ig = image_gt<false>(A, b);
+    const NegCtx neg = neg_ctx(A, ig);
     float best = 0.f;
     int best_gt = 0;
     for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
@@ -544,155 +620,148 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const E
       }
       if (my_colmax != 0u) atomicMax(A.colmax + ig.slot0 + k, my_colmax);
     }
+    // no overlap of this warp exceeds the largest row maximum of its lanes: pass 2 uses it to skip the warp
+    const uint32_t wbest = __reduce_max_sync(0xffffffffu, __float_as_uint(best));
+    if (lane == 0) A.wbest[(int64_t)b * nwarps + (W.a >> 5)] = __uint_as_float(wbest);
     if (W.valid) {
-      // the row maximum is final here; pass 2 only needs the overlaps that can tie with a column maximum
+      const int match = stage1_match<MINING>(A, best, best_gt);
       const int64_t row = (int64_t)b * A.n + W.a;
-      A.rowbest[row] = best;
-      A.rowgt[row] = best_gt;
-      if (NEED_ROW) {
-        const bool less = best < A.low;
-        const bool between = (best < A.high) && (best >= A.low);
-        if (!less && !between) A.haspos[ig.slot0 + best_gt] = 1;
+      if (match >= 0) {
+        if (MINING) atomicAdd(A.cnt + ig.slot0 + match, 1);
+        if (NEED_ROW) A.haspos[ig.slot0 + match] = 1;          // anchor-side positive (anchor_manipulator.py:67-76)
+        write_positive(A, row, W.ab, gt_box(A, ig, match), best, match);
+      } else {
+        write_negative(A, row, W.ab, neg, best, match);
       }
     }
   }
 }
 
+// pass 2 (fused path): stage 2 of the mining matcher (small_mining_match.cc:160-197) / the GT-side claim of the dual
+// matcher (anchor_manipulator.py:84-104) as a PATCH.  An anchor is affected only if its overlap with some GT k reaches
+// that GT's column maximum cm[k] (to within FLT_EPSILON for the mining matcher).  One thread per warp of pass 1 first
+// compares the warp's largest row maximum with the image's column maxima; the few warps that can reach one (and all
+// warps when a GT has no overlap at all: its "maximum" 0 ties with every zero-overlap anchor, tie T7) are collected
+// and re-evaluated by full warps: row maximum again, tie / claim test, and the outputs of the anchors whose match
+// changed are rewritten (a patched anchor is always positive).
+constexpr int kPatchThreads = 128;
+
 template <bool MINING>
-__global__ void __launch_bounds__(kEncThreads, 8) enc_pass2_fused_kernel(const EncArgs A, int batch, int ipw) {
-  const int lane = threadIdx.x & 31;
-  // the kernel is a chain of dependent loads (ncu: long_scoreboard): everything that only depends on the thread's
-  // coordinates is requested first, so the cached row maximum, the GT offsets and the anchor arrive in ONE round trip
-  const int b_first = blockIdx.x * ipw;
-  const int a_first = (gridDim.y - 1 - blockIdx.y) * blockDim.x + threadIdx.x;     // = W.a below
-  float pre_best = 0.f;
-  int pre_gt = 0, pre_off0 = 0, pre_off1 = 0;
-  if (b_first < batch) {
-    if (a_first < A.n) {
-      pre_best = __ldg(A.rowbest + (int64_t)b_first * A.n + a_first);
-      pre_gt = __ldg(A.rowgt + (int64_t)b_first * A.n + a_first);
-    }
-    pre_off0 = __ldg(A.gt_off + b_first);
-    pre_off1 = __ldg(A.gt_off + b_first + 1);
-  }
-  const WarpAnchors W = load_warp_anchors(A);
+__global__ void __launch_bounds__(kPatchThreads) enc_pass2_patch_kernel(const EncArgs A) {
+  __shared__ int s_list[kPatchThreads];
+  __shared__ int s_n;
+  __shared__ float s_cmin[kPatchThreads / 32];
+  __shared__ int s_wide[kPatchThreads / 32];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nwarps = (A.n + 31) >> 5;
+  const ImageGt ig = image_gt<false>(A, b);
   const bool need_haspos = !MINING && !A.gt_max_first;
-  const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
-  for (int b = b_first; b < b_end; ++b) {
-    ImageGt ig;
-    if (b == b_first) {
-      ig.off0 = pre_off0;
-      ig.m_real = pre_off1 - pre_off0;
-      ig.m_eff = ig.m_real > 0 ? ig.m_real : 1;
-      ig.slot0 = pre_off0 + b;
-    } else {
-      ig = image_gt<false>(A, b);
+
+  // smallest column maximum of the image; does any GT tie with zero-overlap anchors?
+  float cmin = 3.0e38f;
+  bool wide = false;
+  for (int k = tid; k < ig.m_eff; k += kPatchThreads) {
+    const float cm = __uint_as_float(A.colmax[ig.slot0 + k]);
+    wide |= MINING ? (cm < FLT_EPSILON) : (cm == 0.f);
+    cmin = fminf(cmin, cm);
+  }
+  cmin = warp_min_f(cmin);
+  wide = __any_sync(0xffffffffu, wide);
+  if (lane == 0) { s_cmin[warp] = cmin; s_wide[warp] = wide ? 1 : 0; }
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kPatchThreads / 32; ++w) { cmin = fminf(cmin, s_cmin[w]); wide |= s_wide[w] != 0; }
+
+  const int wr = blockIdx.y * kPatchThreads + tid;
+  bool cand = false;
+  if (wr < nwarps) {
+    const float wb = A.wbest[(int64_t)b * nwarps + wr];
+    const float reach = MINING ? fadd(wb, 2.f * FLT_EPSILON) : wb;
+    cand = wide || (reach >= cmin);
+  }
+  if (cand) s_list[atomicAdd(&s_n, 1)] = wr;
+  __syncthreads();
+  const int n_list = s_n;
+
+  for (int i = warp; i < n_list; i += kPatchThreads / 32) {
+    const int a = s_list[i] * 32 + lane;
+    const bool valid = a < A.n;
+    AnchorBox ab = {};
+    bool active = false;
+    if (valid) {
+      ab = load_anchor(A, a);
+      active = (A.mask == nullptr) || (A.mask[a] != 0);
     }
+    const WarpBox wbx = warp_bbox(active, ab);
     RowState s;
     s.best = 0.f; s.best_gt = 0; s.ov0 = 0.f;
     s.claimed = false; s.cbest = 0.f; s.cbest_gt = 0;
     s.owner = -1; s.owner_ov = 0.f;
-    if (W.valid) {
-      if (b == b_first) {
-        s.best = pre_best;
-        s.best_gt = pre_gt;
-      } else {
-        const int64_t row = (int64_t)b * A.n + W.a;
-        s.best = A.rowbest[row];
-        s.best_gt = A.rowgt[row];
-      }
-    }
-    // An anchor can tie with / be claimed by GT k only if its overlap reaches the column maximum cm[k] (to within
-    // FLT_EPSILON for the mining matcher).  No overlap of this warp exceeds the largest row maximum of its lanes, so
-    // GTs with cm[k] above that bound are skipped without evaluating a single IoU.
-    const float wbest = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(s.best)));
-    const float reach = MINING ? fadd(wbest, 2.f * FLT_EPSILON) : wbest;
-    int match = -1;
-    float score = 0.f;
     for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
       const int k = k0 + lane;
       bool test = false;
+      float cmk = 0.f;
       if (k < ig.m_eff) {
-        const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + k));
-        const bool wide = MINING ? (cm < FLT_EPSILON) : (cm == 0.f);
-        test = (cm <= reach && may_hit(W.wb, gt_box(A, ig, k))) || wide;
+        cmk = __uint_as_float(A.colmax[ig.slot0 + k]);
+        const bool widek = MINING ? (cmk < FLT_EPSILON) : (cmk == 0.f);
+        test = may_hit(wbx, gt_box(A, ig, k)) || widek;
       }
       unsigned hits = __ballot_sync(0xffffffffu, test);
       while (hits) {
-        const int kk = k0 + __ffs(hits) - 1;
+        const int kl = __ffs(hits) - 1;
+        const int kk = k0 + kl;
         hits &= hits - 1;
         const float4 g = gt_box(A, ig, kk);
+        const float cm = __shfl_sync(0xffffffffu, cmk, kl);
         bool hit = false;
         float ov = 0.f;
-        if (W.active) ov = pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g.x, g.y, g.z, g.w,
-                                    box_area(g.x, g.y, g.z, g.w), hit);
-        const float cm = __uint_as_float(__ldg(A.colmax + ig.slot0 + kk));
-        if (MINING) {
-          // stage 2 tie band, small_mining_match.cc:171,179; ascending GT index => the last GT wins
-          if (fabsf(fsub(ov, cm)) < FLT_EPSILON) { s.owner = kk; s.owner_ov = ov; }
-        } else {
-          // anchor_manipulator.py:88 exact equality with the column maximum
-          const bool claimable = !need_haspos || __ldg(A.haspos + ig.slot0 + kk) == 0;
-          if (claimable && ov == cm) {
-            s.claimed = true;
-            if (ov > s.cbest) { s.cbest = ov; s.cbest_gt = kk; }
-          }
-        }
+        if (active) ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, g.x, g.y, g.z, g.w, box_area(g.x, g.y, g.z, g.w), hit);
+        const bool claimable = !need_haspos || A.haspos[ig.slot0 + kk] == 0;
+        row_update<MINING>(s, kk, ov, cm, claimable);
       }
     }
+    if (!valid) continue;
+    const int match1 = stage1_match<MINING>(A, s.best, s.best_gt);
+    int match = match1;
+    float score = s.best;
     if (MINING) {
-      // stage 1, small_mining_match.cc:85-93
-      if (s.best >= A.neg_low && s.best < A.low) match = -1;
-      else if (s.best >= A.high) match = s.best_gt;
-      else match = -2;
-      score = s.best;
-      // stage 2, :178-186
-      if (s.owner >= 0) { match = s.owner; score = s.owner_ov; }
-      if (W.valid && match >= 0) atomicAdd(A.cnt + ig.slot0 + match, 1);
-    } else {
-      // anchor_manipulator.py:67-76
-      const bool less = s.best < A.low;
-      const bool between = (s.best < A.high) && (s.best >= A.low);
-      const bool neg = A.ignore_between ? less : between;
-      const bool ign = A.ignore_between ? between : less;
-      match = s.best_gt;
-      if (neg) match = -1;
-      if (ign) match = -2;
-      score = s.best;
-      // :95-104 GT-side claim has priority; argmax over (overlap * claim mask)
-      if (s.claimed) {
-        if (s.cbest > 0.f) {
-          match = s.cbest_gt;
-          score = s.cbest;
-        } else {
-          // claimed only through zero-overlap ties: argmax of an all-zero row is GT 0, the score is its overlap
-          const float4 g0 = gt_box(A, ig, 0);
-          bool hit0 = false;
-          match = 0;
-          score = W.active ? pair_iou(W.ab.my0, W.ab.mx0, W.ab.my1, W.ab.mx1, W.ab.marea, g0.x, g0.y, g0.z, g0.w,
-                                      box_area(g0.x, g0.y, g0.z, g0.w), hit0) : 0.f;
-        }
+      if (s.owner >= 0) { match = s.owner; score = s.owner_ov; }     // stage 2, :178-186 (the last tied GT wins)
+      if (match != match1) {
+        if (match1 >= 0) atomicSub(A.cnt + ig.slot0 + match1, 1);
+        atomicAdd(A.cnt + ig.slot0 + match, 1);
       }
+    } else if (s.claimed) {
+      // :95-104 GT-side claim has priority; argmax over (overlap * claim mask); claimed only through zero-overlap
+      // ties: the argmax of an all-zero row is GT 0, the score is its overlap
+      if (s.cbest > 0.f) { match = s.cbest_gt; score = s.cbest; }
+      else { match = 0; score = s.ov0; }
     }
-    if (W.valid) {
-      const int64_t row = (int64_t)b * A.n + W.a;
-      if (match >= 0) {
-        write_positive(A, row, W.ab, gt_box(A, ig, match), score, match);
-      } else {
-        // streaming stores: the 44 B/anchor of a step are written once and not read again by this kernel
-        __stcs(A.targets + row, make_float4(0.f, 0.f, 0.f, 0.f));
-        __stcs(reinterpret_cast<long long*>(A.labels) + row, (long long)((match < -1) ? -1 : 0));   // anchor_manipulator.py:300-302
-        __stcs(A.scores + row, score);
-        if (A.matched != nullptr) __stcs(A.matched + row, make_float4(0.f, 0.f, 0.f, 0.f));
-        if (A.match32 != nullptr) __stcs(A.match32 + row, match);
-      }
-    }
+    if (match != match1 || score != s.best)
+      write_positive(A, (int64_t)b * A.n + a, ab, gt_box(A, ig, match), score, match);
   }
 }
 
 // ---------------------------------------------------------------------------
 // pass 3: stage 3 "hard face compensation", small_mining_match.cc:199-222.
-// One warp per image, GTs in ascending order.
+//
+// The reference walks the GTs in ascending order; a GT j that is short of min_match takes its best still-unmatched
+// anchors with overlap > stop_positive_thres, so GT j sees what the GTs before it took.  That order dependence only
+// exists between GTs that share a candidate anchor.  One CTA per image; the needy GTs are handled in WINDOWS of up to
+// kP3Window consecutive needy GTs, a warp per GT:
+//     sel_j = the `need_j` best candidates of j that are not selected by a needy GT before j
+// is iterated from "nothing is blocked" until no GT's blocked set changes.  The lowest GT of the window is never
+// blocked, so it is final after the first round, the next one after the second, ...: the fixed point is unique and is
+// the reference's sequential result; the number of rounds is the longest chain of GTs that actually compete for an
+// anchor (faces are mostly disjoint: two rounds, the second only confirms).  The selections of a window are then
+// written to the outputs (by all warps) before the next window loads its candidates, which see them as matched.
+// A GT whose candidate bucket overflowed (more than kBucketCap anchors above the stop threshold) is handled alone,
+// by a rescan of all anchors of the image in index order, exactly like the reference's loop.
+// Equal overlaps: pop order of a max-heap == descending key; only a tie that straddles the min_match cut depends
+// on libstdc++'s heap layout, which is then reproduced exactly (heap_order.cuh).
 // ---------------------------------------------------------------------------
 template <bool DENSE>
 DAN_D bool still_unmatched(const EncArgs& A, int64_t row) {
@@ -711,105 +780,106 @@ DAN_D void apply_compensation(const EncArgs& A, const ImageGt& ig, int b, int a,
   }
 }
 
-constexpr int kP3Threads = 128;
-constexpr int kP3Group = 16;        // buckets staged in shared memory at a time
-constexpr int kHashSlots = 4096;    // anchors taken by stage 3 of this image (open addressing)
-constexpr int kApplyCap = 1024;     // deferred output patches
+constexpr int kP3Threads = 512;
+constexpr int kP3Warps = kP3Threads / 32;
+constexpr int kP3Range = 1024;      // GTs scanned for neediness at a time
+constexpr int kP3Window = 64;       // needy GTs resolved together
+constexpr int kP3SelCap = 1024;     // selections of a window (half the hash table)
+constexpr int kP3Hash = 2048;       // anchors selected in the current round -> lowest selecting GT (open addressing)
 
-struct TakenSet {
-  int* slots;      // [kHashSlots], -1 = empty
-  int* count;
+struct P3Hash {
+  int* key;        // [kP3Hash], -1 = empty
+  int* val;        // [kP3Hash]
 };
 
-// Output patches of stage 3 are deferred: the serial walk over the GTs only needs the taken SET (shared memory),
-// so the encode + global stores of each patched anchor run afterwards, in parallel over the whole CTA.
-struct ApplyList {
-  int* a;
-  int* j;
-  float* ov;
-  int* n;
-};
-
-DAN_D bool taken_has(const TakenSet& t, int a) {
-  unsigned h = ((unsigned)a * 2654435761u) & (kHashSlots - 1);
+DAN_D void p3_hash_put(const P3Hash& h, int a, int q) {
+  unsigned i = ((unsigned)a * 2654435761u) & (kP3Hash - 1);
   while (true) {
-    const int v = t.slots[h];
-    if (v == a) return true;
-    if (v < 0) return false;
-    h = (h + 1) & (kHashSlots - 1);
-  }
-}
-
-DAN_D void taken_add(const TakenSet& t, int a) {
-  unsigned h = ((unsigned)a * 2654435761u) & (kHashSlots - 1);
-  while (true) {
-    const int old = atomicCAS(&t.slots[h], -1, a);
-    if (old < 0 || old == a) break;
-    h = (h + 1) & (kHashSlots - 1);
-  }
-  atomicAdd(t.count, 1);
-}
-
-// Select the `need` best of the c entries of `list` (key <= 0 entries are dead) for GT j and apply them.
-// Pop order of a max-heap == descending key; only a tie that straddles the cut depends on libstdc++'s heap
-// layout, which is then reproduced exactly (heap_order.cuh).  Executed by one full warp.
-template <bool DENSE>
-DAN_D void flush_applies(const EncArgs& A, const ImageGt& ig, int b, const ApplyList& al, int first, int step) {
-  const int n = min(*al.n, kApplyCap);
-  for (int e = first; e < n; e += step) apply_compensation<DENSE>(A, ig, b, al.a[e], al.j[e], al.ov[e]);
-}
-
-template <bool DENSE>
-DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int j, int need, HeapItem* list, int c,
-                                bool ordered, HeapItem* sort_buf, HeapItem* heap, const TakenSet& taken, bool use_hash,
-                                const ApplyList& al, bool defer) {
-  const int lane = threadIdx.x & 31;
-  int live = 0;
-  for (int e = lane; e < c; e += 32) live += (list[e].key > 0.f) ? 1 : 0;
-  live = __reduce_add_sync(0xffffffffu, live);
-  auto apply = [&](int a, float ov) {
-    if (use_hash) taken_add(taken, a);
-    if (defer) {
-      const int slot = atomicAdd(al.n, 1);
-      if (slot < kApplyCap) {
-        al.a[slot] = a;
-        al.j[slot] = j;
-        al.ov[slot] = ov;
-        return;
-      }
+    const int old = atomicCAS(&h.key[i], -1, a);
+    if (old < 0 || old == a) {
+      atomicMin(&h.val[i], q);
+      return;
     }
-    apply_compensation<DENSE>(A, ig, b, a, j, ov);
-  };
-  if (live <= need) {
-    for (int e = lane; e < c; e += 32)
-      if (list[e].key > 0.f) apply(list[e].id, list[e].key);
+    i = (i + 1) & (kP3Hash - 1);
+  }
+}
+
+// lowest needy GT (window position) that selected anchor a in the last round, INT_MAX if none
+DAN_D int p3_hash_get(const P3Hash& h, int a) {
+  unsigned i = ((unsigned)a * 2654435761u) & (kP3Hash - 1);
+  while (true) {
+    const int k = h.key[i];
+    if (k == a) return h.val[i];
+    if (k < 0) return 0x7fffffff;
+    i = (i + 1) & (kP3Hash - 1);
+  }
+}
+
+// The `need` best of the c <= kBucketCap entries of `list` whose bit is set in `live`, as a bit mask over the entries.
+// Executed by one full warp; sort_buf / heap: kBucketCap entries of scratch each (only used when a tie straddles the cut).
+DAN_D unsigned long long select_from_bucket(const HeapItem* list, int c, unsigned long long live, int need, HeapItem* sort_buf,
+                                            HeapItem* heap, unsigned char* sort_slot) {
+  const int lane = threadIdx.x & 31;
+  if (__popcll(live) <= need) return live;
+  // one ranking pass: entry e is popped before the cut iff its whole tie group fits (ge <= need), after the cut iff
+  // g >= need; a tie group with g < need < ge straddles the cut
+  const bool l0 = (live >> lane) & 1ull, l1 = (live >> (lane + 32)) & 1ull;
+  const float k0 = l0 ? list[lane].key : 0.f;
+  const float k1 = l1 ? list[lane + 32].key : 0.f;
+  int g0 = 0, ge0 = 0, g1 = 0, ge1 = 0;
+  for (int e = 0; e < c; ++e) {
+    if ((live >> e) & 1ull) {                              // warp-uniform
+      const float v = list[e].key;
+      g0 += (v > k0) ? 1 : 0;
+      ge0 += (v >= k0) ? 1 : 0;
+      g1 += (v > k1) ? 1 : 0;
+      ge1 += (v >= k1) ? 1 : 0;
+    }
+  }
+  const bool st = (l0 && g0 < need && ge0 > need) || (l1 && g1 < need && ge1 > need);
+  if (!__any_sync(0xffffffffu, st)) {
+    const unsigned lo = __ballot_sync(0xffffffffu, l0 && ge0 <= need);
+    const unsigned hi = __ballot_sync(0xffffffffu, l1 && ge1 <= need);
+    return ((unsigned long long)hi << 32) | lo;
+  }
+  // The exact path: every live entry is a member of the reference's heap, pushed in ascending anchor order
+  // (small_mining_match.cc:204-209).  The bucket is unordered: each lane ranks its two entries by anchor index.
+  const int id0 = l0 ? list[lane].id : 0x7fffffff, id1 = l1 ? list[lane + 32].id : 0x7fffffff;
+  int r0 = 0, r1 = 0;
+  for (int f = 0; f < c; ++f) {
+    if ((live >> f) & 1ull) {
+      const int idf = list[f].id;
+      r0 += (idf < id0) ? 1 : 0;
+      r1 += (idf < id1) ? 1 : 0;
+    }
+  }
+  if (l0) { sort_buf[r0] = HeapItem{k0, id0}; sort_slot[r0] = (unsigned char)lane; }
+  if (l1) { sort_buf[r1] = HeapItem{k1, id1}; sort_slot[r1] = (unsigned char)(lane + 32); }
+  __syncwarp();
+  unsigned long long sel = 0ull;
+  if (lane == 0) {
+    // HeapItem.id carries the position in sort_buf so that the popped items can be mapped back to bucket entries
+    const int n = __popcll(live);
+    int len = 0;
+    for (int e = 0; e < n; ++e) heap_push(heap, len, HeapItem{sort_buf[e].key, e});
+    for (int p = 0; p < need && len > 0; ++p) sel |= 1ull << sort_slot[heap_pop(heap, len).id];
+  }
+  __syncwarp();
+  const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)sel, 0), hi = __shfl_sync(0xffffffffu, (unsigned)(sel >> 32), 0);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// Overflowed bucket: all candidates of GT j in anchor order are in `list` (c entries, HBM); take the `need` best and
+// apply them at once.  Executed by one full warp; sort_buf / heap: c entries of HBM scratch each.
+template <bool DENSE>
+DAN_D void compensate_from_spill(const EncArgs& A, const ImageGt& ig, int b, int j, int need, HeapItem* list, int c, HeapItem* heap) {
+  const int lane = threadIdx.x & 31;
+  if (c <= need) {
+    for (int e = lane; e < c; e += 32) apply_compensation<DENSE>(A, ig, b, list[e].id, j, list[e].key);
     return;
   }
   int got = 0;
   bool straddle = false;
-  if (c <= 64) {
-    // one ranking pass: entry e is popped before the cut iff its whole tie group fits (ge <= need), after the
-    // cut iff g >= need; a tie group with g < need < ge straddles the cut
-    const float k0 = (lane < c) ? list[lane].key : 0.f;
-    const float k1 = (lane + 32 < c) ? list[lane + 32].key : 0.f;
-    int g0 = 0, ge0 = 0, g1 = 0, ge1 = 0;
-    for (int e = 0; e < c; ++e) {
-      const float v = list[e].key;
-      if (v > 0.f) {
-        g0 += (v > k0) ? 1 : 0;
-        ge0 += (v >= k0) ? 1 : 0;
-        g1 += (v > k1) ? 1 : 0;
-        ge1 += (v >= k1) ? 1 : 0;
-      }
-    }
-    const bool st = (k0 > 0.f && g0 < need && ge0 > need) || (k1 > 0.f && g1 < need && ge1 > need);
-    straddle = __any_sync(0xffffffffu, st);
-    if (!straddle) {
-      if (k0 > 0.f && ge0 <= need) apply(list[lane].id, k0);
-      if (k1 > 0.f && ge1 <= need) apply(list[lane + 32].id, k1);
-    }
-    got = need;
-  }
   while (got < need) {
     float lmax = 0.f;
     for (int e = lane; e < c; e += 32) lmax = fmaxf(lmax, list[e].key);
@@ -822,7 +892,7 @@ DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int 
     if (got + total > need) { straddle = true; break; }
     for (int e = lane; e < c; e += 32) {
       if (list[e].key == wmax) {
-        apply(list[e].id, wmax);
+        apply_compensation<DENSE>(A, ig, b, list[e].id, j, wmax);
         list[e].key = -wmax;     // taken; the value is kept for the exact path
       }
     }
@@ -831,61 +901,39 @@ DAN_D void compensate_from_list(const EncArgs& A, const ImageGt& ig, int b, int 
   }
   if (straddle) {
     __syncwarp();
-    // The exact path: every live or already taken entry was a member of the reference's heap, pushed in ascending
-    // anchor order (small_mining_match.cc:204-209).  Bucket lists (c <= 64) are unordered: each lane ranks its two
-    // entries by anchor index in parallel; spill lists are already ordered and are compacted by lane 0.
-    int n = 0;
-    if (c <= 64 && !ordered) {
-      const int e0 = lane, e1 = lane + 32;
-      const bool l0 = e0 < c && list[e0].key != 0.f, l1 = e1 < c && list[e1].key != 0.f;
-      const int id0 = l0 ? list[e0].id : 0x7fffffff, id1 = l1 ? list[e1].id : 0x7fffffff;
-      int r0 = 0, r1 = 0;
-      for (int f = 0; f < c; ++f) {
-        const bool lf = list[f].key != 0.f;
-        const int idf = list[f].id;
-        r0 += (lf && idf < id0) ? 1 : 0;
-        r1 += (lf && idf < id1) ? 1 : 0;
-      }
-      if (l0) sort_buf[r0] = HeapItem{fabsf(list[e0].key), id0};
-      if (l1) sort_buf[r1] = HeapItem{fabsf(list[e1].key), id1};
-      n = __popc(__ballot_sync(0xffffffffu, l0)) + __popc(__ballot_sync(0xffffffffu, l1));
-      __syncwarp();
-    } else if (lane == 0) {
-      for (int e = 0; e < c; ++e) {
-        if (list[e].key == 0.f) continue;
-        HeapItem v = list[e];
-        v.key = fabsf(v.key);
-        if (ordered) { sort_buf[n++] = v; continue; }
-        int p = n - 1;
-        while (p >= 0 && sort_buf[p].id > v.id) { sort_buf[p + 1] = sort_buf[p]; --p; }
-        sort_buf[p + 1] = v;
-        ++n;
-      }
-    }
+    // every live or already taken entry was a member of the reference's heap, pushed in ascending anchor order (the
+    // spill list is in that order)
     if (lane == 0) {
       int len = 0;
-      for (int e = 0; e < n; ++e) heap_push(heap, len, sort_buf[e]);
+      for (int e = 0; e < c; ++e) heap_push(heap, len, HeapItem{fabsf(list[e].key), list[e].id});
       for (int p = 0; p < need && len > 0; ++p) {
         const HeapItem it = heap_pop(heap, len);
-        apply(it.id, it.key);     // re-applying an entry taken above is idempotent
+        apply_compensation<DENSE>(A, ig, b, it.id, j, it.key);     // re-applying an entry taken above is idempotent
       }
     }
   }
   __syncwarp();
 }
 
+struct P3Smem {
+  HeapItem cand[kP3Window][kBucketCap];        // candidate buckets of the window (32 KB)
+  HeapItem sort_buf[kP3Warps][kBucketCap];     // per-warp scratch of the exact tie path
+  HeapItem heap[kP3Warps][kBucketCap];
+  unsigned char sort_slot[kP3Warps][kBucketCap];
+  int hash_key[kP3Hash];
+  int hash_val[kP3Hash];
+  unsigned long long alive[kP3Window];         // candidate still unmatched after stage 2 and the earlier windows
+  unsigned long long blocked[kP3Window];       // ... but selected by an earlier GT of the window in the last round
+  unsigned long long sel[kP3Window];
+  int dirty[kP3Window];                        // blocked set changed in the last round: select again
+  int needy_j[kP3Range], needy_need[kP3Range], needy_fill[kP3Range];
+  int warp_cnt[kP3Warps];
+};
+
 template <bool DENSE>
 __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) {
-  __shared__ HeapItem s_group[kP3Group][kBucketCap];
-  __shared__ HeapItem s_sort[kBucketCap];
-  __shared__ HeapItem s_heap[kBucketCap];
-  __shared__ int s_hash[kHashSlots];
-  __shared__ int s_taken_n;
-  __shared__ int s_apply_a[kApplyCap], s_apply_j[kApplyCap];
-  __shared__ float s_apply_ov[kApplyCap];
-  __shared__ int s_apply_n;
-  __shared__ int s_needy_j[kP3Threads], s_needy_need[kP3Threads], s_needy_fill[kP3Threads];
-  __shared__ int s_warp_cnt[kP3Threads / 32];
+  extern __shared__ __align__(16) unsigned char p3_raw[];
+  P3Smem& S = *reinterpret_cast<P3Smem*>(p3_raw);
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -893,116 +941,150 @@ __global__ void __launch_bounds__(kP3Threads) enc_pass3_kernel(const EncArgs A) 
   const int warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const ImageGt ig = image_gt<DENSE>(A, b);
-  TakenSet taken{s_hash, &s_taken_n};
-  ApplyList al{s_apply_a, s_apply_j, s_apply_ov, &s_apply_n};
+  const P3Hash hash{S.hash_key, S.hash_val};
 
-  for (int i = tid; i < kHashSlots; i += kP3Threads) s_hash[i] = -1;
-  if (tid == 0) { s_taken_n = 0; s_apply_n = 0; }
-  __syncthreads();
-
-  for (int j0 = 0; j0 < ig.m_eff; j0 += kP3Threads) {
+  for (int j0 = 0; j0 < ig.m_eff; j0 += kP3Range) {
     // ---- GTs of this range that are short of min_match, in ascending order
-    const int j = j0 + tid;
-    int need = 0, fill = 0;
-    if (j < ig.m_eff) {
-      need = A.min_match - A.cnt[ig.slot0 + j];
-      fill = A.fill[ig.slot0 + j];
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, need > 0);
-    if (lane == 0) s_warp_cnt[warp] = __popc(m);
-    __syncthreads();
-    int before = 0, nneedy = 0;
-    for (int w = 0; w < kP3Threads / 32; ++w) {
-      if (w < warp) before += s_warp_cnt[w];
-      nneedy += s_warp_cnt[w];
-    }
-    if (need > 0) {
-      const int pos = before + __popc(m & lt_mask);
-      s_needy_j[pos] = j;
-      s_needy_need[pos] = need;
-      s_needy_fill[pos] = fill;
-    }
-    __syncthreads();
-
-    for (int g0 = 0; g0 < nneedy; g0 += kP3Group) {
-      const int ng = min(kP3Group, nneedy - g0);
-      // ---- stage the group's candidate buckets (all threads, coalesced)
-      for (int e = tid; e < ng * kBucketCap; e += kP3Threads) {
-        const int g = e / kBucketCap, k = e % kBucketCap;
-        const int f = s_needy_fill[g0 + g];
-        if (f <= kBucketCap && k < f) {
-          HeapItem it = A.bucket[(int64_t)(ig.slot0 + s_needy_j[g0 + g]) * kBucketCap + k];
-          // buckets hold every anchor with overlap > stop; only those still unmatched after stage 2 (and after the
-          // patches of the previous groups, already in HBM) are candidates
-          if (!still_unmatched<DENSE>(A, (int64_t)b * A.n + it.id)) it.key = 0.f;
-          s_group[g][k] = it;
-        }
+    int nneedy = 0;
+    for (int jb = 0; jb < kP3Range && j0 + jb < ig.m_eff; jb += kP3Threads) {
+      const int j = j0 + jb + tid;
+      int need = 0, fill = 0;
+      if (j < ig.m_eff) {
+        need = A.min_match - A.cnt[ig.slot0 + j];
+        fill = A.fill[ig.slot0 + j];
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, need > 0);
+      if (lane == 0) S.warp_cnt[warp] = __popc(m);
+      __syncthreads();
+      int before = nneedy;
+      for (int w = 0; w < kP3Warps; ++w) {
+        if (w < warp) before += S.warp_cnt[w];
+        nneedy += S.warp_cnt[w];
+      }
+      if (need > 0) {
+        const int pos = before + __popc(m & lt_mask);
+        S.needy_j[pos] = j;
+        S.needy_need[pos] = need;
+        S.needy_fill[pos] = fill;
       }
       __syncthreads();
-      // ---- the stage is order dependent: warp 0 walks the GTs in ascending order
-      if (warp == 0) {
-        for (int g = 0; g < ng; ++g) {
-          const int gj = s_needy_j[g0 + g];
-          const int gneed = s_needy_need[g0 + g];
-          const int gfill = s_needy_fill[g0 + g];
-          const bool use_hash = s_taken_n < kHashSlots / 2;
-          if (!use_hash || gfill > kBucketCap) {
-            // this GT reads the labels in HBM as the truth: write the pending patches first
-            flush_applies<DENSE>(A, ig, b, al, lane, 32);
-            __syncwarp();
-            if (lane == 0) s_apply_n = 0;
-            __threadfence_block();
-            __syncwarp();
-          }
-          if (gfill <= kBucketCap) {
-            HeapItem* list = s_group[g];
-            for (int e = lane; e < gfill; e += 32) {
-              const int a = list[e].id;
-              const bool dead = use_hash ? taken_has(taken, a) : !still_unmatched<DENSE>(A, (int64_t)b * A.n + a);
-              if (dead) list[e].key = 0.f;
-            }
-            __syncwarp();
-            // patches can be deferred as long as the taken set is tracked in shared memory
-            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, gfill, false, s_sort, s_heap, taken, use_hash, al, use_hash);
-          } else {
-            // bucket overflowed: rescan every anchor of the image in index order (patches are immediate here)
-            HeapItem* list = A.spill + (int64_t)b * 3 * A.n;
-            int c = 0;
-            const float4 gb = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : gt_box(A, ig, gj);
-            const float garea = box_area(gb.x, gb.y, gb.z, gb.w);
-            for (int a0 = 0; a0 < A.n; a0 += 32) {
-              const int a = a0 + lane;
-              bool ok = false;
-              float ov = 0.f;
-              if (a < A.n) {
-                if (DENSE) {
-                  ov = A.overlaps[(int64_t)a * ig.m_eff + gj];
-                } else if (A.mask == nullptr || A.mask[a] != 0) {
-                  const AnchorBox ab = load_anchor(A, a);
-                  bool hit;
-                  ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, gb.x, gb.y, gb.z, gb.w, garea, hit);
-                }
-                ok = (ov > A.stop) && still_unmatched<DENSE>(A, (int64_t)b * A.n + a);
+    }
+
+    int q0 = 0;
+    while (q0 < nneedy) {                                    // (all decisions below are CTA-uniform)
+      if (S.needy_fill[q0] > kBucketCap) {
+        // ---- bucket overflowed: rescan every anchor of the image in index order; everything before this GT is already
+        // in the outputs, the GT is alone in its "window", and its patches are applied at once (warp 0)
+        if (warp == 0) {
+          const int gj = S.needy_j[q0];
+          HeapItem* list = A.spill + (int64_t)b * 2 * A.n;
+          int c = 0;
+          const float4 gb = DENSE ? make_float4(0.f, 0.f, 0.f, 0.f) : gt_box(A, ig, gj);
+          const float garea = box_area(gb.x, gb.y, gb.z, gb.w);
+          for (int a0 = 0; a0 < A.n; a0 += 32) {
+            const int a = a0 + lane;
+            bool ok = false;
+            float ov = 0.f;
+            if (a < A.n) {
+              if (DENSE) {
+                ov = A.overlaps[(int64_t)a * ig.m_eff + gj];
+              } else if (A.mask == nullptr || A.mask[a] != 0) {
+                const AnchorBox ab = load_anchor(A, a);
+                bool hit;
+                ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, gb.x, gb.y, gb.z, gb.w, garea, hit);
               }
-              const unsigned mm = __ballot_sync(0xffffffffu, ok);
-              if (ok) list[c + __popc(mm & lt_mask)] = HeapItem{ov, a};
-              c += __popc(mm);
+              ok = (ov > A.stop) && still_unmatched<DENSE>(A, (int64_t)b * A.n + a);
             }
-            __threadfence_block();
-            __syncwarp();
-            compensate_from_list<DENSE>(A, ig, b, gj, gneed, list, c, true, list + A.n, list + 2 * (int64_t)A.n, taken, use_hash,
-                                        al, false);
+            const unsigned mm = __ballot_sync(0xffffffffu, ok);
+            if (ok) list[c + __popc(mm & lt_mask)] = HeapItem{ov, a};
+            c += __popc(mm);
           }
           __threadfence_block();
           __syncwarp();
+          compensate_from_spill<DENSE>(A, ig, b, gj, S.needy_need[q0], list, c, list + A.n);
+        }
+        __syncthreads();
+        q0 += 1;
+        continue;
+      }
+      // ---- window [q0, q1): consecutive needy GTs with intact buckets, at most kP3SelCap selections in total
+      int q1 = q0, budget = 0;
+      while (q1 < nneedy && q1 - q0 < kP3Window && S.needy_fill[q1] <= kBucketCap) {
+        const int take = min(S.needy_need[q1], S.needy_fill[q1]);
+        if (q1 > q0 && budget + take > kP3SelCap) break;
+        budget += take;
+        ++q1;
+      }
+      const int nq = q1 - q0;
+      // candidates still unmatched after stage 2 and after the windows before this one (already in HBM)
+      for (int g = warp; g < nq; g += kP3Warps) {
+        const int gj = S.needy_j[q0 + g], gfill = S.needy_fill[q0 + g];
+        bool a0 = false, a1 = false;
+        if (lane < gfill) {
+          const HeapItem it = A.bucket[(int64_t)(ig.slot0 + gj) * kBucketCap + lane];
+          S.cand[g][lane] = it;
+          a0 = still_unmatched<DENSE>(A, (int64_t)b * A.n + it.id);
+        }
+        if (lane + 32 < gfill) {
+          const HeapItem it = A.bucket[(int64_t)(ig.slot0 + gj) * kBucketCap + lane + 32];
+          S.cand[g][lane + 32] = it;
+          a1 = still_unmatched<DENSE>(A, (int64_t)b * A.n + it.id);
+        }
+        const unsigned lo = __ballot_sync(0xffffffffu, a0), hi = __ballot_sync(0xffffffffu, a1);
+        if (lane == 0) {
+          S.alive[g] = ((unsigned long long)hi << 32) | lo;
+          S.blocked[g] = 0ull;
+          S.dirty[g] = 1;
         }
       }
       __syncthreads();
-      // ---- deferred output patches of the group, all threads
-      flush_applies<DENSE>(A, ig, b, al, tid, kP3Threads);
+      // ---- rounds
+      while (true) {
+        // selections under the current blocked sets (a GT whose blocked set did not change keeps its selection)
+        for (int g = warp; g < nq; g += kP3Warps) {
+          if (S.dirty[g] == 0) continue;                        // (warp-uniform: written by this warp in the last round)
+          const unsigned long long live = S.alive[g] & ~S.blocked[g];
+          const unsigned long long sel = select_from_bucket(S.cand[g], S.needy_fill[q0 + g], live, S.needy_need[q0 + g],
+                                                            S.sort_buf[warp], S.heap[warp], S.sort_slot[warp]);
+          if (lane == 0) S.sel[g] = sel;
+        }
+        for (int i = tid; i < kP3Hash; i += kP3Threads) { S.hash_key[i] = -1; S.hash_val[i] = 0x7fffffff; }
+        __syncthreads();
+        if (nq == 1) break;                                     // a lone GT has nobody to compete with
+        for (int g = warp; g < nq; g += kP3Warps) {
+          const unsigned long long sel = S.sel[g];
+          if ((sel >> lane) & 1ull) p3_hash_put(hash, S.cand[g][lane].id, g);
+          if ((sel >> (lane + 32)) & 1ull) p3_hash_put(hash, S.cand[g][lane + 32].id, g);
+        }
+        __syncthreads();
+        bool changed = false;
+        for (int g = warp; g < nq; g += kP3Warps) {
+          const unsigned long long alive = S.alive[g];
+          const bool b0 = ((alive >> lane) & 1ull) && p3_hash_get(hash, S.cand[g][lane].id) < g;
+          const bool b1 = ((alive >> (lane + 32)) & 1ull) && p3_hash_get(hash, S.cand[g][lane + 32].id) < g;
+          const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
+          const unsigned long long blocked = ((unsigned long long)hi << 32) | lo;
+          const bool diff = blocked != S.blocked[g];
+          changed |= diff;
+          __syncwarp();
+          if (lane == 0) {
+            S.blocked[g] = blocked;
+            S.dirty[g] = diff ? 1 : 0;
+          }
+        }
+        if (!__syncthreads_or(changed ? 1 : 0)) break;
+      }
+      // ---- the window's selections go to the outputs
+      for (int g = warp; g < nq; g += kP3Warps) {
+        const unsigned long long sel = S.sel[g];
+        const int gj = S.needy_j[q0 + g];
+        if ((sel >> lane) & 1ull) apply_compensation<DENSE>(A, ig, b, S.cand[g][lane].id, gj, S.cand[g][lane].key);
+        if ((sel >> (lane + 32)) & 1ull) apply_compensation<DENSE>(A, ig, b, S.cand[g][lane + 32].id, gj, S.cand[g][lane + 32].key);
+      }
       __syncthreads();
-      if (tid == 0) s_apply_n = 0;
+      q0 = q1;
     }
+    __syncthreads();
   }
 }
 
@@ -1019,7 +1101,7 @@ __global__ void fill_empty_match_kernel(int32_t* match, float* scores, int n) {
 // host side
 // ---------------------------------------------------------------------------
 struct WsLayout {
-  size_t colmax, cnt, haspos, fill, zero_bytes, bucket, spill, rowbest, rowgt, total;
+  size_t colmax, cnt, haspos, fill, zero_bytes, bucket, spill, wbest, total;
 };
 
 static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
@@ -1031,9 +1113,8 @@ static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
   w.fill = off;   off += align_up(slots * 4, 256);
   w.zero_bytes = off;
   w.bucket = off; off += align_up(slots * kBucketCap * sizeof(HeapItem), 256);
-  w.spill = off;  off += align_up(batch * 3 * n * sizeof(HeapItem), 256);
-  w.rowbest = off; off += align_up(batch * n * 4, 256);
-  w.rowgt = off;   off += align_up(batch * n * 4, 256);
+  w.spill = off;  off += align_up(batch * 2 * n * sizeof(HeapItem), 256);
+  w.wbest = off;  off += align_up(batch * ((n + 31) / 32) * 4, 256);
   w.total = off;
   return w;
 }
@@ -1057,8 +1138,7 @@ static void bind_workspace(EncArgs& A, void* workspace, const WsLayout& w) {
   A.fill = reinterpret_cast<int32_t*>(base + w.fill);
   A.bucket = reinterpret_cast<HeapItem*>(base + w.bucket);
   A.spill = reinterpret_cast<HeapItem*>(base + w.spill);
-  A.rowbest = reinterpret_cast<float*>(base + w.rowbest);
-  A.rowgt = reinterpret_cast<int32_t*>(base + w.rowgt);
+  A.wbest = reinterpret_cast<float*>(base + w.wbest);
 }
 
 // ev (optional, 4 events): recorded before pass 1 and after each pass, for the profile entry point
@@ -1085,13 +1165,16 @@ static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, c
     if (mining) enc_pass2_kernel<true, true><<<grid, kEncThreads, 0, st>>>(A);
     else enc_pass2_kernel<true, false><<<grid, kEncThreads, 0, st>>>(A);
   } else {
-    if (mining) enc_pass2_fused_kernel<true><<<fgrid, fthreads, 0, st>>>(A, batch, ipw);
-    else enc_pass2_fused_kernel<false><<<fgrid, fthreads, 0, st>>>(A, batch, ipw);
+    const dim3 pgrid(batch, ((A.n + 31) / 32 + kPatchThreads - 1) / kPatchThreads);
+    if (mining) enc_pass2_patch_kernel<true><<<pgrid, kPatchThreads, 0, st>>>(A);
+    else enc_pass2_patch_kernel<false><<<pgrid, kPatchThreads, 0, st>>>(A);
   }
   DAN_LAUNCH_CHECK("enc_pass2_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
   if (mining) {
-    enc_pass3_kernel<DENSE><<<batch, kP3Threads, 0, st>>>(A);
+    // (the attribute belongs to the (function, device) pair: set on every call, like the other big-smem kernels)
+    DAN_CUDA(cudaFuncSetAttribute(enc_pass3_kernel<DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P3Smem)));
+    enc_pass3_kernel<DENSE><<<batch, kP3Threads, sizeof(P3Smem), st>>>(A);
     DAN_LAUNCH_CHECK("enc_pass3_kernel");
   }
   if (ev) DAN_CUDA(cudaEventRecord(ev[3], st));

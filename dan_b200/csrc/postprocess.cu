@@ -1,7 +1,8 @@
 // K3-K5: the evaluation half of the path -- utility/bbox_util.py:103-119
 // parse_by_class and its pieces, batched over images and classes.
 //
-//   pp_filter_kernel   softmax -> select(threshold) -> decode -> clip -> min-size;
+//   pp_filter2_kernel  (two classes) / pp_filter_kernel (any number of classes)
+//                      softmax -> select(threshold) -> decode -> clip -> min-size;
 //                      survivors are COMPACTED as 64-bit keys
 //                      (ordered score bits << 32 | ~anchor index).  The reference
 //                      instead multiplies by 0/1 masks and keeps all N rows
@@ -10,15 +11,10 @@
 //   topk_sort_kernel   sort_bboxes alone (bbox_util.py:61-72): block radix select of the keep_topk largest keys
 //                      when more survive, then the bitonic sort of sort.cuh.  Keys are unique, descending key
 //                      order == descending score with ties broken by LOWER index, which is tf.nn.top_k's order.
-//   pp_sort_kernel     per (image, class): the same top-k + sort, then decode of the survivors and the broad phase of
-//                      the NMS: boxes binned by size class (power of two of the longer side) and centre cell.
-//   nms_pairs_kernel   narrow phase: tf.image.non_max_suppression's IoU test (no +1, corners min/max-normalised,
-//                      strict >, area <= 0 never suppresses) only for boxes whose grid windows meet -> a sparse list
-//                      of suppression EDGES (lower rank, higher rank).
-//   nms_resolve_kernel greedy NMS as a relaxation over the edges (kept(i) = no kept lower-ranked neighbour; the depth
-//                      of the dependency chains is a handful of sweeps), ordered compaction, zero padded outputs
-//                      (bbox_util.py:80-90).  Lists with too many edges, a negative threshold or more candidates
-//                      than the pair kernel can stage fall back to rounds of 64 candidates against the kept list.
+//   nms_greedy_kernel  per (image, class): the same top-k + sort, decode of the survivors, and
+//                      tf.image.non_max_suppression (no +1, corners min/max-normalised, strict >, area <= 0 never
+//                      suppresses) as a chunked greedy sweep against the kept list, then the zero padded outputs
+//                      (bbox_util.py:80-90).  One launch, one CTA per list.
 #include <math.h>
 #include <stdlib.h>
 
@@ -52,29 +48,24 @@ struct PpArgs {
   float reject_below;         // 2 classes: logit difference below which softmax <= threshold for sure (-inf: off)
   float ps0, ps1, ps2, ps3;
   int keep_topk, nms_topk;
-  int nms_cap;                // kept-list capacity in shared memory = min(nms_topk, keep_topk)
+  int nms_cap;                // kept-list capacity = min(nms_topk, keep_topk)
   float nms_thr;
-  int force_rounds;           // 1: the pair kernel's staging does not fit shared memory -> round-based NMS for every list
+  // shared-memory plan of the NMS kernel (greedy_plan)
+  int sort_bytes, kcap, wcap, cand_global, kept_global;
   // workspace
   unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
   int32_t* key_count;         // [L]
   float* s_scores;            // sort_bboxes outputs [keep_topk]
   float4* s_boxes;
   int32_t* s_index;
-  // per list, written by the sort kernel, read by the pair and resolve kernels (all L2 resident)
   unsigned long long* s_key;  // [L, keep_topk] sorted keys
-  float4* s_box;              // [L, keep_topk] normalised corners (y0, x0, y1, x1), rank order
+  float4* s_box;              // [L, keep_topk] normalised corners (y0, x0, y1, x1), rank order (lists too long for shared memory)
   float* s_area;              // [L, keep_topk] (y1-y0)*(x1-x0)
-  int32_t* s_len;             // [L] number of sorted candidates K
-  float4* grid_info;          // [L] (origin y, origin x, extent, bit mask of the non-empty size classes)
-  float* class_amin;          // [L, 16] smallest box area per size class (IoU <= area ratio: whole classes are skipped)
-  uint16_t* box_cell;         // [L, keep_topk] flattened (class, cy, cx) of each box, 0xffff = not binned
-  uint16_t* box_pos;          // [L, keep_topk] position of each box inside cell_items
-  uint16_t* cell_start;       // [L, kCellStride] (kTotalCells + 1 entries used; the stride keeps every list 16-byte aligned)
-  uint16_t* cell_items;       // [L, keep_topk] ranks grouped by cell
-  uint32_t* edges;            // [L, kEdgeCap] (hi << 16 | lo): lo suppresses hi when lo is kept
-  int32_t* edge_n;            // [L]
-  int32_t* ovf;               // [L] edge list overflow / negative threshold -> round-based fallback
+  float4* g_kept_box;         // [L, keep_topk] kept list of the NMS when it does not fit shared memory
+  float* g_kept_area;
+  int32_t* g_kept_rank;
+  uint2* s_mask;              // [L, keep_topk] stripe masks of the candidates
+  uint32_t* g_stripes;        // [L, 64, ceil(keep_topk / 32)] stripe bitsets of the kept list
   // outputs
   float4* out_boxes;
   float* out_scores;
@@ -323,186 +314,149 @@ DAN_D bool pair_suppresses(const float4& a, float a_area, const float4& b, float
   return fdiv(inter, uni) > thr;
 }
 
-constexpr int kNmsClasses = 10;                                    // class 9: max side >= 512, one cell
-constexpr int kGridDim = 32;                                       // cells per dimension and class
-constexpr int kCellsPerClass = kGridDim * kGridDim;
-constexpr int kTotalCells = kNmsClasses * kCellsPerClass;
-constexpr int kCellStride = (kTotalCells + 1 + 7) / 8 * 8;      // uint16 entries per list, a multiple of 16 bytes
-constexpr int kEdgeCap = 1 << 18;                                  // suppression edges per list (1 MB)
+// ---------------------------------------------------------------------------
+// K3 for two classes (one list per image): the logits of the whole batch are ONE flat array of (background, face)
+// pairs.  Every lane streams 16-byte vectors (two anchors) with kF2Vec loads in flight, rejects on the logit
+// difference alone, and only the ~3 % possible survivors of the CTA are collected in shared memory and run through
+// the exact path (softmax in tf.nn.softmax's op order, threshold, decode, clip, min-size) on dense warps.
+// ---------------------------------------------------------------------------
+constexpr int kF2Threads = 256;
+constexpr int kF2Vec = 4;                                  // 16-byte loads per thread = 8 anchors
 
-// geometry of the per-class grids of one list
-struct GridGeom {
-  float oy, ox, extent;
-  // cell = half the class's largest side (a window of <= 6x6 cells then covers box + reach tightly), but never
-  // more than kGridDim cells per dimension
-  DAN_D float cell_size(int c) const { return fmaxf((float)(1 << c), extent * (1.f / (kGridDim - 1))); }
-  DAN_D static int cell_of(float v, float org, float inv) {
-    const int q = (int)((v - org) * inv);
-    return min(max(q, 0), kGridDim - 1);
-  }
-};
-
-// shared memory of the resolve kernel
-struct NmsSmem {
-  float4* kept_box;      // [nms_cap]   (fallback)
-  float* kept_area;      // [nms_cap]   (fallback)
-  float4* cand_box;      // [keep_topk] (fallback)
-  float* cand_area;      // [keep_topk] (fallback)
-  uint8_t* status;       // [keep_topk] 0 undecided, 1 kept, 2 suppressed
-  uint8_t* pending;      // [keep_topk]
-  int32_t* kept_pos;     // [nms_cap]
-};
-
-static size_t nms_smem_bytes(int nms_cap, int keep_topk) {
-  return (size_t)nms_cap * 20 + (size_t)keep_topk * 20 + align_up((size_t)keep_topk, 16) * 2 + align_up((size_t)nms_cap * 4, 16);
-}
-constexpr size_t kNmsSmemMax = 227 * 1024 - 6 * 1024;   // dynamic part; a few KB of static shared memory on top
-constexpr size_t kSortSmem = (size_t)kSortCap * 8 > (size_t)kTotalCells * 4 ? (size_t)kSortCap * 8 : (size_t)kTotalCells * 4;   // sort kernel: keys, then (aliased) the cell counters
-
-DAN_D NmsSmem nms_carve(unsigned char* base, int nms_cap, int keep_topk) {
-  NmsSmem m;
-  unsigned char* p = base;
-  m.kept_box = reinterpret_cast<float4*>(p); p += (size_t)nms_cap * 16;
-  m.cand_box = reinterpret_cast<float4*>(p); p += (size_t)keep_topk * 16;
-  m.kept_area = reinterpret_cast<float*>(p); p += (size_t)nms_cap * 4;
-  m.cand_area = reinterpret_cast<float*>(p); p += (size_t)keep_topk * 4;
-  m.status = p; p += ((size_t)keep_topk + 15) / 16 * 16;
-  m.pending = p; p += ((size_t)keep_topk + 15) / 16 * 16;
-  m.kept_pos = reinterpret_cast<int32_t*>(p);
-  return m;
+DAN_D bool f2_maybe(const PpArgs& A, float x0, float x1) {
+  return !(fsub(x1, x0) < A.reject_below) || fabsf(x0) > 1e5f || fabsf(x1) > 1e5f;
 }
 
-// ---- fallback: rounds of 64 candidates against the kept list.  In round c:
-//   S1  all warps      suppression bits among the candidates of round c (their flags vs the kept list are final)
-//   S2  warp 0         serial resolve of round c -> appends nk boxes to the kept list
-//       warps 1..30    candidates of round c+1 vs the kept list as it was BEFORE round c
-//   S3  all warps      candidates of round c+1 vs the nk boxes round c just appended
-// Returns the number of kept boxes; their positions are in m.kept_pos.
-DAN_D int nms_rounds(const NmsSmem& m, int K, int nms_topk, float thr) {
-  __shared__ int s_flag[2][64];
-  __shared__ unsigned long long s_rows[64];
-  __shared__ int s_new_n;
+__global__ void __launch_bounds__(kF2Threads) pp_filter2_kernel(const PpArgs A) {
+  __shared__ int s_list[kF2Threads * kF2Vec * 2];
+  __shared__ int s_n;
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int nchunks = (K + 63) >> 6;
-  float4* kept_box = m.kept_box;
-  float* kept_area = m.kept_area;
-  const float4* cand_box = m.cand_box;
-  const float* cand_area = m.cand_area;
-  if (tid < 128) (&s_flag[0][0])[tid] = 0;
-  __syncthreads();
-  int kept_n = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    const int base = c << 6;
-    const int nvalid = min(64, K - base);
-    const int nvalid_next = max(0, min(64, K - base - 64));
-    const float4* cur_box = cand_box + base;
-    const float* cur_area = cand_area + base;
-    const float4* nxt_box = cand_box + base + 64;
-    const float* nxt_area = cand_area + base + 64;
-    const int fb = c & 1, fb1 = fb ^ 1;
-    // ---- S1: warp w -> rows 2w, 2w+1; lane -> cols lane, lane+32
+  const int64_t total = (int64_t)A.batch * A.n;            // anchors of the batch
+  const int64_t vecs = total >> 1;
+  const int64_t v0 = (int64_t)blockIdx.x * (kF2Threads * kF2Vec) + tid;
+  if (tid == 0) s_n = 0;
+  float4 x[kF2Vec];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = 2 * warp + rr;
-      const bool row_ok = (r < nvalid) && (s_flag[fb][r] == 0);
-      const float4 rb = row_ok ? cur_box[r] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float ra = row_ok ? cur_area[r] : 0.f;
-      const int c0 = lane, c1 = lane + 32;
-      const bool t0 = row_ok && c0 > r && c0 < nvalid && nms_suppresses(rb, ra, cur_box[c0], cur_area[c0], thr);
-      const bool t1 = row_ok && c1 > r && c1 < nvalid && nms_suppresses(rb, ra, cur_box[c1], cur_area[c1], thr);
-      const unsigned lo = __ballot_sync(0xffffffffu, t0);
-      const unsigned hi = __ballot_sync(0xffffffffu, t1);
-      if (lane == 0) s_rows[r] = ((unsigned long long)hi << 32) | lo;
-    }
-    __syncthreads();
-    // ---- S2
-    if (warp == 0) {
-      // greedy resolve of the round, 32-bit halves: bit i of cl/ch set <=> candidate i / 32+i is suppressed
-      const unsigned long long d0 = s_rows[lane], d1 = s_rows[lane + 32];
-      const unsigned d0lo = (unsigned)d0, d0hi = (unsigned)(d0 >> 32), d1hi = (unsigned)(d1 >> 32);
-      const unsigned vlo = (nvalid >= 32) ? 0xffffffffu : ((1u << nvalid) - 1u);
-      const unsigned vhi = (nvalid >= 64) ? 0xffffffffu : ((nvalid > 32) ? ((1u << (nvalid - 32)) - 1u) : 0u);
-      unsigned cl = __ballot_sync(0xffffffffu, s_flag[fb][lane] != 0) | ~vlo;
-      unsigned ch = __ballot_sync(0xffffffffu, s_flag[fb][lane + 32] != 0) | ~vhi;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const unsigned rl = __shfl_sync(0xffffffffu, d0lo, i);
-        const unsigned rh = __shfl_sync(0xffffffffu, d0hi, i);
-        const unsigned alive = ((cl >> i) & 1u) - 1u;       // all ones when candidate i survives
-        cl |= rl & alive;
-        ch |= rh & alive;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const unsigned rh = __shfl_sync(0xffffffffu, d1hi, i);
-        const unsigned alive = ((ch >> i) & 1u) - 1u;
-        ch |= rh & alive;
-      }
-      unsigned long long kept = (((unsigned long long)(~ch & vhi)) << 32) | (unsigned long long)(~cl & vlo);
-      int nk = __popcll(kept);
-      if (kept_n + nk > nms_topk) {             // max_output_size reached inside the round
-        int drop = kept_n + nk - nms_topk;
-        while (drop-- > 0) kept &= ~(1ull << (63 - __clzll((long long)kept)));
-        nk = nms_topk - kept_n;
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = lane + 32 * h;
-        if ((kept >> i) & 1ull) {
-          const int pos = kept_n + __popcll(kept & ((1ull << i) - 1ull));
-          kept_box[pos] = cur_box[i];
-          kept_area[pos] = cur_area[i];
-          m.kept_pos[pos] = base + i;
-        }
-      }
-      if (lane == 0) s_new_n = nk;
-      s_flag[fb][lane] = 0;          // this flag buffer is reused by round c+2
-      s_flag[fb][lane + 32] = 0;
-    } else if (warp < 31) {
-      // round c+1 vs kept[0, kept_n): warp w in 1..30 -> candidates 32*((w-1)&1)+lane, slice (w-1)>>1 of 15.
-      // The loop is kept WARP-UNIFORM (uniform trip count, structured ifs): a per-lane continue/break would let
-      // the lanes drift apart for the rest of the loop and multiply the issued instructions.
-      const int i = (((warp - 1) & 1) << 5) | lane;
-      const bool have = i < nvalid_next;
-      const float4 me = have ? nxt_box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float my_area = have ? nxt_area[i] : 0.f;
-      bool done = !(have && my_area > 0.f);
-      bool sup = false;
-      for (int k = kept_n - 1 - ((warp - 1) >> 1); k >= 0; k -= 60) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int kk = k - 15 * u;
-          if (kk >= 0 && !done && pair_suppresses(kept_box[kk], kept_area[kk], me, my_area, thr)) { sup = true; done = true; }
-        }
-        if (__all_sync(0xffffffffu, done)) break;
-      }
-      if (sup) s_flag[fb1][i] = 1;
-    }
-    __syncthreads();
-    // ---- S3: round c+1 vs the boxes appended by round c: thread -> candidate tid&63, new boxes (tid>>6)+16j
-    const int nk = s_new_n;
-    if (nvalid_next > 0 && nk > 0) {
-      const int i = tid & 63;
-      const bool have = i < nvalid_next;
-      const float4 me = have ? nxt_box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float my_area = have ? nxt_area[i] : 0.f;
-      if (have && my_area > 0.f) {
-        bool sup = false;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = (tid >> 6) + 16 * u;
-          if (j < nk && !sup && pair_suppresses(kept_box[kept_n + j], kept_area[kept_n + j], me, my_area, thr)) sup = true;
-        }
-        if (sup) s_flag[fb1][i] = 1;
-      }
-    }
-    kept_n += nk;
-    __syncthreads();
-    if (kept_n >= nms_topk) break;
+  for (int u = 0; u < kF2Vec; ++u) {
+    const int64_t v = v0 + u * kF2Threads;
+    x[u] = (v < vecs) ? __ldcs(reinterpret_cast<const float4*>(A.cls) + v) : make_float4(0.f, 0.f, 0.f, 0.f);   // read once
   }
-  return kept_n;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kF2Vec; ++u) {
+    const int64_t v = v0 + u * kF2Threads;
+    if (v < vecs) {
+      if (f2_maybe(A, x[u].x, x[u].y)) s_list[atomicAdd(&s_n, 1)] = (int)(2 * v);
+      if (f2_maybe(A, x[u].z, x[u].w)) s_list[atomicAdd(&s_n, 1)] = (int)(2 * v + 1);
+    }
+  }
+  if ((total & 1) && blockIdx.x == gridDim.x - 1 && tid == 0) {      // odd tail of the flat array
+    const float x0 = A.cls[2 * (total - 1)], x1 = A.cls[2 * (total - 1) + 1];
+    if (f2_maybe(A, x0, x1)) s_list[atomicAdd(&s_n, 1)] = (int)(total - 1);
+  }
+  __syncthreads();
+  const int cnt = s_n;
+  for (int i0 = 0; i0 < cnt; i0 += kF2Threads) {           // CTA-uniform trip count
+    const int i = i0 + tid;
+    bool pass = false;
+    int b = 0, a = 0;
+    float p = 0.f;
+    if (i < cnt) {
+      const int g = s_list[i];
+      b = g / A.n;
+      a = g - b * A.n;
+      const float2 xx = *reinterpret_cast<const float2*>(A.cls + 2 * (int64_t)g);
+      // tf.nn.softmax: exp(x - max) * (1 / sum(exp(x - max))), sum in class order
+      const float mx = fmaxf(xx.x, xx.y);
+      const float e0 = cephes_expf(fsub(xx.x, mx));
+      const float e1 = cephes_expf(fsub(xx.y, mx));
+      const float inv = fdiv(1.f, fadd(e0, e1));
+      p = fmul(e1, inv);
+      if (p > A.select_thr) {                              // select_bboxes :24-36
+        const float4 box = pp_box(A, b, a);
+        const float w = fadd(fsub(box.w, box.y), 1.f);     // filter_bboxes :50-59
+        const float h = fadd(fsub(box.z, box.x), 1.f);
+        pass = (w > A.min_size_p1) && (h > A.min_size_p1);
+      }
+    }
+    // one atomic per (warp, image): the survivors of a warp belong to one or two images
+    const unsigned active = __ballot_sync(0xffffffffu, pass);
+    if (pass) {
+      const unsigned peers = __match_any_sync(active, b);
+      const int leader = __ffs(peers) - 1;
+      const int lane = tid & 31;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(A.key_count + b, __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      const int pos = base + __popc(peers & ((1u << lane) - 1u));
+      A.keys[(int64_t)b * A.n + pos] =
+          ((unsigned long long)score_to_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4+K5: one CTA per (image, class) list does everything after the filter:
+//   1. top-k select + sort of the surviving keys in shared memory (select_and_sort, sort.cuh);
+//   2. decode + clip + normalise the K best boxes (shared memory, or the workspace for very long lists);
+//   3. greedy NMS exactly as tf.image.non_max_suppression runs it - a candidate is tested against the boxes KEPT so
+//      far, never against all earlier candidates - but kChunk candidates at a time:
+//        a. every candidate of the chunk against the kept list (one warp per candidate, lanes over the kept boxes,
+//           the warp leaves at the first suppressor): final for the candidates it suppresses, because the kept list
+//           only grows;
+//        b. the survivors are compacted in rank order;
+//        c. their mutual suppression bits T[v] = { u < v : IoU(u, v) > thr } (<= kChunk^2 / 2 tests);
+//        d. kept(v) = no kept u in T[v], evaluated by relaxation (a survivor is decided once one of its suppressors is
+//           known kept, or all are known suppressed): the number of sweeps is the longest dependency chain inside the
+//           chunk, a handful; chains longer than kMaxSweeps are finished serially by one warp;
+//        e. the kept survivors are appended to the kept list in rank order; the loop ends when nms_topk boxes are kept
+//           (max_output_size) or the candidates run out.
+//      The detections of a trained detector are clusters of near duplicates around each face: almost every candidate
+//      is removed in step a by its cluster's head after a few tests, so the work is ~K * kept / 64 warp steps instead
+//      of the K^2 / 2 pair tests of a suppression matrix.
+//   4. the first nms_topk kept boxes are written out in rank order, zero padded (bbox_util.py:80-90).
+// ---------------------------------------------------------------------------
+constexpr int kChunk = 256;
+constexpr int kChunkWords = kChunk / 32;
+constexpr int kMaxSweeps = 12;
+constexpr size_t kGreedySmemMax = 200 * 1024;          // dynamic part (the kernel has ~20 KB of static shared memory)
+
+struct GreedyPlan {
+  size_t smem;          // dynamic shared memory
+  int sort_bytes;       // bytes reserved for the keys while they are sorted
+  int kcap;             // candidate slots
+  int wcap;             // 32-bit words per stripe bitset = ceil(nms_cap / 32)
+  int cand_global;      // candidates live in the workspace instead of shared memory
+  int kept_global;      // so do the kept list and its stripe bitsets
+};
+
+static int next_pow2(int64_t v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static GreedyPlan greedy_plan(int64_t n, int keep_topk, int nms_cap) {
+  GreedyPlan g;
+  const int sort_n = (int)(n < kSortCap ? (n > 0 ? n : 1) : kSortCap);
+  g.sort_bytes = next_pow2(sort_n) * 8;
+  g.kcap = keep_topk < sort_n ? keep_topk : sort_n;
+  g.wcap = (nms_cap + 31) / 32;
+  const size_t kept_bytes = align_up((size_t)nms_cap * 16, 16) + 2 * align_up((size_t)nms_cap * 4, 16) + (size_t)64 * g.wcap * 4;
+  const size_t cand_box = align_up((size_t)g.kcap * 16, 16);
+  const size_t region0 = cand_box > (size_t)g.sort_bytes ? cand_box : (size_t)g.sort_bytes;
+  const size_t full = region0 + align_up((size_t)g.kcap * 4, 16) + align_up((size_t)g.kcap * 8, 16) + kept_bytes;
+  g.cand_global = g.kept_global = 0;
+  g.smem = full;
+  if (full > kGreedySmemMax) {
+    g.cand_global = 1;
+    g.smem = (size_t)g.sort_bytes + kept_bytes;
+    if (g.smem > kGreedySmemMax) {
+      g.kept_global = 1;
+      g.smem = (size_t)g.sort_bytes;
+    }
+  }
+  return g;
 }
 
 // block-wide min / max of a float over all threads (every thread gets the result)
@@ -521,493 +475,369 @@ DAN_D void block_minmax(float lo, float hi, float& out_lo, float& out_hi) {
   __syncthreads();
 }
 
-// ---- kernel S: one CTA per list: top-k + sort, decode, broad-phase grid (steps 1-3) -> HBM (L2 resident)
-template <bool DECODE>
-__global__ void __launch_bounds__(kSortThreads, 1) pp_sort_kernel(const PpArgs A, const float4* __restrict__ src_boxes) {
+// stripe masks of the broad phase (see the kernel); monotone in the coordinate, so overlapping intervals share a bit
+struct Stripes {
+  float ylo, yinv, xlo, xinv;
+  bool all;
+  DAN_D static uint32_t axis(float v0, float v1, float lo, float inv) {
+    const float f0 = (v0 - lo) * inv, f1 = (v1 - lo) * inv;
+    if (!(fabsf(f0) < 1e9f) || !(fabsf(f1) < 1e9f)) return 0xffffffffu;      // non-finite or far outside: every stripe
+    const int s0 = min(max((int)f0, 0), 31), s1 = min(max((int)f1, 0), 31);
+    return (0xffffffffu >> (31 - s1)) & (0xffffffffu << s0);
+  }
+  // (x mask, y mask) of a normalised box (y0, x0, y1, x1); a box without area neither suppresses nor is suppressed
+  DAN_D uint2 masks(float4 bx, float area) const {
+    if (!(area > 0.f)) return make_uint2(0u, 0u);
+    if (all) return make_uint2(0xffffffffu, 0xffffffffu);
+    return make_uint2(axis(bx.y, bx.w, xlo, xinv), axis(bx.x, bx.z, ylo, yinv));
+  }
+};
+
+// barriers among the first kChunk threads of the CTA (hardware barrier 1); the other warps wait at the next __syncthreads
+DAN_D void bar_sync_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(kChunk) : "memory"); }
+DAN_D bool bar_or_chunk(bool pred) {
+  int r;
+  asm volatile(
+      "{\n"
+      "  .reg .pred p, q;\n"
+      "  setp.ne.s32 q, %1, 0;\n"
+      "  bar.red.or.pred p, 1, %2, q;\n"
+      "  selp.s32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"((int)pred), "n"(kChunk)
+      : "memory");
+  return r != 0;
+}
+
+// WHERE: 0 = candidates and kept list in shared memory (the usual case), 1 = candidates in the workspace, 2 = both in the
+// workspace (very long lists).  A template parameter rather than a run-time pointer choice so that the shared-memory
+// accesses compile to LDS / STS / ATOMS instead of generic-address instructions.
+template <bool DECODE, int WHERE>
+__global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArgs A, const float* __restrict__ src_scores,
+                                                                     const float4* __restrict__ src_boxes) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dyn_smem);
-  int* cell_cnt = reinterpret_cast<int*>(dyn_smem);            // aliases the keys once they are in HBM
   __shared__ SortScratch sc;
-  __shared__ int s_scan[kSortThreads / 32];
-  __shared__ int s_class_mask;
-  __shared__ int s_class_amin[kNmsClasses];
+  __shared__ int s_flag[kChunk];                       // step a: candidate r of the chunk is suppressed by the kept list
+  __shared__ int s_surv[kChunk];                       // step b: chunk-local index of survivor u
+  __shared__ float4 s_sbox[kChunk];
+  __shared__ float s_sarea[kChunk];
+  __shared__ uint32_t s_T[kChunk][kChunkWords];
+  __shared__ uint32_t s_keptm[kChunkWords], s_supm[kChunkWords];
+  __shared__ uint2 s_smask[kChunk];
+  __shared__ int s_wcnt[kChunkWords];
+  __shared__ int s_ns;
 
   const int list = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int b = list / max(A.num_classes - 1, 1);
   const int cnt = min(A.key_count[list], A.n);
   const int64_t o = (int64_t)list * A.keep_topk;
+  const float thr = A.nms_thr;
 
+  // ---- carve
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dyn_smem);
+  float4* cbox;
+  float* carea;
+  uint2* cmask;
+  unsigned char* p;
+  if (WHERE >= 1) {
+    cbox = A.s_box + o;
+    carea = A.s_area + o;
+    cmask = A.s_mask + o;
+    p = dyn_smem + A.sort_bytes;
+  } else {
+    const size_t cand_box = ((size_t)A.kcap * 16 + 15) / 16 * 16;
+    cbox = reinterpret_cast<float4*>(dyn_smem);                                    // aliases the keys (see step 2)
+    carea = reinterpret_cast<float*>(dyn_smem + (cand_box > (size_t)A.sort_bytes ? cand_box : (size_t)A.sort_bytes));
+    cmask = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(carea) + ((size_t)A.kcap * 4 + 15) / 16 * 16);
+    p = reinterpret_cast<unsigned char*>(cmask) + ((size_t)A.kcap * 8 + 15) / 16 * 16;
+  }
+  float4* kbox;
+  float* karea;
+  int* krank;
+  uint32_t* stripes;                                   // [2][32][wcap]: kept boxes touching x stripe s / y stripe s
+  const int wcap = A.wcap;
+  if (WHERE >= 2) {
+    const int64_t ok = (int64_t)list * A.keep_topk;
+    kbox = A.g_kept_box + ok;
+    karea = A.g_kept_area + ok;
+    krank = A.g_kept_rank + ok;
+    stripes = A.g_stripes + (int64_t)list * 64 * ((A.keep_topk + 31) / 32);
+  } else {
+    kbox = reinterpret_cast<float4*>(p); p += ((size_t)A.nms_cap * 16 + 15) / 16 * 16;
+    karea = reinterpret_cast<float*>(p); p += ((size_t)A.nms_cap * 4 + 15) / 16 * 16;
+    krank = reinterpret_cast<int*>(p); p += ((size_t)A.nms_cap * 4 + 15) / 16 * 16;
+    stripes = reinterpret_cast<uint32_t*>(p);
+  }
+  uint32_t* xs = stripes;
+  uint32_t* ys = stripes + 32 * wcap;
+
+  // ---- 1. top-k + sort
   DAN_PHASE(0);
   const int K = min(select_and_sort(A.keys + (int64_t)list * A.n, cnt, min(A.keep_topk, cnt), keys, sc), A.keep_topk);
   DAN_PHASE(1);
-  float ylo = 3.0e38f, yhi = -3.0e38f, xlo = 3.0e38f, xhi = -3.0e38f;
-  for (int r = tid; r < K; r += kSortThreads) {
-    const unsigned long long key = keys[r];
-    const uint32_t idx = key_index(key);
-    A.s_key[o + r] = key;
-    const NmsBox nb = nms_norm(DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx]);
-    A.s_box[o + r] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
-    A.s_area[o + r] = nb.area;
-    if (nb.area > 0.f) {
-      ylo = fminf(ylo, nb.y0); yhi = fmaxf(yhi, nb.y1);
-      xlo = fminf(xlo, nb.x0); xhi = fmaxf(xhi, nb.x1);
+
+  // ---- 2. decode + clip + normalise.  The candidate boxes reuse the shared memory of the keys: every thread first
+  // takes its (<= 8) keys into registers.
+  unsigned long long myk[kSortCap / kSortThreads];
+#pragma unroll
+  for (int e = 0; e < kSortCap / kSortThreads; ++e) {
+    const int r = tid + e * kSortThreads;
+    myk[e] = (r < K) ? keys[r] : 0ull;
+    if (r < K) A.s_key[o + r] = myk[e];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < kSortCap / kSortThreads; ++e) {
+    const int r = tid + e * kSortThreads;
+    if (r < K) {
+      const uint32_t idx = key_index(myk[e]);
+      const NmsBox nb = nms_norm(DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx]);
+      cbox[r] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
+      carea[r] = nb.area;
     }
   }
-  if (tid == 0) s_class_mask = 0;
-  if (tid < kNmsClasses) s_class_amin[tid] = 0x7f7fffff;     // FLT_MAX as ordered int (areas are positive)
-  GridGeom g;
-  float ey, ex;
-  block_minmax(ylo, yhi, g.oy, ey);      // (contains barriers: the keys are dead from here on)
-  block_minmax(xlo, xhi, g.ox, ex);
-  g.extent = fmaxf(fmaxf(ey - g.oy, ex - g.ox), 1.f);
+  __syncthreads();
   DAN_PHASE(2);
 
-  for (int i = tid; i < kTotalCells; i += kSortThreads) cell_cnt[i] = 0;
-  __syncthreads();
-  uint16_t* box_cell = A.box_cell + o;
-  for (int i = tid; i < K; i += kSortThreads) {
-    const float4 bx = A.s_box[o + i];
-    int cid = 0xffff;
-    if (A.s_area[o + i] > 0.f) {
-      const float side = fmaxf(bx.z - bx.x, bx.w - bx.y);
-      const int c = (side < 1.f) ? 0 : min(kNmsClasses - 1, (int)((__float_as_uint(side) >> 23) & 255u) - 127);
-      if (c == kNmsClasses - 1) {
-        cid = c * kCellsPerClass;
-      } else {
-        const float inv = 1.f / g.cell_size(c);
-        cid = c * kCellsPerClass + GridGeom::cell_of(0.5f * (bx.x + bx.z), g.oy, inv) * kGridDim +
-              GridGeom::cell_of(0.5f * (bx.y + bx.w), g.ox, inv);
-      }
-      atomicAdd(&cell_cnt[cid], 1);
-      atomicOr(&s_class_mask, 1 << c);
-      atomicMin(&s_class_amin[c], __float_as_int(A.s_area[o + i]));
-    }
-    box_cell[i] = (uint16_t)cid;
-  }
-  __syncthreads();
-  DAN_PHASE(3);
-  uint16_t* cell_start = A.cell_start + (int64_t)list * kCellStride;
-  {  // exclusive scan of the cell counters: consecutive cells per thread
-    constexpr int per = (kTotalCells + kSortThreads - 1) / kSortThreads;
-    int local[per];
-    int sum = 0;
-#pragma unroll
-    for (int e = 0; e < per; ++e) {
-      const int cidx = tid * per + e;
-      local[e] = (cidx < kTotalCells) ? cell_cnt[cidx] : 0;
-      sum += local[e];
-    }
-    int incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
-    }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; ++w) before += s_scan[w];
-    int run = before + incl - sum;
-#pragma unroll
-    for (int e = 0; e < per; ++e) {
-      const int cidx = tid * per + e;
-      if (cidx < kTotalCells) {
-        cell_cnt[cidx] = run;          // start of the cell; becomes the scatter cursor below
-        run += local[e];
-      }
-    }
-    if (tid == kSortThreads - 1) cell_start[kTotalCells] = (uint16_t)run;
-  }
-  __syncthreads();
-  for (int i = tid; i < kTotalCells; i += kSortThreads) cell_start[i] = (uint16_t)cell_cnt[i];   // coalesced copy to HBM
-  __syncthreads();
-  uint16_t* cell_items = A.cell_items + o;
-  for (int i = tid; i < K; i += kSortThreads) {
-    const int cid = box_cell[i];
-    if (cid != 0xffff) {
-      const int pos = atomicAdd(&cell_cnt[cid], 1);
-      cell_items[pos] = (uint16_t)i;
-      A.box_pos[o + i] = (uint16_t)pos;
-    }
-  }
-  DAN_PHASE(4);
-  // the pair kernel stages these arrays with 16-byte copies: define the few entries between K and the next multiple of 8,
-  // and the padding of the cell table
-  for (int i = K + tid; i < min(A.keep_topk, (K + 7) & ~7); i += kSortThreads) {
-    A.s_area[o + i] = 0.f;
-    box_cell[i] = 0xffff;
-    A.box_pos[o + i] = 0;
-    cell_items[i] = 0;
-  }
-  for (int i = kTotalCells + 1 + tid; i < kCellStride; i += kSortThreads) cell_start[i] = 0;
-  if (tid == 0) {
-    A.s_len[list] = K;
-    A.grid_info[list] = make_float4(g.oy, g.ox, g.extent, __int_as_float(s_class_mask));
-    A.edge_n[list] = 0;
-    A.ovf[list] = (A.nms_thr < 0.f || A.force_rounds) ? 1 : 0;     // thr < 0: disjoint boxes suppress too, no spatial pruning
-  }
-  if (tid < kNmsClasses) A.class_amin[list * 16 + tid] = __int_as_float(s_class_amin[tid]);
-}
-
-// ---- kernel P: narrow phase (step 4), up to kPairCtas CTAs per list.  Every CTA stages the list's boxes and grid in
-// shared memory (the searches are chains of dependent lookups: ~30 cycles there instead of an L2 round trip) and its
-// warps take the boxes round-robin.  A box j of class d that overlaps box i has its centre within 2^d (half its largest
-// possible side) of i (+1 px and 1e-6 relative for fp32 rounding), i.e. in a window of at most 4x4 cells of class d's
-// grid (more when the grid had to be coarsened).  Box i searches the classes d > class(i) in full and only the half
-// of its own class's window that follows it (each same-class pair is met exactly once).  Edges are collected in
-// warp-private shared-memory buffers and appended to the list's edge array with one atomic per flush.
-constexpr int kPairCtas = 16;         // upper bound of CTAs per list
-constexpr int kPairEdgeBuf = 8192;
-
-static size_t pairs_smem_bytes(int keep_topk) {
-  return (size_t)keep_topk * 16 + align_up((size_t)keep_topk * 4, 16) + align_up((size_t)keep_topk * 2, 16) * 3 +
-         (size_t)kCellStride * 2 + (size_t)kPairEdgeBuf * 4;
-}
-
-__global__ void __launch_bounds__(kSortThreads, 1) nms_pairs_kernel(const PpArgs A) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ float s_prune[kNmsClasses], s_inv[kNmsClasses];
-  const int list = blockIdx.y;
-  if (A.ovf[list] != 0) return;
-  const int K = A.s_len[list];
-  // long lists get all the CTAs of their grid row, short ones only a few (the others exit at once): the launch time
-  // is set by the longest list
-  // (one CTA per ~320 boxes: every CTA stages the whole list, so more CTAs mostly add staging work; measured at 32 lists
-  // of ~2000 boxes: 160 boxes per CTA 45 us / 403 k img/s, 320 boxes per CTA 43 us / 427 k img/s)
-  const int my_ctas = min((int)gridDim.x, max(1, K / 320));
-  if ((int)blockIdx.x >= my_ctas) return;
-  DAN_PHASE(24);
-  const int tid = threadIdx.x;
-  const int64_t o = (int64_t)list * A.keep_topk;
-  unsigned char* p = dyn_smem;
-  float4* box = reinterpret_cast<float4*>(p); p += (size_t)A.keep_topk * 16;
-  float* area = reinterpret_cast<float*>(p); p += ((size_t)A.keep_topk * 4 + 15) / 16 * 16;
-  uint16_t* box_cell = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
-  uint16_t* box_pos = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
-  uint16_t* cell_items = reinterpret_cast<uint16_t*>(p); p += ((size_t)A.keep_topk * 2 + 15) / 16 * 16;
-  uint16_t* cell_start = reinterpret_cast<uint16_t*>(p); p += (size_t)kCellStride * 2;
-  uint32_t* ebuf = reinterpret_cast<uint32_t*>(p);
-
-  if ((A.keep_topk & 7) == 0) {
-    // every list starts 16-byte aligned: 16-byte copies (reading up to the next multiple of 8 <= keep_topk entries)
-    for (int i = tid; i < K; i += kSortThreads) box[i] = A.s_box[o + i];
-    const int n4 = (K + 3) / 4, n8 = (K + 7) / 8;
-    for (int i = tid; i < n4; i += kSortThreads)
-      reinterpret_cast<float4*>(area)[i] = reinterpret_cast<const float4*>(A.s_area + o)[i];
-    for (int i = tid; i < n8; i += kSortThreads) {
-      reinterpret_cast<uint4*>(box_cell)[i] = reinterpret_cast<const uint4*>(A.box_cell + o)[i];
-      reinterpret_cast<uint4*>(box_pos)[i] = reinterpret_cast<const uint4*>(A.box_pos + o)[i];
-      reinterpret_cast<uint4*>(cell_items)[i] = reinterpret_cast<const uint4*>(A.cell_items + o)[i];
-    }
-  } else {
-    for (int i = tid; i < K; i += kSortThreads) {
-      box[i] = A.s_box[o + i];
-      area[i] = A.s_area[o + i];
-      box_cell[i] = A.box_cell[o + i];
-      box_pos[i] = A.box_pos[o + i];
-      cell_items[i] = A.cell_items[o + i];
-    }
-  }
-  {  // the grid: 16-byte copies (20 KB per CTA; two-byte loads made this the longest part of the staging)
-    const uint4* g_start = reinterpret_cast<const uint4*>(A.cell_start + (int64_t)list * kCellStride);
-    uint4* s_start = reinterpret_cast<uint4*>(cell_start);
-    for (int i = tid; i < kCellStride / 8; i += kSortThreads) s_start[i] = g_start[i];
-  }
-  const float4 gi = A.grid_info[list];
-  GridGeom g;
-  g.oy = gi.x; g.ox = gi.y; g.extent = gi.z;
-  if (tid < kNmsClasses) {
-    s_prune[tid] = A.nms_thr * A.class_amin[list * 16 + tid] * 0.999f;   // area below which class `tid` cannot suppress
-    s_inv[tid] = 1.f / g.cell_size(tid);
-  }
-  __syncthreads();
-  DAN_PHASE(25);
-
-  const int class_mask = __float_as_int(gi.w);
-  uint32_t* edges = A.edges + (int64_t)list * kEdgeCap;
-  const float thr = A.nms_thr;
-  // warp-cooperative search: a half-warp takes one box i at a time and walks its size classes d >= class(i); the item
-  // ranges of the grid rows of the class-d windows form one flat candidate list that its 16 lanes test 16 at a time.
-  // (A thread-per-query loop is SIMT-hostile here: the windows hold anything from 0 to hundreds of boxes.)
-  const int lane = tid & 31;
-  const int warps_total = my_ctas * (kSortThreads / 32);
-  // every warp collects its edges in a private slice of shared memory (no atomics in the search loop) and appends
-  // the slice to the list's edge array with one atomic when it is full and at the end
-  constexpr int kWarpEdgeBuf = kPairEdgeBuf / (kSortThreads / 32);
-  uint32_t* wbuf = ebuf + (tid >> 5) * kWarpEdgeBuf;
-  int wcount = 0;                                            // warp-uniform
-  auto flush_warp = [&]() {
-    __syncwarp();                                            // the buffer entries were written by other lanes
-    int base = 0;
-    if (lane == 0) base = atomicAdd(A.edge_n + list, wcount);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + wcount > kEdgeCap) {
-      if (lane == 0) A.ovf[list] = 1;
-    } else {
-      for (int e = lane; e < wcount; e += 32) edges[base + e] = wbuf[e];
-    }
-    __syncwarp();
-    wcount = 0;
-  };
+  // ---- 3. greedy NMS, kChunk candidates per round
 #ifdef DAN_PHASE_TIMING
-  long long acc_setup = 0, acc_loop = 0, acc_n = 0, acc_boxes = 0, t_a = 0;
+  long long acc[5] = {0, 0, 0, 0, 0}, t_a = 0, n_sweeps = 0, n_surv = 0, n_chunks = 0;
 #define DAN_TICK() (t_a = clock64())
-#define DAN_TOCK(acc) (acc += clock64() - t_a)
+#define DAN_TOCK(i) (acc[i] += clock64() - t_a)
 #else
 #define DAN_TICK() do { } while (0)
-#define DAN_TOCK(acc) do { } while (0)
+#define DAN_TOCK(i) do { } while (0)
 #endif
-  // TWO boxes per warp, one per half-warp (consecutive ranks): most boxes have fewer than 16 candidates and search two
-  // size classes, so a whole warp per box left half of its lanes idle and paid the window set-up once per box.
-  const int half = lane >> 4, hl = lane & 15;
-  for (int i0 = 2 * (blockIdx.x * (kSortThreads / 32) + (tid >> 5)); i0 < K; i0 += 2 * warps_total) {
-    const int i = i0 + half;
-    const int my_cid = (i < K) ? box_cell[i] : 0xffff;
-    const bool live_box = my_cid != 0xffff;
-    if (!__any_sync(0xffffffffu, live_box)) continue;      // warp-uniform
-    const int c = live_box ? my_cid / kCellsPerClass : 0;
-    const int own_row = (my_cid - c * kCellsPerClass) / kGridDim;    // grid row of the box's own cell (0 for the last class)
-    const int after_me = live_box ? box_pos[i] + 1 : 0;
-    const float4 me = live_box ? box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float my_area = live_box ? area[i] : 0.f;
-    auto emit = [&](bool edge, int j) {       // append the edges found by this step to the warp's private buffer
-      const unsigned em = __ballot_sync(0xffffffffu, edge);
-      if (em != 0u) {
-        if (wcount + 32 > kWarpEdgeBuf) flush_warp();
-        if (edge) wbuf[wcount + __popc(em & ((1u << lane) - 1u))] = ((uint32_t)max(i, j) << 16) | (uint32_t)min(i, j);
-        wcount += __popc(em);
-      }
-    };
-    // classes to search (lane hl of a half-warp speaks for class hl): non-empty, d >= c, and not ruled out by the area
-    // ratio (IoU <= area_i / area_j: a class whose smallest box is already too large for the threshold cannot
-    // suppress i)
-    const bool want = live_box && hl >= c && hl < kNmsClasses && ((class_mask >> hl) & 1) &&
-                      (hl == c || !(my_area < s_prune[hl < kNmsClasses ? hl : 0]));
-    unsigned todo = (__ballot_sync(0xffffffffu, want) >> (16 * half)) & 0xffffu;     // per half-warp
-    while (__any_sync(0xffffffffu, todo != 0u)) {          // up to 2 classes per pass and box
-      DAN_TICK();
-      // lane = (class slot, window row): each lane finds the item range of ONE row of ONE class's window, so the
-      // window geometry of the classes is computed in parallel and all candidates of a box form one flat list
-      const int slot = hl >> 3, r = hl & 7;
-      unsigned rest = todo;                                // (slot+1)-th set bit of todo (no __fns: it is a software loop)
-      int dsel = -1;
-#pragma unroll
-      for (int sidx = 0; sidx < 2; ++sidx) {
-        const int dd = rest ? (__ffs(rest) - 1) : -1;
-        if (slot == sidx) dsel = dd;
-        rest &= rest - 1u;
-      }
-      const bool has = dsel >= 0;
-      const int d = has ? dsel : 0;
-      int cy0 = 0, cy1 = 0, cx0 = 0, cx1 = 0;
-      if (has && d < kNmsClasses - 1) {
-        const float inv = s_inv[d];
-        const float reach = (float)(1 << d) + 1.f;
-        cy0 = GridGeom::cell_of(me.x - reach - 1e-6f * fabsf(me.x), g.oy, inv);
-        cy1 = GridGeom::cell_of(me.z + reach + 1e-6f * fabsf(me.z), g.oy, inv);
-        cx0 = GridGeom::cell_of(me.y - reach - 1e-6f * fabsf(me.y), g.ox, inv);
-        cx1 = GridGeom::cell_of(me.w + reach + 1e-6f * fabsf(me.w), g.ox, inv);
-      }
-      // a window taller than 8 rows (possible only when the grid had to be coarsened) is walked in row blocks of 8
-      const int nrows = cy1 - cy0 + 1;
-      const int nblocks = __reduce_max_sync(0xffffffffu, has ? (nrows + 7) >> 3 : 0);
-      for (int rb = 0; rb < nblocks; ++rb) {
-        const int row_in_window = rb * 8 + r;
-        int p0 = 0, len = 0;
-        if (has && row_in_window < nrows) {
-          const int row = d * kCellsPerClass + (cy0 + row_in_window) * kGridDim;
-          p0 = cell_start[row + cx0];
-          // Own class: both boxes of an overlapping pair have each other in their windows, so only the HALF window
-          // after the box is searched: the rest of its own cell, the cells to the right in its own row, and the
-          // rows below.  (The items of a grid row are contiguous, and so are those of a cell.)
-          if (d == c) {
-            if (cy0 + row_in_window < own_row) p0 = 0x7fffffff;
-            else if (cy0 + row_in_window == own_row) p0 = after_me;
-          }
-          len = max((int)cell_start[row + cx1 + 1] - p0, 0);
-        }
-        int incl = len;                                  // inclusive prefix over the 16 (class, row) ranges of the half-warp
-#pragma unroll
-        for (int sh = 1; sh < 16; sh <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, sh, 16);
-          if (hl >= sh) incl += v;
-        }
-        const int n = __shfl_sync(0xffffffffu, incl, 15, 16);          // candidates of this half-warp's box
-        const int n_max = __reduce_max_sync(0xffffffffu, n);
-        const int shift = p0 - (incl - len);             // item position = q + shift inside this lane's range
-        DAN_TOCK(acc_setup);
-        DAN_TICK();
-#ifdef DAN_PHASE_TIMING
-        acc_n += n; acc_boxes += 1;
-#endif
-        for (int q0 = 0; q0 < n_max; q0 += 16) {          // warp-uniform trip count
-          const int q = q0 + hl;
-          int lo = 0;                                      // first range whose inclusive prefix exceeds q
-#pragma unroll
-          for (int st = 8; st >= 1; st >>= 1) {
-            const int v = __shfl_sync(0xffffffffu, incl, lo + st - 1, 16);
-            if (q >= v) lo += st;
-          }
-          lo = min(lo, 15);
-          const int pos = q + __shfl_sync(0xffffffffu, shift, lo, 16);
-          bool edge = false;
-          int j = 0;
-          if (q < n) {
-            j = cell_items[pos];
-            edge = pair_suppresses(box[j], area[j], me, my_area, thr);
-          }
-          emit(edge, j);
-        }
-        DAN_TOCK(acc_loop);
-        DAN_TICK();
-      }
-      todo = rest;                                         // the (up to) 2 classes of this pass are done
-    }
-  }
-  DAN_PHASE(26);
-#ifdef DAN_PHASE_TIMING
-  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_phase[28] = acc_setup; g_phase[29] = acc_loop; g_phase[30] = acc_n; g_phase[31] = acc_boxes; }
-#endif
-  if (wcount > 0) flush_warp();
-  DAN_PHASE(27);
-}
-
-// ---- kernel R: one CTA per list: relaxation over the edges (step 5) and the outputs (step 6)
-template <bool DECODE>
-__global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpArgs A, const float* __restrict__ src_scores,
-                                                                      const float4* __restrict__ src_boxes) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  const NmsSmem m = nms_carve(dyn_smem, A.nms_cap, A.keep_topk);
-  __shared__ int s_scan[kSortThreads / 32];
-
-  const int list = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int K = A.s_len[list];
-  const int64_t o = (int64_t)list * A.keep_topk;
-  int kept_n = 0;
-
-  DAN_PHASE(16);
-  if (A.ovf[list] == 0) {
-    const int n_edges = min(A.edge_n[list], kEdgeCap);
-    const uint32_t* edges = A.edges + (int64_t)list * kEdgeCap;
-    // the relaxation sweeps the edge list several times: keep it in shared memory when it fits (the fallback's
-    // candidate array is unused on this path)
-    const int smem_edges = A.keep_topk * 4;          // 16 B per candidate slot
-    if (n_edges <= smem_edges) {
-      uint32_t* se = reinterpret_cast<uint32_t*>(m.cand_box);
-      // 16-byte copies (the list's edge array is 16-byte aligned and kEdgeCap a multiple of 4)
-      for (int e = tid; e < (n_edges + 3) / 4; e += kSortThreads) {
-        if (4 * e + 3 < n_edges) {
-          reinterpret_cast<uint4*>(se)[e] = reinterpret_cast<const uint4*>(edges)[e];
-        } else {                                          // the last, partial vector: nothing beyond the list is read
-          for (int q = 4 * e; q < n_edges; ++q) se[q] = edges[q];
-        }
-      }
-      edges = se;
-    }
-    for (int i = tid; i < K; i += kSortThreads) { m.status[i] = 0; m.pending[i] = 0; }
-    __syncthreads();
-#ifdef DAN_PHASE_TIMING
-    int dbg_rounds = 0;
-#endif
-    // One sweep of the relaxation reads status[] while other threads set entries to 2 (suppressed) in the same sweep:
-    // an INTENDED race (compute-sanitizer racecheck reports it).  status only moves 0 -> 2 inside a sweep and 0 -> 1
-    // between sweeps (behind the barriers); a stale 0 merely postpones a decision to the next sweep, and the fixed
-    // point - the greedy NMS result - does not depend on the interleaving.  Byte stores do not tear.
-    while (true) {
-#ifdef DAN_PHASE_TIMING
-      ++dbg_rounds;
-#endif
-      for (int e0 = tid; e0 < n_edges; e0 += 4 * kSortThreads) {
-        uint32_t ed[4];
-        int sh[4], sl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                    // independent lookups in flight
-          const int e = e0 + u * kSortThreads;
-          ed[u] = (e < n_edges) ? edges[e] : 0xffffffffu;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool ok = ed[u] != 0xffffffffu;
-          sh[u] = ok ? m.status[ed[u] >> 16] : 1;
-          sl[u] = ok ? m.status[ed[u] & 0xffffu] : 2;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (sh[u] == 0) {
-            if (sl[u] == 1) m.status[ed[u] >> 16] = 2;
-            else if (sl[u] == 0) m.pending[ed[u] >> 16] = 1;
-          }
-        }
-      }
-      __syncthreads();
-      bool any = false;
-      for (int i = tid; i < K; i += kSortThreads) {
-        if (m.status[i] == 0) {
-          if (m.pending[i] == 0) m.status[i] = 1;
-          else { any = true; m.pending[i] = 0; }         // (cleared here for the next sweep: one barrier less per sweep)
-        }
-      }
-      if (!__syncthreads_or(any ? 1 : 0)) break;
-    }
-    DAN_PHASE(17);
-#ifdef DAN_PHASE_TIMING
-    if (threadIdx.x == 0 && blockIdx.x == 0) { g_phase[20] = n_edges; g_phase[21] = dbg_rounds; }
-#endif
-    // ordered compaction of the kept boxes: thread t owns ranks [t*E, (t+1)*E)
-    const int E = (K + kSortThreads - 1) / kSortThreads;
-    int mine_cnt = 0;
-    for (int e = 0; e < E; ++e) {
-      const int i = tid * E + e;
-      if (i < K && m.status[i] == 1) ++mine_cnt;
-    }
-    int incl = mine_cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
-    }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < kSortThreads / 32; ++w) {
-      if (w < warp) before += s_scan[w];
-      total += s_scan[w];
-    }
-    int pos = before + incl - mine_cnt;
-    for (int e = 0; e < E; ++e) {
-      const int i = tid * E + e;
-      if (i < K && m.status[i] == 1) {
-        if (pos < A.nms_topk) m.kept_pos[pos] = i;
-        ++pos;
-      }
-    }
-    kept_n = min(total, A.nms_topk);
-    __syncthreads();
-  } else {
+  // Broad phase: the extent of the candidates is cut into 32 stripes per axis and every box carries the two 32-bit masks
+  // of the stripes it touches.  Boxes that intersect share a stripe on both axes, so a pair whose masks do not meet is
+  // skipped after two ANDs; the (few) pairs that pass are queued and run through the exact test on dense warps.
+  Stripes sg;
+  {
+    float ylo = 3.0e38f, yhi = -3.0e38f, xlo = 3.0e38f, xhi = -3.0e38f;
     for (int r = tid; r < K; r += kSortThreads) {
-      m.cand_box[r] = A.s_box[o + r];
-      m.cand_area[r] = A.s_area[o + r];
+      const float4 bx = cbox[r];
+      if (carea[r] > 0.f && fabsf(bx.x) < 1e30f && fabsf(bx.y) < 1e30f && fabsf(bx.z) < 1e30f && fabsf(bx.w) < 1e30f) {
+        ylo = fminf(ylo, bx.x); yhi = fmaxf(yhi, bx.z);
+        xlo = fminf(xlo, bx.y); xhi = fmaxf(xhi, bx.w);
+      }
+    }
+    float ey, ex;
+    block_minmax(ylo, yhi, sg.ylo, ey);
+    block_minmax(xlo, xhi, sg.xlo, ex);
+    sg.yinv = (ey > sg.ylo) ? 32.f / (ey - sg.ylo) : 0.f;
+    sg.xinv = (ex > sg.xlo) ? 32.f / (ex - sg.xlo) : 0.f;
+    sg.all = thr < 0.f;                                // a negative threshold: disjoint boxes suppress too
+  }
+  for (int r = tid; r < K; r += kSortThreads) cmask[r] = sg.masks(cbox[r], carea[r]);
+  for (int i = tid; i < 64 * wcap; i += kSortThreads) stripes[i] = 0u;
+  __syncthreads();
+  int L = 0;                                           // kept boxes so far (CTA-uniform)
+  for (int c0 = 0; c0 < K && L < A.nms_topk; c0 += kChunk) {
+    const int nc = min(kChunk, K - c0);
+    DAN_TICK();
+    // a. chunk vs kept list.  The kept list is indexed by stripe: bit j of xs[s] / ys[s] says that kept box j touches x / y
+    // stripe s.  The kept boxes a candidate can intersect are (OR of xs over its x stripes) AND (OR of ys over its y
+    // stripes): a group of G lanes owns one candidate, a lane one 32-bit word of the bitset, and only the set bits go
+    // through the exact test (the candidate leaves at the first suppressor).
+    if (L > 0) {
+      const int W = (L + 31) >> 5;
+      const int G = W <= 8 ? 8 : (W <= 16 ? 16 : 32);        // lanes per candidate
+      const int cpw = 32 / G;                                // candidates per warp pass
+      const int gl = lane & (G - 1), sub = lane / G;
+      const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (sub * G);
+      for (int r0 = warp * cpw; r0 < nc; r0 += (kSortThreads / 32) * cpw) {
+        const int r = r0 + sub;
+        const bool have = r < nc;
+        const float4 me = have ? cbox[c0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float my_area = have ? carea[c0 + r] : 0.f;
+        const uint2 mm = have ? cmask[c0 + r] : make_uint2(0u, 0u);      // (no area: no stripes, never suppressed)
+        bool sup = false;
+        for (int wb = 0; wb < W; wb += G) {                  // one block of words unless the kept list is very long
+          const int w = wb + gl;
+          uint32_t poss = 0u;
+          if (w < W) {
+            uint32_t ax = 0u, ay = 0u;
+            for (uint32_t m = mm.x; m != 0u; m &= m - 1u) ax |= xs[(__ffs(m) - 1) * wcap + w];
+            for (uint32_t m = mm.y; m != 0u; m &= m - 1u) ay |= ys[(__ffs(m) - 1) * wcap + w];
+            poss = ax & ay;
+          }
+          while (__any_sync(0xffffffffu, poss != 0u && !sup)) {
+            bool t = false;
+            if (poss != 0u && !sup) {
+              const int j = (w << 5) + __ffs(poss) - 1;
+              poss &= poss - 1u;
+              t = pair_suppresses(kbox[j], karea[j], me, my_area, thr);
+            }
+            if ((__ballot_sync(0xffffffffu, t) & gmask) != 0u) sup = true;
+          }
+        }
+        if (have && gl == 0) s_flag[r] = sup ? 1 : 0;
+      }
+    } else {
+      if (tid < nc) s_flag[tid] = 0;
     }
     __syncthreads();
-    kept_n = nms_rounds(m, K, A.nms_topk, A.nms_thr);
+    DAN_TOCK(0);
+    DAN_TICK();
+    // b. survivors in rank order (the first kChunk threads, named barrier 1)
+    if (tid < kChunk) {
+      const bool f = (tid < nc) && (s_flag[tid] == 0);
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) s_wcnt[warp] = __popc(m);
+      if (tid < kChunkWords) { s_keptm[tid] = 0u; s_supm[tid] = 0u; }
+      bar_sync_chunk();
+      int base = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kChunkWords; ++w) {
+        const int c = s_wcnt[w];
+        if (w < warp) base += c;
+        total += c;
+      }
+      if (f) {
+        const int u = base + __popc(m & lt_mask);
+        const float4 bx = cbox[c0 + tid];
+        const float ar = carea[c0 + tid];
+        s_surv[u] = tid;
+        s_sbox[u] = bx;
+        s_sarea[u] = ar;
+        s_smask[u] = cmask[c0 + tid];
+      }
+      if (tid == 0) s_ns = total;
+    }
+    __syncthreads();
+    const int ns = s_ns;
+    DAN_TOCK(1);
+    DAN_TICK();
+    // c. suppression bits among the survivors: warp -> row v, lanes -> 32 earlier survivors per step
+    for (int v = warp; v < ns; v += kSortThreads / 32) {
+      const float4 me = s_sbox[v];
+      const float my_area = s_sarea[v];
+      const uint2 mm = s_smask[v];
+      const int nw = (v + 31) >> 5;                    // words that hold some u < v
+      for (int w = 0; w < nw; ++w) {
+        const int u = (w << 5) + lane;
+        const uint2 um = s_smask[u];
+        const bool poss = (u < v) && (um.x & mm.x) != 0u && (um.y & mm.y) != 0u;
+        unsigned bits = 0u;
+        if (__any_sync(0xffffffffu, poss)) {
+          const bool t = poss && pair_suppresses(s_sbox[u], s_sarea[u], me, my_area, thr);
+          bits = __ballot_sync(0xffffffffu, t);
+        }
+        if (lane == 0) s_T[v][w] = bits;
+      }
+    }
+    __syncthreads();
+    DAN_TOCK(2);
+    DAN_TICK();
+    // d. relaxation: thread v owns survivor v (the first kChunk threads)
+    int sweeps = 0;
+    if (tid < kChunk) {
+      uint32_t T[kChunkWords];
+      const int vw = tid >> 5;
+      const uint32_t vbit = 1u << (tid & 31);
+      const bool mine = tid < ns;
+#pragma unroll
+      for (int w = 0; w < kChunkWords; ++w) T[w] = (mine && (w << 5) < tid) ? s_T[tid][w] : 0u;
+      bool decided = !mine;
+      bool open = true;
+      while (open && sweeps < kMaxSweeps) {
+        uint32_t hitm = 0u, pendm = 0u;
+        if (!decided) {
+#pragma unroll
+          for (int w = 0; w < kChunkWords; ++w) {
+            const uint32_t kw = s_keptm[w], sw = s_supm[w];
+            hitm |= T[w] & kw;
+            pendm |= T[w] & ~(kw | sw);
+          }
+        }
+        bar_sync_chunk();                              // every thread has read the masks of the previous sweep
+        if (!decided) {
+          if (hitm != 0u) { atomicOr(&s_supm[vw], vbit); decided = true; }
+          else if (pendm == 0u) { atomicOr(&s_keptm[vw], vbit); decided = true; }
+        }
+        open = bar_or_chunk(!decided);
+        ++sweeps;
+      }
+      if (open) {
+        // a dependency chain longer than kMaxSweeps: warp 0 finishes the chunk serially (when it reaches an undecided
+        // survivor every earlier one is decided); lane w holds word w of the masks
+        if (warp == 0) {
+          uint32_t kw = (lane < kChunkWords) ? s_keptm[lane] : 0u;
+          uint32_t sw = (lane < kChunkWords) ? s_supm[lane] : 0u;
+          for (int v = 0; v < ns; ++v) {
+            const int w = v >> 5;
+            const uint32_t bit = 1u << (v & 31);
+            const uint32_t known = __shfl_sync(0xffffffffu, kw | sw, w);
+            if (known & bit) continue;                 // warp-uniform
+            const uint32_t t = (lane < kChunkWords && (lane << 5) < v) ? s_T[v][lane] : 0u;
+            const bool hit = __any_sync(0xffffffffu, (t & kw) != 0u);
+            if (lane == w) {
+              if (hit) sw |= bit;
+              else kw |= bit;
+            }
+          }
+          if (lane < kChunkWords) { s_keptm[lane] = kw; s_supm[lane] = sw; }
+        }
+        bar_sync_chunk();
+      }
+      DAN_TOCK(3);
+      DAN_TICK();
+      // e. append the kept survivors in rank order
+      int before = 0, nk = 0;
+#pragma unroll
+      for (int w = 0; w < kChunkWords; ++w) {
+        const int c = __popc(s_keptm[w]);
+        if (w < vw) before += c;
+        nk += c;
+      }
+      if (mine && (s_keptm[vw] & vbit)) {
+        const int pos = L + before + __popc(s_keptm[vw] & (vbit - 1u));
+        if (pos < A.nms_topk) {
+          kbox[pos] = s_sbox[tid];
+          karea[pos] = s_sarea[tid];
+          krank[pos] = c0 + s_surv[tid];
+          const uint2 sm = s_smask[tid];
+          const uint32_t bit = 1u << (pos & 31);
+          for (uint32_t m = sm.x; m != 0u; m &= m - 1u) atomicOr(&xs[(__ffs(m) - 1) * wcap + (pos >> 5)], bit);
+          for (uint32_t m = sm.y; m != 0u; m &= m - 1u) atomicOr(&ys[(__ffs(m) - 1) * wcap + (pos >> 5)], bit);
+        }
+      }
+    }
+    __syncthreads();
+    {
+      int nk = 0;
+#pragma unroll
+      for (int w = 0; w < kChunkWords; ++w) nk += __popc(s_keptm[w]);
+      L = min(L + nk, A.nms_topk);
+    }
+#ifdef DAN_PHASE_TIMING
+    DAN_TOCK(4);
+    n_sweeps += sweeps; n_surv += ns; ++n_chunks;
+#endif
   }
+  const int kept_n = L;
+  DAN_PHASE(3);
+#ifdef DAN_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) g_phase[10 + i] = acc[i];
+    g_phase[15] = n_sweeps; g_phase[16] = n_surv; g_phase[17] = n_chunks; g_phase[18] = K; g_phase[19] = kept_n;
+  }
+#endif
 
-  DAN_PHASE(18);
-  // ---- outputs, zero padded to nms_topk
+  // ---- 4. outputs, zero padded to nms_topk
   for (int t = tid; t < A.nms_topk; t += kSortThreads) {
     const int64_t oo = (int64_t)list * A.nms_topk + t;
     if (t < kept_n) {
-      const int pos = m.kept_pos[t];
+      const int pos = krank[t];
       const unsigned long long key = A.s_key[o + pos];
       const uint32_t idx = key_index(key);
       A.out_scores[oo] = DECODE ? key_to_score((uint32_t)(key >> 32)) : src_scores[idx];
-      A.out_boxes[oo] = DECODE ? A.s_box[o + pos] : src_boxes[idx];     // clipped boxes are already min/max ordered
+      A.out_boxes[oo] = DECODE ? kbox[t] : src_boxes[idx];     // clipped boxes are already min/max ordered
       if (A.out_index != nullptr) A.out_index[oo] = (int32_t)idx;
       if (A.out_keep != nullptr) A.out_keep[oo] = A.filler ? pos : (int32_t)idx;
     } else {
@@ -1023,7 +853,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
     }
   }
   if (tid == 0 && A.out_counts != nullptr) A.out_counts[list] = kept_n;
-  DAN_PHASE(19);
+  DAN_PHASE(4);
 }
 
 // ---------------------------------------------------------------------------
@@ -1031,7 +861,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_resolve_kernel(const PpAr
 // ---------------------------------------------------------------------------
 
 struct PpLayout {
-  size_t key_count, s_len, edge_n, ovf, grid_info, class_amin, keys, s_key, s_box, s_area, box_cell, box_pos, cell_start, cell_items, edges, total;
+  size_t key_count, keys, s_key, s_box, s_area, kept_box, kept_area, kept_rank, s_mask, stripes, total;
 };
 
 static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms) {
@@ -1040,19 +870,14 @@ static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms)
   auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
   w.key_count = take(lists * 4);
   w.keys = take(lists * n * 8);
-  w.s_len = take(nms ? lists * 4 : 0);
-  w.edge_n = take(nms ? lists * 4 : 0);
-  w.ovf = take(nms ? lists * 4 : 0);
-  w.grid_info = take(nms ? lists * 16 : 0);
-  w.class_amin = take(nms ? lists * 64 : 0);
   w.s_key = take(nms ? lists * keep_topk * 8 : 0);
   w.s_box = take(nms ? lists * keep_topk * 16 : 0);
   w.s_area = take(nms ? lists * keep_topk * 4 : 0);
-  w.box_cell = take(nms ? lists * keep_topk * 2 : 0);
-  w.box_pos = take(nms ? lists * keep_topk * 2 : 0);
-  w.cell_start = take(nms ? lists * (size_t)kCellStride * 2 : 0);
-  w.cell_items = take(nms ? lists * keep_topk * 2 : 0);
-  w.edges = take(nms ? lists * (size_t)kEdgeCap * 4 : 0);
+  w.kept_box = take(nms ? lists * keep_topk * 16 : 0);
+  w.kept_area = take(nms ? lists * keep_topk * 4 : 0);
+  w.kept_rank = take(nms ? lists * keep_topk * 4 : 0);
+  w.s_mask = take(nms ? lists * keep_topk * 8 : 0);
+  w.stripes = take(nms ? lists * 64 * ((keep_topk + 31) / 32) * 4 : 0);
   w.total = off;
   return w;
 }
@@ -1061,58 +886,43 @@ static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
   char* base = static_cast<char*>(ws);
   A.key_count = reinterpret_cast<int32_t*>(base + w.key_count);
   A.keys = reinterpret_cast<unsigned long long*>(base + w.keys);
-  A.s_len = reinterpret_cast<int32_t*>(base + w.s_len);
-  A.edge_n = reinterpret_cast<int32_t*>(base + w.edge_n);
-  A.ovf = reinterpret_cast<int32_t*>(base + w.ovf);
-  A.grid_info = reinterpret_cast<float4*>(base + w.grid_info);
-  A.class_amin = reinterpret_cast<float*>(base + w.class_amin);
   A.s_key = reinterpret_cast<unsigned long long*>(base + w.s_key);
   A.s_box = reinterpret_cast<float4*>(base + w.s_box);
   A.s_area = reinterpret_cast<float*>(base + w.s_area);
-  A.box_cell = reinterpret_cast<uint16_t*>(base + w.box_cell);
-  A.box_pos = reinterpret_cast<uint16_t*>(base + w.box_pos);
-  A.cell_start = reinterpret_cast<uint16_t*>(base + w.cell_start);
-  A.cell_items = reinterpret_cast<uint16_t*>(base + w.cell_items);
-  A.edges = reinterpret_cast<uint32_t*>(base + w.edges);
+  A.g_kept_box = reinterpret_cast<float4*>(base + w.kept_box);
+  A.g_kept_area = reinterpret_cast<float*>(base + w.kept_area);
+  A.g_kept_rank = reinterpret_cast<int32_t*>(base + w.kept_rank);
+  A.s_mask = reinterpret_cast<uint2*>(base + w.s_mask);
+  A.g_stripes = reinterpret_cast<uint32_t*>(base + w.stripes);
 }
 
-static bool nms_fits(int nms_cap, int keep_topk) {
-  return nms_smem_bytes(nms_cap, keep_topk) <= kNmsSmemMax;   // (the pair kernel is skipped when ITS staging does not fit)
-}
-
+// opt-in to > 48 KB of dynamic shared memory; the attribute belongs to the (function, device) pair, so it is set on
+// every call (a few hundred ns of host time) rather than cached in a process-wide flag
 static int enable_big_smem() {
-  static bool done = false;
-  if (!done) {
-    DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
-    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
-    DAN_CUDA(cudaFuncSetAttribute(pp_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
-    DAN_CUDA(cudaFuncSetAttribute(nms_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
-    DAN_CUDA(cudaFuncSetAttribute(nms_resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
-    DAN_CUDA(cudaFuncSetAttribute(nms_resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemMax));
-    done = true;
-  }
+  DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortCap * 8)));
+  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
+  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
+  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
+  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
+  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
+  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
   return DAN_OK;
 }
 
-// sort+grid -> pairs -> resolve for `lists` lists whose keys are in the workspace; ev (optional): 3 events, one after
-// each kernel
+// sort + greedy NMS for `lists` lists whose keys are in the workspace
 template <bool DECODE>
-static int run_sort_nms(const PpArgs& A_in, int lists, const float* src_scores, const float4* src_boxes, cudaStream_t st,
-                        cudaEvent_t* ev = nullptr) {
+static int run_sort_nms(const PpArgs& A_in, int lists, const float* src_scores, const float4* src_boxes, cudaStream_t st) {
   PpArgs A = A_in;
-  A.force_rounds = pairs_smem_bytes(A.keep_topk) > kNmsSmemMax ? 1 : 0;     // very long lists (> ~6 500 candidates)
-  pp_sort_kernel<DECODE><<<lists, kSortThreads, kSortSmem, st>>>(A, src_boxes);
-  DAN_LAUNCH_CHECK("pp_sort_kernel");
-  if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
-  // up to kPairCtas CTAs per list; a CTA exits at once when its list is short (see the kernel)
-  if (!A.force_rounds) {
-    nms_pairs_kernel<<<dim3(kPairCtas, lists), kSortThreads, pairs_smem_bytes(A.keep_topk), st>>>(A);
-    DAN_LAUNCH_CHECK("nms_pairs_kernel");
-  }
-  if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
-  nms_resolve_kernel<DECODE><<<lists, kSortThreads, nms_smem_bytes(A.nms_cap, A.keep_topk), st>>>(A, src_scores, src_boxes);
-  DAN_LAUNCH_CHECK("nms_resolve_kernel");
-  if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));
+  const GreedyPlan g = greedy_plan(A.n, A.keep_topk, A.nms_cap);
+  A.sort_bytes = g.sort_bytes;
+  A.kcap = g.kcap;
+  A.wcap = g.wcap;
+  A.cand_global = g.cand_global;
+  A.kept_global = g.kept_global;
+  if (g.kept_global) nms_greedy_kernel<DECODE, 2><<<lists, kSortThreads, g.smem, st>>>(A, src_scores, src_boxes);
+  else if (g.cand_global) nms_greedy_kernel<DECODE, 1><<<lists, kSortThreads, g.smem, st>>>(A, src_scores, src_boxes);
+  else nms_greedy_kernel<DECODE, 0><<<lists, kSortThreads, g.smem, st>>>(A, src_scores, src_boxes);
+  DAN_LAUNCH_CHECK("nms_greedy_kernel");
   return DAN_OK;
 }
 
@@ -1152,10 +962,8 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   DAN_REQUIRE(p->select_threshold >= 0.f, DAN_ERR_INVALID_ARGUMENT,
               "select_threshold must be >= 0 (a negative threshold would let zero-score rows carry boxes), got %g", p->select_threshold);
   DAN_REQUIRE(p->keep_topk >= 1 && p->nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "keep_topk and nms_topk must be >= 1");
-  DAN_REQUIRE(p->keep_topk <= kSortCap, DAN_ERR_UNSUPPORTED, "keep_topk %d exceeds the in-shared-memory sort capacity %d", p->keep_topk, kSortCap);
-  DAN_REQUIRE(nms_fits(p->nms_topk < p->keep_topk ? p->nms_topk : p->keep_topk, p->keep_topk), DAN_ERR_UNSUPPORTED,
-              "keep_topk %d / nms_topk %d do not fit the NMS kernel's shared memory (22 B per candidate + 24 B per kept box in "
-              "%zu bytes)", p->keep_topk, p->nms_topk, kNmsSmemMax);
+  DAN_REQUIRE(p->keep_topk <= kSortCap || num_anchors <= kSortCap, DAN_ERR_UNSUPPORTED,
+              "min(keep_topk, num_anchors) = %d exceeds the in-shared-memory sort capacity %d", p->keep_topk, kSortCap);
   DAN_REQUIRE((loc_pred != nullptr) != (boxes_pred != nullptr), DAN_ERR_INVALID_ARGUMENT, "exactly one of loc_pred / boxes_pred must be given");
   if (batch == 0) return DAN_OK;
   DAN_REQUIRE(cls_pred && out_boxes && out_scores, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
@@ -1199,11 +1007,19 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   DAN_CUDA(cudaMemsetAsync(A.key_count, 0, (size_t)lists * 4, st));
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
   if (num_anchors > 0) {
-    pp_filter_kernel<<<dim3((num_anchors + 256 * kFilterPerThread - 1) / (256 * kFilterPerThread), batch), 256, 0, st>>>(A);
+    const int64_t total = (int64_t)num_anchors * batch;
+    if (p->num_classes == 2 && aligned16(cls_pred) && total < 0x7fffffff) {
+      const int64_t per_cta = (int64_t)kF2Threads * kF2Vec * 2;
+      pp_filter2_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), kF2Threads, 0, st>>>(A);
+    } else {
+      pp_filter_kernel<<<dim3((num_anchors + 256 * kFilterPerThread - 1) / (256 * kFilterPerThread), batch), 256, 0, st>>>(A);
+    }
     DAN_LAUNCH_CHECK("pp_filter_kernel");
   }
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
-  return run_sort_nms<true>(A, lists, nullptr, nullptr, st, ev ? ev + 2 : nullptr);
+  rc = run_sort_nms<true>(A, lists, nullptr, nullptr, st);
+  if (ev && rc == DAN_OK) DAN_CUDA(cudaEventRecord(ev[2], st));
+  return rc;
 }
 
 int dan_postprocess_batch(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
@@ -1220,17 +1036,17 @@ int dan_postprocess_batch_profile(const dan_postprocess_params* p, const float* 
                                   int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos, void* workspace,
                                   size_t workspace_bytes, void* stream, float* h_kernel_ms) {
   DAN_REQUIRE(h_kernel_ms != nullptr, DAN_ERR_INVALID_ARGUMENT, "h_kernel_ms is NULL");
-  for (int i = 0; i < 4; ++i) h_kernel_ms[i] = 0.f;
-  cudaEvent_t ev[5];
-  for (int i = 0; i < 5; ++i) DAN_CUDA(cudaEventCreate(&ev[i]));
+  h_kernel_ms[0] = h_kernel_ms[1] = 0.f;
+  cudaEvent_t ev[3];
+  for (int i = 0; i < 3; ++i) DAN_CUDA(cudaEventCreate(&ev[i]));
   int rc = postprocess_core(p, cls_pred, loc_pred, boxes_pred, a_ymin, a_xmin, a_ymax, a_xmax, num_anchors, batch, out_boxes,
                             out_scores, out_counts, out_anchor_index, out_keep_pos, workspace, workspace_bytes, stream, ev);
   if (rc == DAN_OK && batch > 0) {
-    cudaError_t e = cudaEventSynchronize(ev[4]);
+    cudaError_t e = cudaEventSynchronize(ev[2]);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
-    else for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h_kernel_ms[i], ev[i], ev[i + 1]);
+    else for (int i = 0; i < 2; ++i) cudaEventElapsedTime(&h_kernel_ms[i], ev[i], ev[i + 1]);
   }
-  for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+  for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
   return rc;
 }
 
@@ -1264,11 +1080,9 @@ int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t 
 int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t nms_topk, float nms_threshold, float* out_scores,
                    float* out_boxes, int32_t* out_keep, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
   DAN_REQUIRE(n >= 0 && nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "bad size");
-  const int n_eff = n > 0 ? (int)(n < kSortCap ? n : kSortCap) : 1;
+  DAN_REQUIRE(n <= kSortCap, DAN_ERR_UNSUPPORTED, "n %lld exceeds the sort capacity %d", (long long)n, kSortCap);
+  const int n_eff = n > 0 ? (int)n : 1;
   const int cap = nms_topk < n_eff ? nms_topk : n_eff;
-  DAN_REQUIRE(n <= kSortCap && nms_fits(cap, n_eff), DAN_ERR_UNSUPPORTED,
-              "n %lld (max %d) / nms_topk %d do not fit the NMS kernel's shared memory (%zu bytes)", (long long)n, kSortCap, nms_topk,
-              kNmsSmemMax);
   DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
   DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
   const PpLayout w = pp_layout(n, 1, n_eff, true);

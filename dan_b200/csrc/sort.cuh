@@ -25,76 +25,80 @@ struct SortScratch {
   int fill;
 };
 
-// compare-exchange stage at distance ST (1, 2 or 4) inside a thread's 8 keys; all register indices are static
-template <int ST>
-DAN_D void reg_stage(unsigned long long (&r)[8], int lsize, bool desc_t) {
+// compare-exchange stage at distance ST (a power of two < KPT) inside a thread's KPT keys; all register indices
+// are static
+template <int KPT, int ST>
+DAN_D void reg_stage(unsigned long long (&r)[KPT], int lsize, bool desc_t) {
+  constexpr int LK = KPT == 8 ? 3 : KPT == 4 ? 2 : KPT == 2 ? 1 : 0;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
+  for (int e = 0; e < KPT; ++e) {
     if ((e & ST) == 0) {
-      const bool desc = (lsize >= 3) ? desc_t : (((e >> lsize) & 1) == 0);
+      const bool desc = (lsize >= LK) ? desc_t : (((e >> lsize) & 1) == 0);
       const unsigned long long x = r[e], y = r[e | ST];
       if ((x < y) == desc) { r[e] = y; r[e | ST] = x; }
     }
   }
 }
 
-// Bitonic sort (descending) of P = 2^lp2 >= 256 64-bit keys with the keys held in REGISTERS: thread t owns the 8
-// consecutive keys 8t..8t+7.  Compare-exchange partners at distance 1, 2, 4 are in the same thread, at distance
-// 8..128 in another lane of the same warp (shfl.xor), and only distances >= 256 go through shared memory, written
-// transposed ([e][thread]) so that both the store and the partner's load are conflict free.  The plain shared-memory
-// version is bandwidth bound (4 x 8 B accesses per compare-exchange, ~800 wavefronts per stage for 4096 keys).
+// Bitonic sort (descending) of P = 2^lp2 64-bit keys with the keys held in REGISTERS, KPT per thread: thread t owns
+// the consecutive keys KPT*t .. KPT*t + KPT-1 and T = P / KPT threads take part (KPT is chosen so that as many of the
+// CTA's 1024 threads as possible work: the sort is a chain of ~lp2^2/2 dependent stages, so the time is stages x
+// per-stage latency, and the per-stage latency grows with the keys a thread has to move).  Compare-exchange partners at a
+// distance below KPT are in the same thread, up to 16*KPT in another lane of the same warp (shfl.xor), and only the
+// larger distances go through shared memory, written transposed ([e][thread]) so that both the store and the
+// partner's load are conflict free.
+template <int KPT>
 DAN_D void bitonic_sort_regs(unsigned long long* s_keys, int lp2) {
+  constexpr int LK = KPT == 8 ? 3 : KPT == 4 ? 2 : KPT == 2 ? 1 : 0;
   const int tid = threadIdx.x;
-  const int T = 1 << (lp2 - 3);                 // threads that own keys
+  const int T = 1 << (lp2 - LK);                // threads that own keys
   const bool active = tid < T;
-  unsigned long long r[8];
+  unsigned long long r[KPT];
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) r[e] = s_keys[8 * tid + e];
+    for (int e = 0; e < KPT; ++e) r[e] = s_keys[KPT * tid + e];
   }
   for (int lsize = 1; lsize <= lp2; ++lsize) {
     // direction of the merge this key takes part in: descending iff bit `lsize` of its index is 0
-    const bool desc_t = ((tid >> (lsize >= 3 ? lsize - 3 : 0)) & 1) == 0;
+    const bool desc_t = ((tid >> (lsize >= LK ? lsize - LK : 0)) & 1) == 0;
     for (int ls = lsize - 1; ls >= 0; --ls) {
-      if (ls >= 8) {
+      if (ls >= LK + 5) {
         __syncthreads();
         if (active) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) s_keys[e * T + tid] = r[e];
+          for (int e = 0; e < KPT; ++e) s_keys[e * T + tid] = r[e];
         }
         __syncthreads();
         if (active) {
-          const int partner = tid ^ (1 << (ls - 3));
-          const bool keep_max = ((tid & (1 << (ls - 3))) == 0) == desc_t;
+          const int partner = tid ^ (1 << (ls - LK));
+          const bool keep_max = ((tid & (1 << (ls - LK))) == 0) == desc_t;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < KPT; ++e) {
             const unsigned long long o = s_keys[e * T + partner];
             r[e] = ((r[e] < o) == keep_max) ? o : r[e];      // keys are unique: max takes o iff r < o, min iff r > o
           }
         }
       } else if (!active) {
         // warps that own no keys only take part in the barriers above (T is a multiple of 32: warp-uniform)
-      } else if (ls >= 3) {
-        const int lmask = 1 << (ls - 3);
+      } else if (ls >= LK) {
+        const int lmask = 1 << (ls - LK);
         const bool keep_max = ((tid & lmask) == 0) == desc_t;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < KPT; ++e) {
           const unsigned long long o = __shfl_xor_sync(0xffffffffu, r[e], lmask);
           r[e] = ((r[e] < o) == keep_max) ? o : r[e];
         }
-      } else if (ls == 2) {
-        reg_stage<4>(r, lsize, desc_t);
-      } else if (ls == 1) {
-        reg_stage<2>(r, lsize, desc_t);
       } else {
-        reg_stage<1>(r, lsize, desc_t);
+        if constexpr (KPT > 4) { if (ls == 2) reg_stage<KPT, 4>(r, lsize, desc_t); }
+        if constexpr (KPT > 2) { if (ls == 1) reg_stage<KPT, 2>(r, lsize, desc_t); }
+        if constexpr (KPT > 1) { if (ls == 0) reg_stage<KPT, 1>(r, lsize, desc_t); }
       }
     }
   }
   __syncthreads();
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s_keys[8 * tid + e] = r[e];
+    for (int e = 0; e < KPT; ++e) s_keys[KPT * tid + e] = r[e];
   }
   __syncthreads();
 }
@@ -109,8 +113,11 @@ DAN_D void sort_smem_keys(unsigned long long* s_keys, int m) {
   const int p2 = 1 << lp2;
   for (int i = m + tid; i < p2; i += kSortThreads) s_keys[i] = 0ull;
   __syncthreads();
-  if (lp2 >= 8) {
-    bitonic_sort_regs(s_keys, lp2);
+  if (lp2 >= 5) {            // (at least one full warp of owners)
+    if (lp2 <= 10) bitonic_sort_regs<1>(s_keys, lp2);
+    else if (lp2 == 11) bitonic_sort_regs<2>(s_keys, lp2);
+    else if (lp2 == 12) bitonic_sort_regs<4>(s_keys, lp2);
+    else bitonic_sort_regs<8>(s_keys, lp2);
     return;
   }
   // small lists: plain bitonic sort in shared memory, descending; strides are powers of two -> shifts only

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib as L
 
-_ws = L.Workspace()
+_ws = L.StreamWorkspaces()
 
 EncodeResult = namedtuple("EncodeResult", ["targets", "labels", "scores", "matched_gt", "match"])
 Detections = namedtuple("Detections", ["boxes", "scores", "counts", "anchor_index", "keep_pos"])
@@ -398,8 +398,8 @@ def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=
             L.dev_ptr(boxes), L.dev_ptr(scores), L.dev_ptr(counts), L.dev_ptr(aidx), L.dev_ptr(kpos), L.dev_ptr(ws), nbytes,
             L.stream_ptr()]
     with torch.cuda.device(dev):
-        if profile:   # [filter, top-k/sort + grid, NMS pairs, NMS resolve] in ms (synchronises)
-            ms = (ctypes.c_float * 4)()
+        if profile:   # [filter, top-k/sort + NMS] in ms (synchronises)
+            ms = (ctypes.c_float * 2)()
             L.check(L.lib().dan_postprocess_batch_profile(*args, ms))
             return Detections(boxes, scores, counts, aidx, kpos), list(ms)
         L.check(L.lib().dan_postprocess_batch(*args))

@@ -162,8 +162,7 @@ class HotPath(object):
                                       out=det_out, workspace=self.ws_pp, profile=profile)
             if profile:
                 return enc[0], det[0], {"enc_pass1": enc[1][0], "enc_pass2": enc[1][1], "enc_pass3": enc[1][2],
-                                        "pp_filter": det[1][0], "pp_sort": det[1][1], "nms_pairs": det[1][2],
-                                        "nms_resolve": det[1][3]}
+                                        "pp_filter": det[1][0], "nms_greedy": det[1][1]}
             return enc, det
         main = torch.cuda.current_stream()
         if self._side is None:

@@ -208,7 +208,8 @@ int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t n
 /* ------------------------------------------------------------------------- *
  * (a17) batched fused parse_by_class, bbox_util.py:103-119:
  *   softmax -> select(threshold) -> [decode] -> clip -> min-size filter ->
- *   per-class top-k (block radix select + sort) -> bitmask NMS -> zero pad.
+ *   per-class top-k (block radix select + sort) -> greedy NMS against the kept
+ *   list -> zero pad.
  * cls_pred [B,N,C] logits.  Exactly one of `loc_pred` ([B,N,4] offsets, decoded
  * in-kernel against the anchors like decode_anchors) or `boxes_pred` ([B,N,4]
  * already decoded boxes, what parse_by_class literally takes) must be non-NULL.
@@ -244,8 +245,8 @@ int dan_postprocess_batch(const dan_postprocess_params* h_params, const float* c
                           int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos,
                           void* workspace, size_t workspace_bytes, void* stream);
 
-/* Profiling variant: durations in ms of the filter, top-k/sort(+grid), NMS pair and
- * NMS resolve kernels written to h_kernel_ms[4] (HOST pointer).
+/* Profiling variant: durations in ms of the filter kernel and of the top-k/sort +
+ * NMS kernel written to h_kernel_ms[2] (HOST pointer).
  * Synchronises; not graph capturable. */
 int dan_postprocess_batch_profile(const dan_postprocess_params* h_params, const float* cls_pred,
                                   const float* loc_pred, const float* boxes_pred,
@@ -351,6 +352,31 @@ int dan_gt_handoff(const float* gt_boxes, const int32_t* gt_offsets, const float
                    float target_width, float min_height, float min_width, float* out_gt_boxes,
                    int32_t* out_gt_offsets, int32_t* out_image_index, int32_t* out_counts,
                    void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (e) multi-GPU: the one exchange step of the path.  Images are sharded per rank
+ * with no data-path collective (the reference's analogue is the batch split of
+ * tf_replicate_model_fn.py:458-501, which has no collective at all); the
+ * variable-length detections of all ranks are exchanged as fixed-capacity slabs
+ * (counts | boxes | scores, written in place by dan_postprocess_batch) with ONE
+ * ncclAllGather enqueued on `stream`, i.e. on the device timeline right after the
+ * NMS kernel and capturable in the step's CUDA graph.
+ *   dan_nccl_load       bind NCCL at run time (NULL / "" = the libnccl.so.2 the
+ *                       process already uses, e.g. PyTorch's); optional, the other
+ *                       calls bind on first use.
+ *   dan_comm_unique_id  ncclGetUniqueId -> 128 bytes (rank 0; ship them to the
+ *                       other ranks by any means).
+ *   dan_comm_init       ncclCommInitRank on the CURRENT device -> opaque comm.
+ *   dan_gather_detections  recv_slabs [world, slab_bytes] <- send_slab [slab_bytes]
+ *                       of every rank, rank order.
+ * ------------------------------------------------------------------------- */
+int dan_nccl_load(const char* path);
+int dan_nccl_version(void);
+int dan_comm_unique_id(void* out_id128);
+int dan_comm_init(const void* id128, int32_t rank, int32_t world_size, void** out_comm);
+int dan_comm_destroy(void* comm);
+int dan_gather_detections(void* comm, const void* send_slab, void* recv_slabs, size_t slab_bytes,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -192,6 +192,10 @@ def _check_encode(ref, got, name=""):
     np.testing.assert_array_equal(scores, ref[2], err_msg=name + " scores")
     np.testing.assert_array_equal(targets, ref[0], err_msg=name + " targets")
     np.testing.assert_array_equal(matched, ref[3], err_msg=name + " matched_gt")
+    # bit-exact including the sign of zero: the reference multiplies every target / matched box by float(positive)
+    # (anchor_manipulator.py:324,326), which leaves -0.0 where the raw value of a non-positive anchor is negative
+    np.testing.assert_array_equal(np.signbit(targets), np.signbit(ref[0]), err_msg=name + " sign of targets")
+    np.testing.assert_array_equal(np.signbit(matched), np.signbit(ref[3]), err_msg=name + " sign of matched_gt")
     assert labels.dtype == np.int64 and targets.dtype == np.float32
 
 
@@ -561,8 +565,11 @@ def test_postprocess_errors(cuda):
     box = torch.zeros((1, 100, 4), device=cuda)
     with pytest.raises(_lib.DanError):
         bu.parse_by_class_batch([64, 64], cls, 2, -0.5, 0, 100, 10, 0.3, bboxes_pred=box)
-    with pytest.raises(_lib.DanError):
-        bu.parse_by_class_batch([64, 64], cls, 2, 0.1, 0, 100000, 10, 0.3, bboxes_pred=box)
+    big = torch.zeros((1, 9000, 2), device=cuda)
+    with pytest.raises(_lib.DanError):      # more anchors AND a larger keep_topk than the in-shared-memory sort holds
+        bu.parse_by_class_batch([64, 64], big, 2, 0.1, 0, 100000, 10, 0.3, bboxes_pred=torch.zeros((1, 9000, 4), device=cuda))
+    det = bu.parse_by_class_batch([64, 64], cls, 2, 0.1, 0, 100000, 10, 0.3, bboxes_pred=box)     # keep_topk > N is fine
+    assert int(det.counts.sum()) == 0
     with pytest.raises(TypeError):
         bu.parse_by_class_batch([64, 64], cls.cpu(), 2, 0.1, 0, 100, 10, 0.3, bboxes_pred=box)      # no CPU fallback
     det = bu.parse_by_class_batch([64, 64], cls, 2, 0.9, 0, 100, 10, 0.3, bboxes_pred=box)
