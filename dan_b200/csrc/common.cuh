@@ -63,15 +63,17 @@ DAN_D void point2center(float ymin, float xmin, float ymax, float xmax, float& c
                         float& w) {
   h = fadd(fsub(ymax, ymin), 1.f);
   w = fadd(fsub(xmax, xmin), 1.f);
-  cy = fdiv(fadd(ymin, ymax), 2.f);
-  cx = fdiv(fadd(xmin, xmax), 2.f);
+  // x / 2 == x * 0.5 exactly (a power-of-two scaling rounds identically, also into the denormals): one FMUL instead of
+  // the IEEE division sequence
+  cy = fmul(fadd(ymin, ymax), 0.5f);
+  cx = fmul(fadd(xmin, xmax), 0.5f);
 }
 
 // center2point, anchor_manipulator.py:125-127
 DAN_D void center2point(float cy, float cx, float h, float w, float& ymin, float& xmin, float& ymax,
                         float& xmax) {
-  const float hh = fdiv(fsub(h, 1.f), 2.f);
-  const float hw = fdiv(fsub(w, 1.f), 2.f);
+  const float hh = fmul(fsub(h, 1.f), 0.5f);
+  const float hw = fmul(fsub(w, 1.f), 0.5f);
   ymin = fsub(cy, hh);
   xmin = fsub(cx, hw);
   ymax = fadd(cy, hh);

@@ -68,6 +68,9 @@ struct EncArgs {
   HeapItem* bucket;      // [G, kBucketCap]
   HeapItem* spill;       // [B, 2, n] (candidate list and heap of the overflow path)
   float* wbest;          // [B, ceil(n/32)] largest row maximum of each warp of fused pass 1 (read by the patch pass)
+  float4* wbox;          // [ceil(n/32)] bounding box of the warp's (matching) anchors, the same for every image
+  int32_t* queue_n;      // [1] warps of pass 1 that the patch pass has to re-evaluate ...
+  int2* queue;           // [B * ceil(n/32)] ... as (image, warp)
   // outputs
   float4* targets;
   int64_t* labels;
@@ -586,6 +589,7 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const E
   const int lane = threadIdx.x & 31;
   const WarpAnchors W = load_warp_anchors(A);
   const int nwarps = (A.n + 31) >> 5;
+  if (blockIdx.x == 0 && lane == 0 && (W.a >> 5) < nwarps) A.wbox[W.a >> 5] = make_float4(W.wb.y0, W.wb.x0, W.wb.y1, W.wb.x1);
   const int b_end = min(batch, (int)(blockIdx.x + 1) * ipw);
   for (int b = blockIdx.x * ipw; b < b_end; ++b) {
     const ImageGt ig = image_gt<false>(A, b);
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const E
     }
     // no overlap of this warp exceeds the largest row maximum of its lanes: pass 2 uses it to skip the warp
     const uint32_t wbest = __reduce_max_sync(0xffffffffu, __float_as_uint(best));
-    if (lane == 0) A.wbest[(int64_t)b * nwarps + (W.a >> 5)] = __uint_as_float(wbest);
+    if (lane == 0 && (W.a >> 5) < nwarps) A.wbest[(int64_t)b * nwarps + (W.a >> 5)] = __uint_as_float(wbest);     // (the last CTA may hold a warp beyond the anchors)
     if (W.valid) {
       const int match = stage1_match<MINING>(A, best, best_gt);
       const int64_t row = (int64_t)b * A.n + W.a;
@@ -645,10 +649,16 @@ __global__ void __launch_bounds__(kEncThreads, 8) enc_pass1_fused_kernel(const E
 // and re-evaluated by full warps: row maximum again, tie / claim test, and the outputs of the anchors whose match
 // changed are rewritten (a patched anchor is always positive).
 constexpr int kPatchThreads = 128;
+constexpr int kPatchGt = 1024;        // GT boxes staged in shared memory at a time
 
 template <bool MINING>
-__global__ void __launch_bounds__(kPatchThreads) enc_pass2_patch_kernel(const EncArgs A) {
+__global__ void __launch_bounds__(kPatchThreads) enc_pass2_find_kernel(const EncArgs A) {
   __shared__ int s_list[kPatchThreads];
+  __shared__ float s_reach[kPatchThreads];
+  __shared__ float4 s_wbox[kPatchThreads];
+  __shared__ int s_flag[kPatchThreads];
+  __shared__ float4 s_box[kPatchGt];
+  __shared__ float s_cm[kPatchGt];
   __shared__ int s_n;
   __shared__ float s_cmin[kPatchThreads / 32];
   __shared__ int s_wide[kPatchThreads / 32];
@@ -659,12 +669,18 @@ __global__ void __launch_bounds__(kPatchThreads) enc_pass2_patch_kernel(const En
   const int nwarps = (A.n + 31) >> 5;
   const ImageGt ig = image_gt<false>(A, b);
   const bool need_haspos = !MINING && !A.gt_max_first;
+  // the usual case: all GT boxes and column maxima of the image fit the staging arrays and stay there
+  const bool staged = ig.m_eff <= kPatchGt;
 
   // smallest column maximum of the image; does any GT tie with zero-overlap anchors?
   float cmin = 3.0e38f;
   bool wide = false;
   for (int k = tid; k < ig.m_eff; k += kPatchThreads) {
     const float cm = __uint_as_float(A.colmax[ig.slot0 + k]);
+    if (staged) {
+      s_cm[k] = cm;
+      s_box[k] = gt_box(A, ig, k);
+    }
     wide |= MINING ? (cm < FLT_EPSILON) : (cm == 0.f);
     cmin = fminf(cmin, cm);
   }
@@ -676,20 +692,87 @@ __global__ void __launch_bounds__(kPatchThreads) enc_pass2_patch_kernel(const En
 #pragma unroll
   for (int w = 0; w < kPatchThreads / 32; ++w) { cmin = fminf(cmin, s_cmin[w]); wide |= s_wide[w] != 0; }
 
+  // first level, one thread per warp of pass 1: can the warp reach the smallest column maximum at all?
   const int wr = blockIdx.y * kPatchThreads + tid;
   bool cand = false;
+  float my_reach = 0.f;
   if (wr < nwarps) {
     const float wb = A.wbest[(int64_t)b * nwarps + wr];
-    const float reach = MINING ? fadd(wb, 2.f * FLT_EPSILON) : wb;
-    cand = wide || (reach >= cmin);
+    my_reach = MINING ? fadd(wb, 2.f * FLT_EPSILON) : wb;
+    cand = wide || (my_reach >= cmin);
   }
-  if (cand) s_list[atomicAdd(&s_n, 1)] = wr;
+  if (cand) {
+    const int pos = atomicAdd(&s_n, 1);
+    s_list[pos] = wr;
+    s_reach[pos] = my_reach;
+    s_wbox[pos] = A.wbox[wr];                                 // (all candidates of the CTA in one round trip)
+    s_flag[pos] = wide ? 1 : 0;
+  }
   __syncthreads();
   const int n_list = s_n;
+  if (n_list == 0) return;                                   // (CTA-uniform)
 
-  for (int i = warp; i < n_list; i += kPatchThreads / 32) {
-    const int a = s_list[i] * 32 + lane;
+  // second level, still without touching the anchors: is there a GT whose column maximum the warp can reach AND whose
+  // box meets the warp's bounding box?  A warp tests 32 GTs per step for each of its list entries.
+  if (!wide) {
+    for (int c0 = 0; c0 < ig.m_eff; c0 += kPatchGt) {
+      const int mc = min(kPatchGt, ig.m_eff - c0);
+      if (!staged) {
+        __syncthreads();
+        for (int k = tid; k < mc; k += kPatchThreads) {
+          s_box[k] = gt_box(A, ig, c0 + k);
+          s_cm[k] = __uint_as_float(A.colmax[ig.slot0 + c0 + k]);
+        }
+        __syncthreads();
+      }
+      for (int i = warp; i < n_list; i += kPatchThreads / 32) {
+        if (s_flag[i]) continue;                             // (warp-uniform)
+        const float reach_w = s_reach[i];
+        const float4 wq = s_wbox[i];
+        const WarpBox wrec = {wq.x, wq.y, wq.z, wq.w};
+        bool any = false;
+        for (int k0 = 0; k0 < mc && !any; k0 += 32) {
+          const int k = k0 + lane;
+          any = __any_sync(0xffffffffu, (k < mc) && (s_cm[k] <= reach_w) && may_hit(wrec, s_box[k]));
+        }
+        if (any && lane == 0) s_flag[i] = 1;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  // the flagged warps go to the batch-wide work queue of enc_pass2_apply_kernel: they cluster in a few CTAs (the coarse
+  // pyramid levels meet every GT), and each costs a chain of dependent loads, so they are spread over the whole GPU
+  const bool flagged = tid < n_list && s_flag[tid] != 0;
+  const unsigned fm = __ballot_sync(0xffffffffu, flagged);
+  if (fm != 0u) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(A.queue_n, __popc(fm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flagged) A.queue[base + __popc(fm & ((1u << lane) - 1u))] = make_int2(b, s_list[tid]);
+  }
+}
+
+// third level of pass 2: one warp per queued (image, warp of pass 1): load the anchors, evaluate the GTs the warp can
+// reach, and if an anchor really ties with (mining) / is claimed by (dual) a GT, evaluate the full row again - the row
+// maximum decides what stage 1 had written - and rewrite the outputs of the anchors whose match changed.
+template <bool MINING>
+__global__ void __launch_bounds__(kPatchThreads) enc_pass2_apply_kernel(const EncArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (A.n + 31) >> 5;
+  const bool need_haspos = !MINING && !A.gt_max_first;
+  const int total = *A.queue_n;
+  const int wstride = gridDim.x * (kPatchThreads / 32);
+  for (int e = blockIdx.x * (kPatchThreads / 32) + (threadIdx.x >> 5); e < total; e += wstride) {
+    const int2 q = A.queue[e];
+    const int b = q.x;
+    const ImageGt ig = image_gt<false>(A, b);
+    auto box_at = [&](int k) { return gt_box(A, ig, k); };
+    auto cm_at = [&](int k) { return __uint_as_float(__ldg(A.colmax + ig.slot0 + k)); };
+    const int a = q.y * 32 + lane;
     const bool valid = a < A.n;
+    const float wb = A.wbest[(int64_t)b * nwarps + q.y];
+    const float reach_w = MINING ? fadd(wb, 2.f * FLT_EPSILON) : wb;
     AnchorBox ab = {};
     bool active = false;
     if (valid) {
@@ -697,6 +780,36 @@ __global__ void __launch_bounds__(kPatchThreads) enc_pass2_patch_kernel(const En
       active = (A.mask == nullptr) || (A.mask[a] != 0);
     }
     const WarpBox wbx = warp_bbox(active, ab);
+    // the GTs the warp can reach: does any anchor really tie with / get claimed by one?
+    bool tie = false;
+    for (int k0 = 0; k0 < ig.m_eff; k0 += 32) {
+      const int k = k0 + lane;
+      bool test = false;
+      float cmk = 0.f;
+      float4 gk = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < ig.m_eff) {
+        cmk = cm_at(k);
+        gk = box_at(k);
+        const bool widek = MINING ? (cmk < FLT_EPSILON) : (cmk == 0.f);
+        test = widek || (cmk <= reach_w && may_hit(wbx, gk));
+      }
+      unsigned hits = __ballot_sync(0xffffffffu, test);
+      while (hits) {
+        const int kl = __ffs(hits) - 1;
+        const int kk = k0 + kl;
+        hits &= hits - 1;
+        const float4 g = make_float4(__shfl_sync(0xffffffffu, gk.x, kl), __shfl_sync(0xffffffffu, gk.y, kl),
+                                     __shfl_sync(0xffffffffu, gk.z, kl), __shfl_sync(0xffffffffu, gk.w, kl));
+        const float cm = __shfl_sync(0xffffffffu, cmk, kl);
+        bool hit = false;
+        float ov = 0.f;
+        if (active) ov = pair_iou(ab.my0, ab.mx0, ab.my1, ab.mx1, ab.marea, g.x, g.y, g.z, g.w, box_area(g.x, g.y, g.z, g.w), hit);
+        if (MINING) tie |= fabsf(fsub(ov, cm)) < FLT_EPSILON;
+        else tie |= (ov == cm) && (!need_haspos || A.haspos[ig.slot0 + kk] == 0);
+      }
+    }
+    if (!__any_sync(0xffffffffu, tie && valid)) continue;
+    // the full row again, then the patch
     RowState s;
     s.best = 0.f; s.best_gt = 0; s.ov0 = 0.f;
     s.claimed = false; s.cbest = 0.f; s.cbest_gt = 0;
@@ -705,17 +818,20 @@ __global__ void __launch_bounds__(kPatchThreads) enc_pass2_patch_kernel(const En
       const int k = k0 + lane;
       bool test = false;
       float cmk = 0.f;
+      float4 gk = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < ig.m_eff) {
-        cmk = __uint_as_float(A.colmax[ig.slot0 + k]);
+        cmk = cm_at(k);
+        gk = box_at(k);
         const bool widek = MINING ? (cmk < FLT_EPSILON) : (cmk == 0.f);
-        test = may_hit(wbx, gt_box(A, ig, k)) || widek;
+        test = may_hit(wbx, gk) || widek;
       }
       unsigned hits = __ballot_sync(0xffffffffu, test);
       while (hits) {
         const int kl = __ffs(hits) - 1;
         const int kk = k0 + kl;
         hits &= hits - 1;
-        const float4 g = gt_box(A, ig, kk);
+        const float4 g = make_float4(__shfl_sync(0xffffffffu, gk.x, kl), __shfl_sync(0xffffffffu, gk.y, kl),
+                                     __shfl_sync(0xffffffffu, gk.z, kl), __shfl_sync(0xffffffffu, gk.w, kl));
         const float cm = __shfl_sync(0xffffffffu, cmk, kl);
         bool hit = false;
         float ov = 0.f;
@@ -741,7 +857,7 @@ __global__ void __launch_bounds__(kPatchThreads) enc_pass2_patch_kernel(const En
       else { match = 0; score = s.ov0; }
     }
     if (match != match1 || score != s.best)
-      write_positive(A, (int64_t)b * A.n + a, ab, gt_box(A, ig, match), score, match);
+      write_positive(A, (int64_t)b * A.n + a, ab, box_at(match), score, match);
   }
 }
 
@@ -1101,7 +1217,7 @@ __global__ void fill_empty_match_kernel(int32_t* match, float* scores, int n) {
 // host side
 // ---------------------------------------------------------------------------
 struct WsLayout {
-  size_t colmax, cnt, haspos, fill, zero_bytes, bucket, spill, wbest, total;
+  size_t colmax, cnt, haspos, fill, queue_n, zero_bytes, bucket, spill, wbest, wbox, queue, total;
 };
 
 static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
@@ -1111,10 +1227,13 @@ static WsLayout ws_layout(int64_t n, int64_t batch, int64_t slots) {
   w.cnt = off;    off += align_up(slots * 4, 256);
   w.haspos = off; off += align_up(slots * 4, 256);
   w.fill = off;   off += align_up(slots * 4, 256);
+  w.queue_n = off; off += 256;
   w.zero_bytes = off;
   w.bucket = off; off += align_up(slots * kBucketCap * sizeof(HeapItem), 256);
   w.spill = off;  off += align_up(batch * 2 * n * sizeof(HeapItem), 256);
   w.wbest = off;  off += align_up(batch * ((n + 31) / 32) * 4, 256);
+  w.wbox = off;   off += align_up(((n + 31) / 32) * 16, 256);
+  w.queue = off;  off += align_up(batch * ((n + 31) / 32) * 8, 256);
   w.total = off;
   return w;
 }
@@ -1139,6 +1258,9 @@ static void bind_workspace(EncArgs& A, void* workspace, const WsLayout& w) {
   A.bucket = reinterpret_cast<HeapItem*>(base + w.bucket);
   A.spill = reinterpret_cast<HeapItem*>(base + w.spill);
   A.wbest = reinterpret_cast<float*>(base + w.wbest);
+  A.wbox = reinterpret_cast<float4*>(base + w.wbox);
+  A.queue_n = reinterpret_cast<int32_t*>(base + w.queue_n);
+  A.queue = reinterpret_cast<int2*>(base + w.queue);
 }
 
 // ev (optional, 4 events): recorded before pass 1 and after each pass, for the profile entry point
@@ -1166,8 +1288,14 @@ static int run_passes(const EncArgs& A, bool mining, bool need_row, int batch, c
     else enc_pass2_kernel<true, false><<<grid, kEncThreads, 0, st>>>(A);
   } else {
     const dim3 pgrid(batch, ((A.n + 31) / 32 + kPatchThreads - 1) / kPatchThreads);
-    if (mining) enc_pass2_patch_kernel<true><<<pgrid, kPatchThreads, 0, st>>>(A);
-    else enc_pass2_patch_kernel<false><<<pgrid, kPatchThreads, 0, st>>>(A);
+    const int agrid = 148 * 4;                           // the queue is walked by a fixed grid (its length is only known on the device)
+    if (mining) {
+      enc_pass2_find_kernel<true><<<pgrid, kPatchThreads, 0, st>>>(A);
+      enc_pass2_apply_kernel<true><<<agrid, kPatchThreads, 0, st>>>(A);
+    } else {
+      enc_pass2_find_kernel<false><<<pgrid, kPatchThreads, 0, st>>>(A);
+      enc_pass2_apply_kernel<false><<<agrid, kPatchThreads, 0, st>>>(A);
+    }
   }
   DAN_LAUNCH_CHECK("enc_pass2_kernel");
   if (ev) DAN_CUDA(cudaEventRecord(ev[2], st));

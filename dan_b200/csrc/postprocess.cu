@@ -1,7 +1,7 @@
 // K3-K5: the evaluation half of the path -- utility/bbox_util.py:103-119
 // parse_by_class and its pieces, batched over images and classes.
 //
-//   pp_filter2_kernel  (two classes) / pp_filter_kernel (any number of classes)
+//   pp_filter_kernel   (more than two classes; for two classes the NMS kernel filters its own image)
 //                      softmax -> select(threshold) -> decode -> clip -> min-size;
 //                      survivors are COMPACTED as 64-bit keys
 //                      (ordered score bits << 32 | ~anchor index).  The reference
@@ -31,6 +31,10 @@ __device__ long long g_phase[32];
 #define DAN_PHASE(slot) do { } while (0)
 #endif
 
+#ifndef DAN_PP_THREADS
+#define DAN_PP_THREADS 1024           // threads of the per-list kernels (512 was measured: +20 % latency, no gain from sharing the SM
+#endif                                // with the encode CTAs)
+#define DAN_SORT_THREADS DAN_PP_THREADS
 #include "sort.cuh"
 
 struct PpArgs {
@@ -55,6 +59,7 @@ struct PpArgs {
   // workspace
   unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
   int32_t* key_count;         // [L]
+  int32_t* maybe;             // [L, n] anchors that pass the quick reject (fused filter; beyond shared memory)
   float* s_scores;            // sort_bboxes outputs [keep_topk]
   float4* s_boxes;
   int32_t* s_index;
@@ -256,23 +261,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const PpArgs
 }
 
 // ---------------------------------------------------------------------------
-// K4+K5: one CTA per (image, class) list does everything after the filter:
-//   1. top-k select + sort of the surviving keys in shared memory (select_and_sort above);
-//   2. decode + clip + normalise the K best boxes into shared memory;
-//   3. broad phase: boxes are binned by size class (max side in [2^c, 2^(c+1))) and by the cell of their centre in a
-//      per-class uniform grid whose cell is as large as the class's boxes, so that a box only has to look at <= 3x3
-//      cells per class to find everything it can overlap (counting sort in shared memory);
-//   4. narrow phase: tf.image.non_max_suppression's IoU test (no +1, corners min/max normalised, area <= 0 never
-//      suppresses, strict >) on those few candidates; every pair (lo, hi) with lo ranked above hi and IoU > thr
-//      becomes an edge "lo suppresses hi if lo is kept".  ~K*6 edges instead of K*K/2 tests;
-//   5. greedy NMS == evaluation of the DAG  kept(i) = !any(kept(j) : edge j -> i)  in rank order.  It is evaluated by
-//      parallel relaxation over the edges: a box is decided as soon as one suppressor is known kept (suppressed) or
-//      all of them are known suppressed (kept).  The number of sweeps is the longest dependency chain (6 for the
-//      benchmark detections), not K;
-//   6. the first nms_topk kept boxes in rank order are written out, zero padded (bbox_util.py:80-90); this is what
-//      TF's sequential loop selects because a decision never depends on lower ranked boxes.
-// Fallback (more edges than fit, or a negative threshold where even disjoint boxes suppress): rounds of 64
-// candidates tested against the kept list in shared memory, resolved serially per round (nms_rounds below).
+// pair tests of tf.image.non_max_suppression (shared by the NMS kernel below)
 // ---------------------------------------------------------------------------
 struct NmsBox {
   float y0, x0, y1, x1, area;
@@ -288,8 +277,10 @@ DAN_D NmsBox nms_norm(float4 b) {
   return r;
 }
 
-// IOUGreaterThanThreshold of TF's non_max_suppression_op.cc for normalised boxes
-DAN_D bool nms_suppresses(float4 a, float a_area, float4 b, float b_area, float thr) {
+// IOUGreaterThanThreshold of TF's non_max_suppression_op.cc for normalised boxes.  Kept out of line: the callers reach
+// it only when a pair is within 1e-6 of the threshold (or the threshold is negative), and the chunk loop of the NMS
+// kernel has to stay small enough for the instruction cache.
+__device__ __noinline__ bool nms_suppresses(float4 a, float a_area, float4 b, float b_area, float thr) {
   if (a_area <= 0.f || b_area <= 0.f) return false;
   const float h = fmaxf(fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
   const float w = fmaxf(fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
@@ -301,98 +292,25 @@ DAN_D bool nms_suppresses(float4 a, float a_area, float4 b, float b_area, float 
 // same predicate; for thr >= 0 disjoint boxes are rejected first and the division is only evaluated when
 // inter / union is within 1e-6 (relative) of the threshold
 DAN_D bool pair_suppresses(const float4& a, float a_area, const float4& b, float b_area, float thr) {
-  if (thr < 0.f) return nms_suppresses(a, a_area, b, b_area, thr);
-  const float h = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
-  const float w = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
-  if (!(h > 0.f && w > 0.f)) return false;
-  if (!(a_area > 0.f && b_area > 0.f)) return false;
-  const float inter = fmul(h, w);
-  const float uni = fsub(fadd(a_area, b_area), inter);
-  const float t = fmul(thr, uni);
-  if (t > 1e-30f && inter > fmul(t, 1.000001f)) return true;
-  if (t > 1e-30f && inter < fmul(t, 0.999999f)) return false;
-  return fdiv(inter, uni) > thr;
+  if (thr >= 0.f) {
+    const float h = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float w = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (!(h > 0.f && w > 0.f)) return false;
+    if (!(a_area > 0.f && b_area > 0.f)) return false;
+    const float inter = fmul(h, w);
+    const float t = fmul(thr, fsub(fadd(a_area, b_area), inter));
+    if (t > 1e-30f) {
+      if (inter > fmul(t, 1.000001f)) return true;
+      if (inter < fmul(t, 0.999999f)) return false;
+    }
+  }
+  return nms_suppresses(a, a_area, b, b_area, thr);
 }
 
-// ---------------------------------------------------------------------------
-// K3 for two classes (one list per image): the logits of the whole batch are ONE flat array of (background, face)
-// pairs.  Every lane streams 16-byte vectors (two anchors) with kF2Vec loads in flight, rejects on the logit
-// difference alone, and only the ~3 % possible survivors of the CTA are collected in shared memory and run through
-// the exact path (softmax in tf.nn.softmax's op order, threshold, decode, clip, min-size) on dense warps.
-// ---------------------------------------------------------------------------
-constexpr int kF2Threads = 256;
-constexpr int kF2Vec = 4;                                  // 16-byte loads per thread = 8 anchors
-
+// two classes: softmax_1 = sigmoid(x1 - x0); an anchor whose logit difference is more than 0.05 below logit(threshold)
+// cannot pass (the fp32 evaluation is accurate to ~1e-6 relative), so ~97 % of the anchors leave after one subtraction
 DAN_D bool f2_maybe(const PpArgs& A, float x0, float x1) {
   return !(fsub(x1, x0) < A.reject_below) || fabsf(x0) > 1e5f || fabsf(x1) > 1e5f;
-}
-
-__global__ void __launch_bounds__(kF2Threads) pp_filter2_kernel(const PpArgs A) {
-  __shared__ int s_list[kF2Threads * kF2Vec * 2];
-  __shared__ int s_n;
-  const int tid = threadIdx.x;
-  const int64_t total = (int64_t)A.batch * A.n;            // anchors of the batch
-  const int64_t vecs = total >> 1;
-  const int64_t v0 = (int64_t)blockIdx.x * (kF2Threads * kF2Vec) + tid;
-  if (tid == 0) s_n = 0;
-  float4 x[kF2Vec];
-#pragma unroll
-  for (int u = 0; u < kF2Vec; ++u) {
-    const int64_t v = v0 + u * kF2Threads;
-    x[u] = (v < vecs) ? __ldcs(reinterpret_cast<const float4*>(A.cls) + v) : make_float4(0.f, 0.f, 0.f, 0.f);   // read once
-  }
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < kF2Vec; ++u) {
-    const int64_t v = v0 + u * kF2Threads;
-    if (v < vecs) {
-      if (f2_maybe(A, x[u].x, x[u].y)) s_list[atomicAdd(&s_n, 1)] = (int)(2 * v);
-      if (f2_maybe(A, x[u].z, x[u].w)) s_list[atomicAdd(&s_n, 1)] = (int)(2 * v + 1);
-    }
-  }
-  if ((total & 1) && blockIdx.x == gridDim.x - 1 && tid == 0) {      // odd tail of the flat array
-    const float x0 = A.cls[2 * (total - 1)], x1 = A.cls[2 * (total - 1) + 1];
-    if (f2_maybe(A, x0, x1)) s_list[atomicAdd(&s_n, 1)] = (int)(total - 1);
-  }
-  __syncthreads();
-  const int cnt = s_n;
-  for (int i0 = 0; i0 < cnt; i0 += kF2Threads) {           // CTA-uniform trip count
-    const int i = i0 + tid;
-    bool pass = false;
-    int b = 0, a = 0;
-    float p = 0.f;
-    if (i < cnt) {
-      const int g = s_list[i];
-      b = g / A.n;
-      a = g - b * A.n;
-      const float2 xx = *reinterpret_cast<const float2*>(A.cls + 2 * (int64_t)g);
-      // tf.nn.softmax: exp(x - max) * (1 / sum(exp(x - max))), sum in class order
-      const float mx = fmaxf(xx.x, xx.y);
-      const float e0 = cephes_expf(fsub(xx.x, mx));
-      const float e1 = cephes_expf(fsub(xx.y, mx));
-      const float inv = fdiv(1.f, fadd(e0, e1));
-      p = fmul(e1, inv);
-      if (p > A.select_thr) {                              // select_bboxes :24-36
-        const float4 box = pp_box(A, b, a);
-        const float w = fadd(fsub(box.w, box.y), 1.f);     // filter_bboxes :50-59
-        const float h = fadd(fsub(box.z, box.x), 1.f);
-        pass = (w > A.min_size_p1) && (h > A.min_size_p1);
-      }
-    }
-    // one atomic per (warp, image): the survivors of a warp belong to one or two images
-    const unsigned active = __ballot_sync(0xffffffffu, pass);
-    if (pass) {
-      const unsigned peers = __match_any_sync(active, b);
-      const int leader = __ffs(peers) - 1;
-      const int lane = tid & 31;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(A.key_count + b, __popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      const int pos = base + __popc(peers & ((1u << lane) - 1u));
-      A.keys[(int64_t)b * A.n + pos] =
-          ((unsigned long long)score_to_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -401,9 +319,10 @@ __global__ void __launch_bounds__(kF2Threads) pp_filter2_kernel(const PpArgs A) 
 //   2. decode + clip + normalise the K best boxes (shared memory, or the workspace for very long lists);
 //   3. greedy NMS exactly as tf.image.non_max_suppression runs it - a candidate is tested against the boxes KEPT so
 //      far, never against all earlier candidates - but kChunk candidates at a time:
-//        a. every candidate of the chunk against the kept list (one warp per candidate, lanes over the kept boxes,
-//           the warp leaves at the first suppressor): final for the candidates it suppresses, because the kept list
-//           only grows;
+//        a. every candidate of the chunk against the kept list, which is indexed by 32 x 32 stripes of the image
+//           (bitsets over the kept boxes, see the kernel): a candidate only meets the few kept boxes that share a
+//           stripe with it on both axes and leaves at the first suppressor.  Final for the candidates it suppresses,
+//           because the kept list only grows;
 //        b. the survivors are compacted in rank order;
 //        c. their mutual suppression bits T[v] = { u < v : IoU(u, v) > thr } (<= kChunk^2 / 2 tests);
 //        d. kept(v) = no kept u in T[v], evaluated by relaxation (a survivor is decided once one of its suppressors is
@@ -412,14 +331,14 @@ __global__ void __launch_bounds__(kF2Threads) pp_filter2_kernel(const PpArgs A) 
 //        e. the kept survivors are appended to the kept list in rank order; the loop ends when nms_topk boxes are kept
 //           (max_output_size) or the candidates run out.
 //      The detections of a trained detector are clusters of near duplicates around each face: almost every candidate
-//      is removed in step a by its cluster's head after a few tests, so the work is ~K * kept / 64 warp steps instead
-//      of the K^2 / 2 pair tests of a suppression matrix.
+//      is removed in step a by its cluster's head after one or two exact tests, instead of the K^2 / 2 pair tests of a
+//      suppression matrix.
 //   4. the first nms_topk kept boxes are written out in rank order, zero padded (bbox_util.py:80-90).
 // ---------------------------------------------------------------------------
 constexpr int kChunk = 256;
 constexpr int kChunkWords = kChunk / 32;
 constexpr int kMaxSweeps = 12;
-constexpr size_t kGreedySmemMax = 200 * 1024;          // dynamic part (the kernel has ~20 KB of static shared memory)
+constexpr size_t kGreedySmemMax = 186 * 1024;          // dynamic part (the kernel has ~38 KB of static shared memory)
 
 struct GreedyPlan {
   size_t smem;          // dynamic shared memory
@@ -467,7 +386,7 @@ DAN_D void block_minmax(float lo, float hi, float& out_lo, float& out_hi) {
   const int wh = __reduce_max_sync(0xffffffffu, float_to_ordered(hi));
   if (lane == 0) { s_lo[warp] = wl; s_hi[warp] = wh; }
   __syncthreads();
-  int a = s_lo[lane], b = s_hi[lane];
+  int a = (lane < kSortThreads / 32) ? s_lo[lane] : 0x7fffffff, b = (lane < kSortThreads / 32) ? s_hi[lane] : (int)0x80000000;
   a = __reduce_min_sync(0xffffffffu, a);
   b = __reduce_max_sync(0xffffffffu, b);
   out_lo = ordered_to_float(a);
@@ -513,8 +432,35 @@ DAN_D bool bar_or_chunk(bool pred) {
 // WHERE: 0 = candidates and kept list in shared memory (the usual case), 1 = candidates in the workspace, 2 = both in the
 // workspace (very long lists).  A template parameter rather than a run-time pointer choice so that the shared-memory
 // accesses compile to LDS / STS / ATOMS instead of generic-address instructions.
-template <bool DECODE, int WHERE>
-__global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArgs A, const float* __restrict__ src_scores,
+// A dependency chain longer than kMaxSweeps inside a chunk: one warp finishes the chunk serially (when it reaches an
+// undecided survivor every earlier one is decided); lane w holds word w of the masks.  Out of line (rare).
+__device__ __noinline__ void resolve_chunk_serially(const uint32_t* T, uint32_t* keptm, uint32_t* supm, int ns) {
+  const int lane = threadIdx.x & 31;
+  uint32_t kw = (lane < kChunkWords) ? keptm[lane] : 0u;
+  uint32_t sw = (lane < kChunkWords) ? supm[lane] : 0u;
+  for (int v = 0; v < ns; ++v) {
+    const int w = v >> 5;
+    const uint32_t bit = 1u << (v & 31);
+    const uint32_t known = __shfl_sync(0xffffffffu, kw | sw, w);
+    if (known & bit) continue;                 // warp-uniform
+    const uint32_t t = (lane < kChunkWords && (lane << 5) < v) ? T[v * kChunkWords + lane] : 0u;
+    const bool hit = __any_sync(0xffffffffu, (t & kw) != 0u);
+    if (lane == w) {
+      if (hit) sw |= bit;
+      else kw |= bit;
+    }
+  }
+  if (lane < kChunkWords) { keptm[lane] = kw; supm[lane] = sw; }
+}
+
+// FILTER (two classes, one list per image): the CTA also runs K3 for its image - it streams the image's logits, keeps
+// the indices of the few anchors the quick reject lets through, runs them through the exact path (softmax in
+// tf.nn.softmax's op order, threshold, decode, clip, min-size) on dense warps, and the surviving keys land directly in
+// the shared memory the sort works in: no filter launch, no key list in HBM, no global atomics.
+constexpr int kMaybeCap = 4096;                        // indices kept in shared memory (the rest goes to the workspace)
+
+template <bool DECODE, int WHERE, bool FILTER>
+__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) nms_greedy_kernel(const PpArgs A, const float* __restrict__ src_scores,
                                                                      const float4* __restrict__ src_boxes) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ SortScratch sc;
@@ -526,6 +472,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
   __shared__ uint32_t s_keptm[kChunkWords], s_supm[kChunkWords];
   __shared__ uint2 s_smask[kChunk];
   __shared__ int s_wcnt[kChunkWords];
+  __shared__ int s_next[2];                             // work counters of steps a and c
   __shared__ int s_ns;
 
   const int list = blockIdx.x;
@@ -534,7 +481,6 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
   const int warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int b = list / max(A.num_classes - 1, 1);
-  const int cnt = min(A.key_count[list], A.n);
   const int64_t o = (int64_t)list * A.keep_topk;
   const float thr = A.nms_thr;
 
@@ -576,26 +522,95 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
   uint32_t* xs = stripes;
   uint32_t* ys = stripes + 32 * wcap;
 
-  // ---- 1. top-k + sort
+  // ---- 0. filter (FILTER) or the number of keys the filter kernel left in the workspace
   DAN_PHASE(0);
-  const int K = min(select_and_sort(A.keys + (int64_t)list * A.n, cnt, min(A.keep_topk, cnt), keys, sc), A.keep_topk);
+  unsigned long long* gkeys = A.keys + (int64_t)list * A.n;
+  int cnt;
+  if (FILTER) {
+    __shared__ int s_maybe[kMaybeCap];
+    __shared__ int s_nmaybe, s_nkeys;
+    int* gmaybe = A.maybe + (int64_t)list * A.n;
+    const int key_cap = A.sort_bytes / 8;              // keys that fit the sort's shared memory
+    if (tid == 0) { s_nmaybe = 0; s_nkeys = 0; }
+    __syncthreads();
+    auto push = [&](int a) {
+      const int pos = atomicAdd(&s_nmaybe, 1);
+      if (pos < kMaybeCap) s_maybe[pos] = a;
+      else gmaybe[pos] = a;
+    };
+    // the image's logits as 16-byte vectors (two anchors); the row of an image starts 8-byte aligned only
+    const float* x = A.cls + (int64_t)b * A.n * 2;
+    const int head = (reinterpret_cast<uintptr_t>(x) & 15u) ? 1 : 0;
+    const int nvec = (A.n - head) >> 1;
+    const float4* xv = reinterpret_cast<const float4*>(x + 2 * head);
+    for (int v0 = 0; v0 < nvec; v0 += 4 * kSortThreads) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * kSortThreads + tid;
+        q[u] = (v < nvec) ? __ldcs(xv + v) : make_float4(0.f, 0.f, 0.f, 0.f);       // read once: streaming
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * kSortThreads + tid;
+        if (v < nvec) {
+          if (f2_maybe(A, q[u].x, q[u].y)) push(head + 2 * v);
+          if (f2_maybe(A, q[u].z, q[u].w)) push(head + 2 * v + 1);
+        }
+      }
+    }
+    if (tid == 0 && head == 1 && f2_maybe(A, x[0], x[1])) push(0);
+    if (tid == 1 && head + 2 * nvec < A.n && f2_maybe(A, x[2 * (A.n - 1)], x[2 * (A.n - 1) + 1])) push(A.n - 1);
+    __syncthreads();
+    const int nmaybe = s_nmaybe;
+    for (int i0 = 0; i0 < nmaybe; i0 += kSortThreads) {
+      const int i = i0 + tid;
+      if (i < nmaybe) {
+        const int a = (i < kMaybeCap) ? s_maybe[i] : gmaybe[i];
+        const float2 xx = *reinterpret_cast<const float2*>(x + 2 * a);
+        // tf.nn.softmax: exp(x - max) * (1 / sum(exp(x - max))), sum in class order
+        const float mx = fmaxf(xx.x, xx.y);
+        const float e0 = cephes_expf(fsub(xx.x, mx));
+        const float e1 = cephes_expf(fsub(xx.y, mx));
+        const float pr = fmul(e1, fdiv(1.f, fadd(e0, e1)));
+        if (pr > A.select_thr) {                            // select_bboxes :24-36
+          const float4 box = pp_box(A, b, a);
+          const float w = fadd(fsub(box.w, box.y), 1.f);    // filter_bboxes :50-59
+          const float h = fadd(fsub(box.z, box.x), 1.f);
+          if ((w > A.min_size_p1) && (h > A.min_size_p1)) {
+            const unsigned long long key = ((unsigned long long)score_to_key(pr) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+            const int pos = atomicAdd(&s_nkeys, 1);
+            if (pos < key_cap) keys[pos] = key;
+            else gkeys[pos] = key;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    cnt = s_nkeys;
+    if (cnt > kSortCap) {                                   // too many survivors for shared memory: the select runs on HBM
+      for (int i = tid; i < min(cnt, key_cap); i += kSortThreads) gkeys[i] = keys[i];
+      __syncthreads();
+    }
+  } else {
+    cnt = min(A.key_count[list], A.n);
+  }
+
+  // ---- 1. top-k + sort
+  DAN_PHASE(8);
+  const int K = min(select_and_sort(gkeys, cnt, min(A.keep_topk, cnt), keys, sc, FILTER), A.keep_topk);
   DAN_PHASE(1);
 
-  // ---- 2. decode + clip + normalise.  The candidate boxes reuse the shared memory of the keys: every thread first
-  // takes its (<= 8) keys into registers.
-  unsigned long long myk[kSortCap / kSortThreads];
-#pragma unroll
-  for (int e = 0; e < kSortCap / kSortThreads; ++e) {
-    const int r = tid + e * kSortThreads;
-    myk[e] = (r < K) ? keys[r] : 0ull;
-    if (r < K) A.s_key[o + r] = myk[e];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int e = 0; e < kSortCap / kSortThreads; ++e) {
-    const int r = tid + e * kSortThreads;
+  // ---- 2. decode + clip + normalise.  The candidate boxes (16 B) reuse the shared memory of the keys (8 B): the ranks
+  // are walked in DEscending batches of one key per thread, so a batch's boxes only overwrite key slots of ranks that
+  // are already done (box r covers key slots 2r and 2r+1 >= r); the barrier protects the batch's own keys.
+  for (int r0 = K > 0 ? ((K - 1) / kSortThreads) * kSortThreads : -1; r0 >= 0; r0 -= kSortThreads) {
+    const int r = r0 + tid;
+    const unsigned long long key = (r < K) ? keys[r] : 0ull;
+    if (r < K) A.s_key[o + r] = key;
+    __syncthreads();
     if (r < K) {
-      const uint32_t idx = key_index(myk[e]);
+      const uint32_t idx = key_index(key);
       const NmsBox nb = nms_norm(DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx]);
       cbox[r] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
       carea[r] = nb.area;
@@ -606,16 +621,18 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
 
   // ---- 3. greedy NMS, kChunk candidates per round
 #ifdef DAN_PHASE_TIMING
-  long long acc[5] = {0, 0, 0, 0, 0}, t_a = 0, n_sweeps = 0, n_surv = 0, n_chunks = 0;
+  long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_a = 0, t_b = 0, n_sweeps = 0, n_surv = 0, n_chunks = 0;
+#define DAN_LAP(i) do { const long long now__ = clock64(); acc[i] += now__ - t_b; t_b = now__; } while (0)
 #define DAN_TICK() (t_a = clock64())
 #define DAN_TOCK(i) (acc[i] += clock64() - t_a)
 #else
 #define DAN_TICK() do { } while (0)
 #define DAN_TOCK(i) do { } while (0)
+#define DAN_LAP(i) do { } while (0)
 #endif
   // Broad phase: the extent of the candidates is cut into 32 stripes per axis and every box carries the two 32-bit masks
-  // of the stripes it touches.  Boxes that intersect share a stripe on both axes, so a pair whose masks do not meet is
-  // skipped after two ANDs; the (few) pairs that pass are queued and run through the exact test on dense warps.
+  // of the stripes it touches.  Boxes that intersect share a stripe on both axes, so a pair whose masks do not meet on
+  // either axis needs no exact test.
   Stripes sg;
   {
     float ylo = 3.0e38f, yhi = -3.0e38f, xlo = 3.0e38f, xhi = -3.0e38f;
@@ -635,6 +652,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
   }
   for (int r = tid; r < K; r += kSortThreads) cmask[r] = sg.masks(cbox[r], carea[r]);
   for (int i = tid; i < 64 * wcap; i += kSortThreads) stripes[i] = 0u;
+  if (tid < 2) s_next[tid] = 0;
   __syncthreads();
   int L = 0;                                           // kept boxes so far (CTA-uniform)
   for (int c0 = 0; c0 < K && L < A.nms_topk; c0 += kChunk) {
@@ -650,7 +668,11 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
       const int cpw = 32 / G;                                // candidates per warp pass
       const int gl = lane & (G - 1), sub = lane / G;
       const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (sub * G);
-      for (int r0 = warp * cpw; r0 < nc; r0 += (kSortThreads / 32) * cpw) {
+      while (true) {                                         // candidates are handed out dynamically: their cost varies a lot
+        int r0 = 0;
+        if (lane == 0) r0 = atomicAdd(&s_next[0], cpw);
+        r0 = __shfl_sync(0xffffffffu, r0, 0);
+        if (r0 >= nc) break;
         const int r = r0 + sub;
         const bool have = r < nc;
         const float4 me = have ? cbox[c0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -660,10 +682,14 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
         for (int wb = 0; wb < W; wb += G) {                  // one block of words unless the kept list is very long
           const int w = wb + gl;
           uint32_t poss = 0u;
-          if (w < W) {
+          if (w < W && mm.x != 0u && mm.y != 0u) {
+            // (the stripes of a box are a contiguous range: independent loads, no address chain)
             uint32_t ax = 0u, ay = 0u;
-            for (uint32_t m = mm.x; m != 0u; m &= m - 1u) ax |= xs[(__ffs(m) - 1) * wcap + w];
-            for (uint32_t m = mm.y; m != 0u; m &= m - 1u) ay |= ys[(__ffs(m) - 1) * wcap + w];
+            const int xe = 31 - __clz(mm.x), ye = 31 - __clz(mm.y);
+#pragma unroll 2
+            for (int st = __ffs(mm.x) - 1; st <= xe; ++st) ax |= xs[st * wcap + w];
+#pragma unroll 2
+            for (int st = __ffs(mm.y) - 1; st <= ye; ++st) ay |= ys[st * wcap + w];
             poss = ax & ay;
           }
           while (__any_sync(0xffffffffu, poss != 0u && !sup)) {
@@ -686,11 +712,16 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
     DAN_TICK();
     // b. survivors in rank order (the first kChunk threads, named barrier 1)
     if (tid < kChunk) {
+#ifdef DAN_PHASE_TIMING
+      t_b = clock64();
+#endif
       const bool f = (tid < nc) && (s_flag[tid] == 0);
       const unsigned m = __ballot_sync(0xffffffffu, f);
       if (lane == 0) s_wcnt[warp] = __popc(m);
       if (tid < kChunkWords) { s_keptm[tid] = 0u; s_supm[tid] = 0u; }
+      DAN_LAP(5);
       bar_sync_chunk();
+      DAN_LAP(6);
       int base = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < kChunkWords; ++w) {
@@ -708,13 +739,19 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
         s_smask[u] = cmask[c0 + tid];
       }
       if (tid == 0) s_ns = total;
+      DAN_LAP(7);
     }
     __syncthreads();
     const int ns = s_ns;
     DAN_TOCK(1);
     DAN_TICK();
     // c. suppression bits among the survivors: warp -> row v, lanes -> 32 earlier survivors per step
-    for (int v = warp; v < ns; v += kSortThreads / 32) {
+    while (true) {                                           // rows handed out dynamically, the longest ones first
+      int vi = 0;
+      if (lane == 0) vi = atomicAdd(&s_next[1], 1);
+      vi = __shfl_sync(0xffffffffu, vi, 0);
+      if (vi >= ns) break;
+      const int v = ns - 1 - vi;
       const float4 me = s_sbox[v];
       const float my_area = s_sarea[v];
       const uint2 mm = s_smask[v];
@@ -745,6 +782,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
       for (int w = 0; w < kChunkWords; ++w) T[w] = (mine && (w << 5) < tid) ? s_T[tid][w] : 0u;
       bool decided = !mine;
       bool open = true;
+#ifdef DAN_PHASE_TIMING
+      t_b = clock64();
+#endif
       while (open && sweeps < kMaxSweeps) {
         uint32_t hitm = 0u, pendm = 0u;
         if (!decided) {
@@ -755,34 +795,20 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
             pendm |= T[w] & ~(kw | sw);
           }
         }
+        DAN_LAP(8);
         bar_sync_chunk();                              // every thread has read the masks of the previous sweep
+        DAN_LAP(9);
         if (!decided) {
           if (hitm != 0u) { atomicOr(&s_supm[vw], vbit); decided = true; }
           else if (pendm == 0u) { atomicOr(&s_keptm[vw], vbit); decided = true; }
         }
+        DAN_LAP(10);
         open = bar_or_chunk(!decided);
+        DAN_LAP(11);
         ++sweeps;
       }
       if (open) {
-        // a dependency chain longer than kMaxSweeps: warp 0 finishes the chunk serially (when it reaches an undecided
-        // survivor every earlier one is decided); lane w holds word w of the masks
-        if (warp == 0) {
-          uint32_t kw = (lane < kChunkWords) ? s_keptm[lane] : 0u;
-          uint32_t sw = (lane < kChunkWords) ? s_supm[lane] : 0u;
-          for (int v = 0; v < ns; ++v) {
-            const int w = v >> 5;
-            const uint32_t bit = 1u << (v & 31);
-            const uint32_t known = __shfl_sync(0xffffffffu, kw | sw, w);
-            if (known & bit) continue;                 // warp-uniform
-            const uint32_t t = (lane < kChunkWords && (lane << 5) < v) ? s_T[v][lane] : 0u;
-            const bool hit = __any_sync(0xffffffffu, (t & kw) != 0u);
-            if (lane == w) {
-              if (hit) sw |= bit;
-              else kw |= bit;
-            }
-          }
-          if (lane < kChunkWords) { s_keptm[lane] = kw; s_supm[lane] = sw; }
-        }
+        if (warp == 0) resolve_chunk_serially(&s_T[0][0], s_keptm, s_supm, ns);
         bar_sync_chunk();
       }
       DAN_TOCK(3);
@@ -795,6 +821,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
         if (w < vw) before += c;
         nk += c;
       }
+      if (tid < 2) s_next[tid] = 0;
       if (mine && (s_keptm[vw] & vbit)) {
         const int pos = L + before + __popc(s_keptm[vw] & (vbit - 1u));
         if (pos < A.nms_topk) {
@@ -825,6 +852,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
 #ifdef DAN_PHASE_TIMING
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int i = 0; i < 5; ++i) g_phase[10 + i] = acc[i];
+    for (int i = 5; i < 12; ++i) g_phase[15 + i] = acc[i];
     g_phase[15] = n_sweeps; g_phase[16] = n_surv; g_phase[17] = n_chunks; g_phase[18] = K; g_phase[19] = kept_n;
   }
 #endif
@@ -861,7 +889,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) nms_greedy_kernel(const PpArg
 // ---------------------------------------------------------------------------
 
 struct PpLayout {
-  size_t key_count, keys, s_key, s_box, s_area, kept_box, kept_area, kept_rank, s_mask, stripes, total;
+  size_t key_count, keys, maybe, s_key, s_box, s_area, kept_box, kept_area, kept_rank, s_mask, stripes, total;
 };
 
 static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms) {
@@ -870,6 +898,7 @@ static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms)
   auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
   w.key_count = take(lists * 4);
   w.keys = take(lists * n * 8);
+  w.maybe = take(nms ? lists * n * 4 : 0);
   w.s_key = take(nms ? lists * keep_topk * 8 : 0);
   w.s_box = take(nms ? lists * keep_topk * 16 : 0);
   w.s_area = take(nms ? lists * keep_topk * 4 : 0);
@@ -886,6 +915,7 @@ static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
   char* base = static_cast<char*>(ws);
   A.key_count = reinterpret_cast<int32_t*>(base + w.key_count);
   A.keys = reinterpret_cast<unsigned long long*>(base + w.keys);
+  A.maybe = reinterpret_cast<int32_t*>(base + w.maybe);
   A.s_key = reinterpret_cast<unsigned long long*>(base + w.s_key);
   A.s_box = reinterpret_cast<float4*>(base + w.s_box);
   A.s_area = reinterpret_cast<float*>(base + w.s_area);
@@ -898,19 +928,16 @@ static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
 
 // opt-in to > 48 KB of dynamic shared memory; the attribute belongs to the (function, device) pair, so it is set on
 // every call (a few hundred ns of host time) rather than cached in a process-wide flag
-static int enable_big_smem() {
-  DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortCap * 8)));
-  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
-  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
-  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
-  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
-  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
-  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGreedySmemMax));
+template <bool DECODE, int WHERE, bool FILTER>
+static int launch_greedy(const PpArgs& A, int lists, size_t smem, const float* src_scores, const float4* src_boxes, cudaStream_t st) {
+  DAN_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<DECODE, WHERE, FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_greedy_kernel<DECODE, WHERE, FILTER><<<lists, kSortThreads, smem, st>>>(A, src_scores, src_boxes);
+  DAN_LAUNCH_CHECK("nms_greedy_kernel");
   return DAN_OK;
 }
 
-// sort + greedy NMS for `lists` lists whose keys are in the workspace
-template <bool DECODE>
+// [filter +] sort + greedy NMS for `lists` lists
+template <bool DECODE, bool FILTER>
 static int run_sort_nms(const PpArgs& A_in, int lists, const float* src_scores, const float4* src_boxes, cudaStream_t st) {
   PpArgs A = A_in;
   const GreedyPlan g = greedy_plan(A.n, A.keep_topk, A.nms_cap);
@@ -919,11 +946,9 @@ static int run_sort_nms(const PpArgs& A_in, int lists, const float* src_scores, 
   A.wcap = g.wcap;
   A.cand_global = g.cand_global;
   A.kept_global = g.kept_global;
-  if (g.kept_global) nms_greedy_kernel<DECODE, 2><<<lists, kSortThreads, g.smem, st>>>(A, src_scores, src_boxes);
-  else if (g.cand_global) nms_greedy_kernel<DECODE, 1><<<lists, kSortThreads, g.smem, st>>>(A, src_scores, src_boxes);
-  else nms_greedy_kernel<DECODE, 0><<<lists, kSortThreads, g.smem, st>>>(A, src_scores, src_boxes);
-  DAN_LAUNCH_CHECK("nms_greedy_kernel");
-  return DAN_OK;
+  if (g.kept_global) return launch_greedy<DECODE, 2, FILTER>(A, lists, g.smem, src_scores, src_boxes, st);
+  if (g.cand_global) return launch_greedy<DECODE, 1, FILTER>(A, lists, g.smem, src_scores, src_boxes, st);
+  return launch_greedy<DECODE, 0, FILTER>(A, lists, g.smem, src_scores, src_boxes, st);
 }
 
 }  // namespace dan
@@ -973,8 +998,6 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   const PpLayout w = pp_layout(num_anchors, lists, p->keep_topk, true);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
-  int rc = enable_big_smem();
-  if (rc != DAN_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   PpArgs A = {};
   A.cls = cls_pred;
@@ -1004,20 +1027,18 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   A.out_keep = out_keep_pos;
   A.filler = 1;
   pp_bind(A, workspace, w);
-  DAN_CUDA(cudaMemsetAsync(A.key_count, 0, (size_t)lists * 4, st));
+  // two classes: the NMS kernel filters its own image (one launch for the whole evaluation side)
+  const bool fused = p->num_classes == 2 && (reinterpret_cast<uintptr_t>(cls_pred) & 7u) == 0;
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));
-  if (num_anchors > 0) {
-    const int64_t total = (int64_t)num_anchors * batch;
-    if (p->num_classes == 2 && aligned16(cls_pred) && total < 0x7fffffff) {
-      const int64_t per_cta = (int64_t)kF2Threads * kF2Vec * 2;
-      pp_filter2_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), kF2Threads, 0, st>>>(A);
-    } else {
+  if (!fused) {
+    DAN_CUDA(cudaMemsetAsync(A.key_count, 0, (size_t)lists * 4, st));
+    if (num_anchors > 0) {
       pp_filter_kernel<<<dim3((num_anchors + 256 * kFilterPerThread - 1) / (256 * kFilterPerThread), batch), 256, 0, st>>>(A);
+      DAN_LAUNCH_CHECK("pp_filter_kernel");
     }
-    DAN_LAUNCH_CHECK("pp_filter_kernel");
   }
   if (ev) DAN_CUDA(cudaEventRecord(ev[1], st));
-  rc = run_sort_nms<true>(A, lists, nullptr, nullptr, st);
+  int rc = fused ? run_sort_nms<true, true>(A, lists, nullptr, nullptr, st) : run_sort_nms<true, false>(A, lists, nullptr, nullptr, st);
   if (ev && rc == DAN_OK) DAN_CUDA(cudaEventRecord(ev[2], st));
   return rc;
 }
@@ -1059,8 +1080,7 @@ int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t 
   const PpLayout w = pp_layout(n, 1, 1, false);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
-  int rc = enable_big_smem();
-  if (rc != DAN_OK) return rc;
+  DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortCap * 8)));
   cudaStream_t st = (cudaStream_t)stream;
   PpArgs A = {};
   A.n = (int)n;
@@ -1088,8 +1108,6 @@ int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t n
   const PpLayout w = pp_layout(n, 1, n_eff, true);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
-  int rc = enable_big_smem();
-  if (rc != DAN_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   PpArgs A = {};
   A.n = (int)n;
@@ -1107,7 +1125,7 @@ int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t n
   pp_bind(A, workspace, w);
   key_build_kernel<<<grid_for(n), 256, 0, st>>>(scores, n, A.keys, A.key_count);
   DAN_LAUNCH_CHECK("key_build_kernel");
-  return run_sort_nms<false>(A, 1, scores, reinterpret_cast<const float4*>(boxes), st);
+  return run_sort_nms<false, false>(A, 1, scores, reinterpret_cast<const float4*>(boxes), st);
 }
 
 }  // extern "C"

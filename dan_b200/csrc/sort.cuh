@@ -8,7 +8,10 @@
 #endif
 
 constexpr int kSortCap = 8192;      // keys sorted in shared memory (64 KB)
-constexpr int kSortThreads = 1024;
+#ifndef DAN_SORT_THREADS
+#define DAN_SORT_THREADS 1024          // threads per CTA of the including file's sort kernels (a power of two >= 256)
+#endif
+constexpr int kSortThreads = DAN_SORT_THREADS;
 
 // order-preserving float <-> uint32 (descending key order = descending score)
 DAN_D uint32_t score_to_key(float s) { return (uint32_t)float_to_ordered(s) ^ 0x80000000u; }
@@ -29,7 +32,7 @@ struct SortScratch {
 // are static
 template <int KPT, int ST>
 DAN_D void reg_stage(unsigned long long (&r)[KPT], int lsize, bool desc_t) {
-  constexpr int LK = KPT == 8 ? 3 : KPT == 4 ? 2 : KPT == 2 ? 1 : 0;
+  constexpr int LK = KPT == 32 ? 5 : KPT == 16 ? 4 : KPT == 8 ? 3 : KPT == 4 ? 2 : KPT == 2 ? 1 : 0;
 #pragma unroll
   for (int e = 0; e < KPT; ++e) {
     if ((e & ST) == 0) {
@@ -49,7 +52,7 @@ DAN_D void reg_stage(unsigned long long (&r)[KPT], int lsize, bool desc_t) {
 // partner's load are conflict free.
 template <int KPT>
 DAN_D void bitonic_sort_regs(unsigned long long* s_keys, int lp2) {
-  constexpr int LK = KPT == 8 ? 3 : KPT == 4 ? 2 : KPT == 2 ? 1 : 0;
+  constexpr int LK = KPT == 32 ? 5 : KPT == 16 ? 4 : KPT == 8 ? 3 : KPT == 4 ? 2 : KPT == 2 ? 1 : 0;
   const int tid = threadIdx.x;
   const int T = 1 << (lp2 - LK);                // threads that own keys
   const bool active = tid < T;
@@ -89,6 +92,8 @@ DAN_D void bitonic_sort_regs(unsigned long long* s_keys, int lp2) {
           r[e] = ((r[e] < o) == keep_max) ? o : r[e];
         }
       } else {
+        if constexpr (KPT > 16) { if (ls == 4) reg_stage<KPT, 16>(r, lsize, desc_t); }
+        if constexpr (KPT > 8) { if (ls == 3) reg_stage<KPT, 8>(r, lsize, desc_t); }
         if constexpr (KPT > 4) { if (ls == 2) reg_stage<KPT, 4>(r, lsize, desc_t); }
         if constexpr (KPT > 2) { if (ls == 1) reg_stage<KPT, 2>(r, lsize, desc_t); }
         if constexpr (KPT > 1) { if (ls == 0) reg_stage<KPT, 1>(r, lsize, desc_t); }
@@ -114,10 +119,15 @@ DAN_D void sort_smem_keys(unsigned long long* s_keys, int m) {
   for (int i = m + tid; i < p2; i += kSortThreads) s_keys[i] = 0ull;
   __syncthreads();
   if (lp2 >= 5) {            // (at least one full warp of owners)
-    if (lp2 <= 10) bitonic_sort_regs<1>(s_keys, lp2);
-    else if (lp2 == 11) bitonic_sort_regs<2>(s_keys, lp2);
-    else if (lp2 == 12) bitonic_sort_regs<4>(s_keys, lp2);
-    else bitonic_sort_regs<8>(s_keys, lp2);
+    // keys per thread: the smallest power of two that lets kSortThreads threads own all 2^lp2 keys
+    constexpr int kLogThreads = kSortThreads == 1024 ? 10 : kSortThreads == 512 ? 9 : 8;
+    const int lk = lp2 > kLogThreads ? lp2 - kLogThreads : 0;
+    if (lk == 0) bitonic_sort_regs<1>(s_keys, lp2);
+    else if (lk == 1) bitonic_sort_regs<2>(s_keys, lp2);
+    else if (lk == 2) bitonic_sort_regs<4>(s_keys, lp2);
+    else if (lk == 3) bitonic_sort_regs<8>(s_keys, lp2);
+    else if (lk == 4) { if constexpr (kSortThreads < 1024) bitonic_sort_regs<16>(s_keys, lp2); }
+    else { if constexpr (kSortThreads < 512) bitonic_sort_regs<32>(s_keys, lp2); }
     return;
   }
   // small lists: plain bitonic sort in shared memory, descending; strides are powers of two -> shifts only
@@ -136,11 +146,14 @@ DAN_D void sort_smem_keys(unsigned long long* s_keys, int m) {
   }
 }
 
-DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, int k, unsigned long long* s_keys, SortScratch& sc) {
+// staged = true: when cnt <= kSortCap the keys are already in s_keys[0, cnt) (the caller produced them there)
+DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, int k, unsigned long long* s_keys, SortScratch& sc,
+                          bool staged = false) {
   const int tid = threadIdx.x;
   int m = cnt;
   if (cnt <= kSortCap) {
-    for (int i = tid; i < cnt; i += kSortThreads) s_keys[i] = keys[i];
+    if (!staged)
+      for (int i = tid; i < cnt; i += kSortThreads) s_keys[i] = keys[i];
   } else {
     // block radix select, MSB first, 8 bits per pass: find the k-th largest key
     if (tid == 0) { sc.prefix = 0ull; sc.remaining = k; }

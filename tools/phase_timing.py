@@ -9,11 +9,13 @@ lib_dbg = "/tmp/libdan_b200_phase.so"
 cmd = ["nvcc"] + build.NVCC_FLAGS + ["-shared", "-DDAN_PHASE_TIMING"] + [os.path.join(build.CSRC, s) for s in build.SOURCES] + ["-o", lib_dbg]
 subprocess.run(cmd, check=True)
 from dan_b200 import _lib
-_lib.LIB_PATH = lib_dbg
+if "--prod" not in sys.argv:
+    _lib.LIB_PATH = lib_dbg
 from dan_b200 import functional as F, synthetic
 from dan_b200.utility import anchor_manipulator as am
 L = _lib.lib()
-L.dan_debug_phases.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+if "--prod" not in sys.argv:
+    L.dan_debug_phases.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
 dev = torch.device("cuda", 0)
 ps = [0.1, 0.1, 0.2, 0.2]
 enc = am.AnchorEncoder(0.4, 0.4, ps)
@@ -25,6 +27,9 @@ for faces, seed in ((60, 1420), (300, 3100), (300, 7), (450, 4150)):
     cls = torch.from_numpy(cls[None]).to(dev); loc = torch.from_numpy(loc[None]).to(dev)
     for _ in range(3):
         det, ms = F.postprocess_batch(pp, cls, loc_pred=loc, anchors=a_eval[:4], profile=True)
+    if "--prod" in sys.argv:
+        print("production build: kept=%d kernel us: %s" % (int(det.counts[0, 0]), [round(1e3 * v, 1) for v in ms]))
+        continue
     buf = (ctypes.c_longlong * 32)()
     L.dan_debug_phases(buf)
     t = np.array(list(buf), dtype=np.float64) / 1965.0   # us at 1965 MHz
@@ -33,3 +38,5 @@ for faces, seed in ((60, 1420), (300, 3100), (300, 7), (450, 4150)):
           (t[8] - t[0], t[1] - t[8], t[2] - t[1], t[3] - t[2], t[4] - t[3]))
     print("  greedy: a (vs kept) %.1f | b (compact) %.1f | c (pair bits) %.1f | d (relax) %.1f | e (append) %.1f ; %d chunks, %d survivors, %d sweeps"
           % (t[10], t[11], t[12], t[13], t[14], buf[17], buf[16], buf[15]))
+    print("  b: pre-barrier %.2f | named barrier %.2f | copy %.2f ;  d per sweep total: read masks %.2f | barrier %.2f | decide+atomic %.2f | barrier.or %.2f"
+          % (t[20], t[21], t[22], t[23], t[24], t[25], t[26]))
