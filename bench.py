@@ -9,8 +9,8 @@ One "step" = one pass of the hot path over one batch of synthetic images PER GPU
                    G1 ground truth with <= 50 faces / image                      (BASELINE.json configs[1])
   evaluation side  decode + softmax + threshold 0.01 + top-k 5000 + NMS 0.3 -> 750 on G3 predictions
                    (parse_by_class semantics, configs[3] at 640^2)
-  N > 1            images are sharded per rank (configs[4]: 8 x 32 = 256 images); one NCCL all-gather of the
-                   fixed-capacity detection slabs per step.
+  N > 1            images are sharded per rank (configs[4]: 8 x 32 = 256 images); ONE ncclAllGather of the
+                   fixed-capacity detection slabs per step, enqueued behind the NMS kernel inside the step's CUDA graph.
 `value` is timed with inputs resident in HBM (CUDA events, the step replayed as a CUDA graph, rotating input/output
 buffer sets larger than L2); `e2e` is timed through the public python API with HOST (pinned) buffers, H2D and D2H
 copies inside the timed region.
@@ -35,17 +35,17 @@ UNIT = "images/s"
 IMAGE = (640, 640)
 PP = (0.01, 0, 5000, 750, 0.3)      # select_threshold, min_size, keep_topk, nms_topk, nms_threshold
 CPU_CFG = dict(kind="s3fd", size=IMAGE, pos=0.4, ign=0.4, mining=True, max_gt=50, max_faces=300, pp=PP)
-KERNELS_PER_STEP = 5                # enc_pass1/2/3, pp_filter, nms_greedy
+# kernels of one step (the memset node aside): enc_pass1, enc_pass2_find, enc_pass2_apply, enc_pass3, nms_greedy
+# (+ the NCCL kernel at N > 1)
+KERNELS_PER_STEP = 5
 
 
-def workload_config(batch, n_gpus, extra=None):
-    cfg = {"workload": "S3FD 640x640 (34125 anchors): mining encode of <=50 GT faces/image + decode/threshold 0.01/"
-                       "top-k 5000/NMS 0.3->750 of G3 predictions, batch %d per GPU" % batch,
-           "images_per_gpu": batch, "global_batch": batch * n_gpus, "num_anchors": 34125,
-           "parallelism": "per-image sharding, dp%d" % n_gpus}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def workload_config(batch, n_gpus):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": "S3FD 640x640 (34125 anchors): mining encode of <=50 GT faces/image + decode/threshold 0.01/"
+                        "top-k 5000/NMS 0.3->750 of G3 predictions, batch %d per GPU" % batch,
+            "images_per_gpu": batch, "global_batch": batch * n_gpus, "num_anchors": 34125,
+            "parallelism": "per-image sharding, dp%d" % n_gpus}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -68,8 +68,15 @@ def cpu_measure(images, steps, warmup, procs=None):
         busy += b
     pool.close()
     total = sum(walls)
+    lib = os.path.join("oracle", "_ref", "libsmm_ref.so") if pool.impl == "reference" else os.path.join("oracle", "liboracle_native.so")
     return {"value": images * steps / total, "ms_per_step": 1e3 * total / steps, "cores": procs, "impl": pool.impl,
-            "images": images, "core_seconds_per_image": busy / (images * steps)}
+            "images": images, "core_seconds_per_image": busy / (images * steps), "matcher_library": lib}
+
+
+def cpu_kind(r):
+    """"reference": the matcher is the reference's own functor compiled from /root/reference (oracle/_ref); the TF graph
+    ops around it are restated in numpy either way (TensorFlow 1.8 is not installable)."""
+    return "reference" if r["impl"] == "reference" else "port"
 
 
 def run_reference(args):
@@ -79,15 +86,16 @@ def run_reference(args):
     procs = os.cpu_count() or 1
     images = min(args.batch, max(2 * procs, 8))
     r = cpu_measure(images, args.steps, max(args.warmup, 1), procs)
-    kind = "port"
     sample = ("%d images/step x %d steps, %d worker processes (one image per task); numpy fp32 restatement of the TF graph ops"
-              " + %s SmallMiningMatch + restated tf.nn.top_k / non_max_suppression (TF 1.8 is not installable)"
-              % (images, args.steps, procs, "the reference's own compiled" if r["impl"] == "reference" else "ported"))
+              " + %s SmallMiningMatch (%s, loaded by the worker processes) + restated tf.nn.top_k / non_max_suppression "
+              "(TF 1.8 is not installable)"
+              % (images, args.steps, procs, "the reference's own compiled" if r["impl"] == "reference" else "ported", r["matcher_library"]))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.batch, args.gpus, {"cpu_sample_images_per_step": images}),
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+            "config": workload_config(args.batch, args.gpus),
+            "run": {"cpu_sample_images_per_step": images, "native_so_loaded": [r["matcher_library"]]},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": procs, "kind": cpu_kind(r), "sample": sample},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -158,8 +166,17 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def fp32_peak():
+    """Non-FMA FP32 issue rate (instructions/s): calibrated on the box with tools/fp32_peak.cu, else 148 x 128 x 1.965 GHz."""
+    try:
+        return (1e12 * json.load(open(os.path.join(ROOT, "profiles", "r01_fp32_peak.json")))["fp32_nonfma_tinstr_s"],
+                "measured (profiles/r01_fp32_peak.json, tools/fp32_peak.cu)")
+    except Exception:
+        return 37.2e12, "nominal 148 SM x 128 lanes x 1.965 GHz"
+
+
 def ncu_traffic():
-    """dram bytes/launch of the dominant kernel from the committed ncu --set full capture (profiles/), else None."""
+    """dram bytes/launch per kernel from the committed ncu --set full capture (profiles/), else None."""
     path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(path):
         try:
@@ -169,10 +186,35 @@ def ncu_traffic():
     return None
 
 
+def pin_rank_to_cores(local_rank, local_world):
+    """Give every rank of the node its own slice of the host cores BEFORE it allocates pinned memory: the pinned
+    buffers are then first-touched (and the copies issued) from distinct cores / memory controllers instead of all
+    ranks sharing whatever cores the launcher left them on."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(local_world, 1))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except (AttributeError, OSError):
+        return None
+
+
+def log(msg):
+    """Progress on stderr (DAN_BENCH_VERBOSE=1): where a multi-rank run is, should it ever stall."""
+    if os.environ.get("DAN_BENCH_VERBOSE"):
+        sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
+_T0 = time.time()
+
+
 def run_cuda(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     B = args.batch
 
     # ---- CPU baseline first (rank 0, N == 1 only): needs fork, so it runs before CUDA is initialised ----------
@@ -181,11 +223,13 @@ def run_cuda(args):
         procs = os.cpu_count() or 1
         images = max(4 * procs, 32)
         r = cpu_measure(images, 5, 1, procs)
-        cpu_base = {"value": r["value"], "unit": UNIT, "cores": procs, "kind": "port",
+        cpu_base = {"value": r["value"], "unit": UNIT, "cores": procs, "kind": cpu_kind(r),
                     "sample": "%d images x 5 passes after 1 warm-up pass (%.0f core-seconds), %d worker processes; numpy restatement + %s "
-                              "SmallMiningMatch; %.1f ms per image per core" % (images, r["core_seconds_per_image"] * images * 5, procs,
-                                                                                "reference-compiled" if r["impl"] == "reference" else "ported",
-                                                                                1e3 * r["core_seconds_per_image"])}
+                              "SmallMiningMatch (%s); %.1f ms per image per core"
+                              % (images, r["core_seconds_per_image"] * images * 5, procs,
+                                 "reference-compiled" if r["impl"] == "reference" else "ported", r["matcher_library"],
+                                 1e3 * r["core_seconds_per_image"])}
+    cores_per_rank = pin_rank_to_cores(local_rank, local_world) if world > 1 else None
 
     import numpy as np
     import torch
@@ -200,6 +244,7 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    log("process group ready")
     # ---- anchors, parameters ----------------------------------------------------------------------------------
     ps = [0.1, 0.1, 0.2, 0.2]
     enc = am.AnchorEncoder(0.4, 0.4, ps)
@@ -217,16 +262,14 @@ def run_cuda(args):
     per_set = B * N * (8 + 16 + 44)          # cls + loc in, encode outputs out
     R = args.sets if args.sets > 0 else max(4, int(np.ceil(3.0 * 126e6 / per_set)))
     # `inflight` consecutive steps are in flight at a time, each on its own stream with its own workspaces (different
-    # buffer sets, no shared state): the top-k sort, the NMS resolve and the compensation pass run one CTA per image,
-    # i.e. on 32 of the 148 SMs, and their latency chain would otherwise leave most of the GPU idle
+    # buffer sets, no shared state): the fused sort + NMS kernel and the compensation pass run one CTA per image, i.e. on
+    # 32 of the 148 SMs, and their latency would otherwise leave most of the GPU idle
     L = max(1, args.inflight)
     R = (R + L - 1) // L * L                  # a set always runs on the same lane
     ws_lanes = [(_lib.Workspace(), _lib.Workspace()) for _ in range(L)]
-    # the detection slabs of the L sets of a group are contiguous: at N > 1 ONE all-gather moves the detections of L steps
-    # (a collective per step costs ~50 us of host time in torch.distributed, more than a step takes on the GPU)
+    # one NCCL communicator per lane: collectives of one communicator must not run concurrently, the lanes do
+    gathers = [pipeline.DeviceGather(rank, world, dev) for _ in range(L)] if world > 1 else [None] * L
     slab_words = pipeline.DetectionSlab.words_for(B, pp_params.num_classes - 1, pp_params.nms_topk)
-    group_send = [torch.zeros(L * slab_words, dtype=torch.float32, device=dev) for _ in range(R // L)]
-    group_recv = [torch.empty(world * L * slab_words, dtype=torch.float32, device=dev) for _ in range(R // L)] if world > 1 else None
     sets = []
     for r in range(R):
         order = [(i + r) % B for i in range(B)]
@@ -235,19 +278,22 @@ def run_cuda(args):
              "cls": torch.from_numpy(np.stack([preds[i][0] for i in order])).pin_memory(),
              "loc": torch.from_numpy(np.stack([preds[i][1] for i in order])).pin_memory()}
         d = {k: v.to(dev) for k, v in h.items()}
+        recv = torch.zeros(world * slab_words, dtype=torch.float32, device=dev) if world > 1 else None
         hp = pipeline.HotPath(a_train[:4], a_train[4], enc_params, pp_params, anchors_eval=a_eval[:4],
-                              workspaces=ws_lanes[r % L], overlap=not args.no_overlap,
-                              slab_buffer=group_send[r // L][(r % L) * slab_words:(r % L + 1) * slab_words])
-        sets.append({"host": h, "dev": d, "hp": hp, "total_gt": int(offs[-1])})
+                              workspaces=ws_lanes[r % L], overlap=not args.no_overlap, device_gather=gathers[r % L], recv_buffer=recv)
+        sets.append({"host": h, "dev": d, "hp": hp, "recv": recv, "total_gt": int(offs[-1])})
     total_gt_mean = float(np.mean([s["total_gt"] for s in sets]))
 
+    log("inputs and %d communicators ready" % L)
     def run_set(s, profile=False):
         return s["hp"].step(s["dev"]["gt"], s["dev"]["offs"], s["dev"]["cls"], s["dev"]["loc"], profile=profile)
 
-    # warm-up outside graphs (sizes the workspace, sets kernel attributes), then capture one CUDA graph per set
+    # warm-up outside graphs (sizes the workspace, sets kernel attributes, opens the NCCL channels), then capture one
+    # CUDA graph per set; at N > 1 the graph contains the all-gather of the step's detection slab
     for s in sets:
         run_set(s)
     torch.cuda.synchronize()
+    log("eager warm-up done")
     graphs = []
     if not args.no_graph:
         side = torch.cuda.Stream()
@@ -261,82 +307,63 @@ def run_cuda(args):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
 
-    # the all-gather of step k runs on its own stream and overlaps the compute of step k+1 (different buffer set);
-    # a set is not replayed again before its previous gather has finished
-    comm = torch.cuda.Stream() if world > 1 else None
-    ev_comm = [torch.cuda.Event() for _ in range(R // L)]
+    log("graphs captured")
     main = torch.cuda.current_stream()
     lanes = [torch.cuda.Stream() for _ in range(L)]
-    pending = []                 # streams holding steps whose detections have not been gathered yet
 
     def lane_of(k, serial=False):
         return lanes[0] if serial else lanes[(k % R) % L]
 
-    def flush_gather(g):
-        """All-gather of group g's slabs on the communication stream; overlaps the compute of the following steps
-        (other buffer sets).  A set is not replayed again before the gather that reads its slab has finished."""
-        for ln in set(pending):
-            comm.wait_stream(ln)
-        del pending[:]
-        with torch.cuda.stream(comm):
-            pipeline.gather_slab_group(group_send[g], group_recv[g])
-            ev_comm[g].record(comm)
-
-    def step(k, gather=True, serial=False):
+    def step(k, serial=False):
         """Enqueue step k on its lane's stream (serial=True: every step on lane 0, one after the other)."""
-        r = k % R
-        s = sets[r]
-        cur = lane_of(k, serial)
-        if comm is not None:
-            cur.wait_event(ev_comm[r // L])
-        with torch.cuda.stream(cur):
+        with torch.cuda.stream(lane_of(k, serial)):
             if graphs:
-                graphs[r].replay()
+                graphs[k % R].replay()
             else:
-                run_set(s)
-        if comm is not None and gather:
-            pending.append(cur)
-            if r % L == L - 1:
-                flush_gather(r // L)
+                run_set(sets[k % R])
 
     def fork():
         for ln in lanes:
             ln.wait_stream(main)
 
-    def drain(last_k=None):
-        if comm is not None and pending and last_k is not None:
-            flush_gather((last_k % R) // L)          # the last, incomplete group
+    def drain():
         for ln in lanes:
             main.wait_stream(ln)
-        if comm is not None:
-            main.wait_stream(comm)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(n):
+        fork()
+        for k in range(n):
+            step(k)
+            if k % 256 == 255:
+                torch.cuda.synchronize()
+        drain()
+        torch.cuda.synchronize()
+
     # ---- device-resident timing: W warm-up steps, then exactly K steps between barrier+sync ----------------------
-    # warm-up: at least W steps AND at least ~0.5 s of load so that the SM clocks have ramped up from idle
-    # (the time-based part runs without the collective: ranks may do different numbers of those)
+    # warm-up: at least W steps AND ~0.5 s of load so that the SM clocks have ramped up from idle.  Every rank runs
+    # the same number of steps (the collective is part of a step): the time-based part is sized on rank 0.
     W, K = max(args.warmup, 3), args.steps
-    fork()
-    for k in range(W):
-        step(k)
-    drain(W - 1)
-    fork()
-    t_warm = time.time() + 0.5
-    k = 0
-    while time.time() < t_warm:
-        step(k, gather=False)
-        k += 1
-        if k % 64 == 0:
-            torch.cuda.synchronize()
+    run_steps(W)
+    t0 = time.time()
+    run_steps(4 * R)
+    per_step_s = max((time.time() - t0) / (4 * R), 1e-6)
+    plan = torch.tensor([int(0.5 / per_step_s), int(1.0 / per_step_s)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(plan, src=0)
+    n_ramp, n_tail = int(plan[0].item()), int(plan[1].item())
+    run_steps(n_ramp)
+    log("clock ramp done")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
         sampler.start()
         time.sleep(0.3)
+
     def timed(serial):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         drain()
@@ -345,22 +372,16 @@ def run_cuda(args):
         fork()
         for k in range(K):
             step(W + k, serial=serial)
-        drain(W + K - 1)
+        drain()
         e1.record()
         barrier()
         return e0.elapsed_time(e1)
 
     serial_ms = timed(True) if L > 1 else None       # one step at a time: the latency of a step
     elapsed_ms = timed(False)
-    # keep the GPU busy a little longer so that the clock sampler sees the loaded state
-    t_end = time.time() + (1.0 if sampler else 0.0)
-    k = 0
-    while time.time() < t_end:
-        step(k, gather=False)
-        k += 1
-    torch.cuda.synchronize()
+    log("timed regions done: %.3f ms/step" % (elapsed_ms / K))
+    run_steps(n_tail)                                # keep the GPU busy a little longer: the clock sampler sees the loaded state
     clocks = sampler.stop() if sampler else None
-    drain()
     t = torch.tensor([elapsed_ms, serial_ms if serial_ms is not None else elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -371,8 +392,9 @@ def run_cuda(args):
     # bit for bit with the outputs of the same set run alone
     def outputs(s):
         return list(s["hp"]._enc_out[:4]) + [s["hp"]._slab.buf]
+    fork()
     for r in range(R):
-        step(r, gather=False, serial=True)
+        step(r, serial=True)
     drain()
     torch.cuda.synchronize()
     alone = [[t.clone() for t in outputs(s)] for s in sets]
@@ -380,29 +402,52 @@ def run_cuda(args):
         for t in outputs(s):
             t.fill_(-7)
     torch.cuda.synchronize()
-    fork()
-    for k in range(2 * R):
-        step(k, gather=False)
-    drain()
-    torch.cuda.synchronize()
+    run_steps(2 * R)
     for r, s in enumerate(sets):
         for a, b in zip(alone[r], outputs(s)):
             if not torch.equal(a, b):
                 raise RuntimeError("set %d: outputs with %d steps in flight differ from the serial run" % (r, L))
     del alone
 
-    # ---- end to end: host buffers in, detections out, every step -------------------------------------------------
-    # Software pipeline of depth 2 over three streams: while step k computes, the inputs of step k+1 cross PCIe on the
-    # copy-in stream and the detections of step k-1 are read back.  Every step's inputs come from pinned host memory
-    # and every step's result lands in pinned host memory inside the timed region.
-    slab_words = sets[0]["hp"]._slab.words
+    log("in-flight outputs verified")
+    # ---- N > 1: what every rank received must be what every rank sent.  Each rank checksums its own slab of every set;
+    # the checksums travel separately (torch.distributed, outside any timed region) and are compared with checksums of
+    # the received slabs; the rank's own slot must be bit-identical to its send buffer.
+    gather_check = None
+    if world > 1:
+        weights = torch.arange(slab_words, device=dev, dtype=torch.int64) % 65521 + 1
+
+        def checksum(x):
+            v = x.view(torch.int32).to(torch.int64)
+            return torch.stack([v.sum(), (v * weights).sum()])
+        mine = torch.stack([checksum(s["hp"]._slab.buf) for s in sets])                    # [R, 2]
+        allsums = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allsums, mine)
+        for r, s in enumerate(sets):
+            for q in range(world):
+                got = checksum(s["recv"][q * slab_words:(q + 1) * slab_words])
+                if not torch.equal(got, allsums[q, r]):
+                    raise RuntimeError("rank %d, set %d: the slab received from rank %d differs from what it sent" % (rank, r, q))
+            if not torch.equal(s["recv"][rank * slab_words:(rank + 1) * slab_words], s["hp"]._slab.buf):
+                raise RuntimeError("rank %d, set %d: own slot of the gathered buffer differs from the send slab" % (rank, r))
+        per_rank = [int(v[0].sum()) for v in sets[0]["hp"].gathered()]
+        gather_check = {"verified": "checksums of all %d x %d received slabs equal the senders' on every rank" % (world, R),
+                        "detections_per_rank_set0": per_rank}
+
+    log("gather verified")
+    # ---- end to end: host buffers in, results out, every step ----------------------------------------------------
+    # Software pipeline over three streams: while step k computes, the inputs of step k+1 cross PCIe on the copy-in stream
+    # and the results of step k-1 are read back.  Every step's inputs come from pinned host memory and every step's
+    # result lands in pinned host memory inside the timed region.  full=True also returns the encode outputs (targets,
+    # labels, scores, matched boxes: 44 B/anchor), which the reference produces in host RAM (dataset_common.py:150,178).
     h_out = [torch.empty(slab_words, dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_enc = [None, None]
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     ev_in = [torch.cuda.Event() for _ in range(R)]
     ev_done = [torch.cuda.Event() for _ in range(R)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_run(n_steps):
+    def e2e_run(n_steps, full):
         def copy_in(k):
             s = sets[k % R]
             with torch.cuda.stream(s_in):
@@ -425,81 +470,139 @@ def run_cuda(args):
                 s_out.wait_event(ev_done[k % R])
                 ev_out[k % 2].synchronize()                   # the host consumed this pinned buffer two steps ago
                 h_out[k % 2].copy_(sets[k % R]["hp"]._slab.buf, non_blocking=True)
+                if full:
+                    for dst, src in zip(h_enc[k % 2], sets[k % R]["hp"]._enc_out[:4]):
+                        dst.copy_(src, non_blocking=True)
                 ev_out[k % 2].record(s_out)
             if k >= 1:
                 ev_out[(k - 1) % 2].synchronize()             # result of step k-1 is on the host now
         ev_out[(n_steps - 1) % 2].synchronize()
         torch.cuda.synchronize()
 
-    e2e_run(4)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(K)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    def e2e_measure(full):
+        e2e_run(4, full)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(K, full)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     h2d = sum(int(sets[0]["host"][n].numel() * sets[0]["host"][n].element_size()) for n in ("gt", "offs", "cls", "loc"))
     d2h = slab_words * 4
+    e2e_s = e2e_measure(False)
     e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": 1e3 * e2e_s / K, "h2d_gbs_per_gpu": h2d * K / e2e_s / 1e9,
+           "returns": "detection slab (counts, boxes, scores); the encode targets stay on the device, where a training "
+                      "loop consumes them",
            "note": "per step: pinned host GT + predictions copied in, hot path, detection slab copied out to pinned host memory; "
-                   "copies of neighbouring steps overlap the compute (3 streams); encode targets stay on the device "
-                   "(consumed by the loss there); bound by the host-to-device copy of the predictions over PCIe "
-                   "(h2d_gbs_per_gpu is what the link delivers)"}
+                   "copies of neighbouring steps overlap the compute (3 streams); bound by the host-to-device copy of the "
+                   "predictions over PCIe (h2d_gbs_per_gpu is what the link delivers)"}
+    h_enc = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in sets[0]["hp"]._enc_out[:4]] for _ in range(2)]
+    d2h_full = d2h + sum(int(t.numel() * t.element_size()) for t in sets[0]["hp"]._enc_out[:4])
+    e2e_full_s = e2e_measure(True)
+    e2e_full = {"value": world * B * K / e2e_full_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
+                "ms_per_step": 1e3 * e2e_full_s / K,
+                "returns": "detection slab AND the encode outputs (targets, labels, scores, matched boxes) in pinned host memory, "
+                           "as the reference's input pipeline produces them (dataset_common.py:150,178-186)"}
+    h_enc = [None, None]
 
+    log("e2e done")
     # ---- per-kernel CUDA-event durations (profile entry points), cold buffers --------------------------------------
     prof = {}
     reps = max(10, R)
     for k in range(reps):
-        _, _, ms = run_set(sets[k % R], profile=True)
+        _, det, ms = run_set(sets[k % R], profile=True)
         for name, v in ms.items():
             prof.setdefault(name, []).append(v)
     kernel_ms = {name: statistics.mean(v[2:]) for name, v in prof.items()}
+    kernel_ms.pop("pp_filter", None)          # two classes: the filter runs inside nms_greedy_kernel
     step_kernel_sum = sum(kernel_ms.values())
-    dom = max(kernel_ms, key=kernel_ms.get)
-    peak, peak_src = measured_hbm_peak()
-    enc_bytes = B * (44.0 * N) + 16.0 * total_gt_mean + 17.0 * N       # SURVEY 8(d): 44N + 16M + 17N/B per image
-    pp_bytes = B * 24.0 * N + B * 20.0 * 750
-    alg = {"enc_pass2": enc_bytes, "enc_pass1": 17.0 * N + 16.0 * total_gt_mean, "pp_filter": pp_bytes}
-    traffic = ncu_traffic()
-    roof_kernel = "enc_pass2"
-    achieved = alg[roof_kernel] / (kernel_ms[roof_kernel] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "enc_pass2_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": (traffic or {}).get("enc_pass2_fused_kernel"), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[roof_kernel], "kernel_ms": kernel_ms[roof_kernel],
-                "share_of_step_kernel_time": kernel_ms[roof_kernel] / step_kernel_sum,
-                "longest_kernel": dom,
-                "pp_filter_achieved_gbs": alg["pp_filter"] / (kernel_ms["pp_filter"] * 1e-3) / 1e9}
+    longest = max(kernel_ms, key=kernel_ms.get)
 
-    # the match kernels against the non-FMA FP32 issue rate (calibrated: tools/fp32_peak.cu), as the DENSE
-    # evaluation figure N(20M+30) per image; pairs with an empty intersection are culled, so this is an equivalent rate
-    fp32_peak = 37.2e12
-    try:
-        fp32_peak = 1e12 * json.load(open(os.path.join(ROOT, "profiles", "r01_fp32_peak.json")))["fp32_nonfma_tinstr_s"]
-    except Exception:
-        pass
-    dense_flops = N * (20.0 * total_gt_mean + 30.0 * B)
-    match_ms = kernel_ms["enc_pass1"] + kernel_ms["enc_pass2"]
-    roofline["fp32_dense_equivalent"] = {"flops_per_step": dense_flops, "kernels": "enc_pass1 + enc_pass2", "kernel_ms": match_ms,
-                                         "achieved_tflops": dense_flops / (match_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak / 1e12,
-                                         "frac": dense_flops / (match_ms * 1e-3) / fp32_peak}
+    # ---- roofline of the STEP: per stage t = max(bytes / BW_HBM, flops / P_FP32) on the ALGORITHMIC
+    # work, summed over the stages, against the measured time of a step
+    peak_hbm, peak_src = measured_hbm_peak()
+    p_fp32, fp32_src = fp32_peak()
+    # candidates per image K (after threshold / top-k): where fewer than nms_topk boxes were kept, the first filler row
+    # of the keep list sits at position K
+    last = sets[(reps - 1) % R]["hp"]
+    cnts = last._slab.views()[0].reshape(-1).cpu().numpy()
+    keep = last._aux[1].reshape(len(cnts), -1).cpu().numpy()
+    Ks = np.array([keep[i, cnts[i]] if cnts[i] < pp_params.nms_topk else pp_params.keep_topk for i in range(len(cnts))], dtype=np.float64)
+    enc_bytes = B * (44.0 * N) + 16.0 * total_gt_mean + 17.0 * N       # 44N + 16M + 17N/B per image
+    enc_flops = N * (20.0 * total_gt_mean + 30.0 * B)                  # N (20 M + 30) per image, non-FMA flops
+    pp_bytes = B * 24.0 * N + float(np.sum(20.0 * np.minimum(cnts, pp_params.nms_topk)))   # 24 N + 20 K_out per image
+    pp_flops = 40.0 * N * B
+    nms_flops = float(np.sum(16.0 * Ks * (Ks - 1.0) / 2.0))            # 16 K (K-1) / 2 per image
+    nms_bytes = 20.0 * float(np.sum(Ks))
+
+    def stage(nbytes, flops):
+        t_h, t_f = 1e6 * nbytes / (peak_hbm * 1e9), 1e6 * flops / p_fp32
+        return {"bytes": nbytes, "flops": flops, "t_hbm_us": t_h, "t_fp32_us": t_f, "bound": "hbm" if t_h >= t_f else "fp32",
+                "t_roofline_us": max(t_h, t_f)}
+    stages = {"encode": stage(enc_bytes, enc_flops), "decode_filter": stage(pp_bytes, pp_flops), "nms": stage(nms_bytes, nms_flops)}
+    t_roof_us = sum(st["t_roofline_us"] for st in stages.values())
+    step_us = 1e3 * elapsed_ms / K
+    traffic = ncu_traffic() or {}
+    step_bytes = enc_bytes + pp_bytes
+    p1_gbs = enc_bytes / (kernel_ms["enc_pass1"] * 1e-3) / 1e9
+    roofline = {
+        # the step against the roofline: images/s of the measured step vs images/s at which the algorithmic work of the
+        # three stages would run at the binding peak of each stage (encode, NMS: non-FMA FP32 issue rate; filter: HBM)
+        "bound": "fp32 (encode, nms) + hbm (decode_filter), per stage",
+        "achieved": B * 1e6 / step_us, "peak": B * 1e6 / t_roof_us, "unit": "images/s per GPU",
+        "frac": t_roof_us / step_us,
+        "t_roofline_us": t_roof_us, "t_step_us": step_us, "stages": stages,
+        "mean_candidates_per_image": float(np.mean(Ks)),
+        "peak_hbm_gbs": peak_hbm, "peak_hbm_source": peak_src, "peak_fp32_tinstr_s": p_fp32 / 1e12, "peak_fp32_source": fp32_src,
+        "serial_frac": (t_roof_us / (1e3 * serial_ms / K)) if serial_ms else None,
+        "kernel": longest, "kernel_ms": kernel_ms[longest],
+        # HBM view: algorithmic bytes of the whole step over the step time, and of the kernel that writes all encode outputs
+        "hbm": {"step_bytes": step_bytes, "step_achieved_gbs": step_bytes / (step_us * 1e-6) / 1e9,
+                "step_frac": step_bytes / (step_us * 1e-6) / 1e9 / peak_hbm,
+                "enc_pass1": {"algorithmic_bytes_per_launch": enc_bytes, "kernel_ms": kernel_ms["enc_pass1"], "achieved_gbs": p1_gbs,
+                              "frac": p1_gbs / peak_hbm}},
+        "traffic": traffic.get("enc_pass1_fused_kernel"),
+        "fp32_dense_equivalent": {"flops_per_step": enc_flops, "kernel": "enc_pass1", "kernel_ms": kernel_ms["enc_pass1"],
+                                  "achieved_tflops": enc_flops / (kernel_ms["enc_pass1"] * 1e-3) / 1e12,
+                                  "frac": enc_flops / (kernel_ms["enc_pass1"] * 1e-3) / p_fp32},
+    }
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": workload_config(B, world, {"l2_policy": "%d rotating input/output buffer sets (%.0f MB) > 126 MB L2" %
-                                                                  (R, R * per_set / 1e6),
-                                                     "cuda_graph": not args.no_graph, "two_stream_overlap": not args.no_overlap,
-                                                     "steps_in_flight": L, "inflight_outputs": "bit-identical to the serial run (checked on all sets)", "mean_gt_per_image": total_gt_mean / B}),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * K,
+                "config": workload_config(B, world),
+                "run": {"l2_policy": "%d rotating input/output buffer sets (%.0f MB) > 126 MB L2" % (R, R * per_set / 1e6),
+                        "cuda_graph": not args.no_graph, "two_stream_overlap": not args.no_overlap, "steps_in_flight": L,
+                        "inflight_outputs": "bit-identical to the serial run (checked on all sets)",
+                        "mean_gt_per_image": total_gt_mean / B,
+                        "gather": "ncclAllGather inside each step's CUDA graph (dan_gather_detections)" if world > 1 else None,
+                        "gather_check": gather_check, "host_cores_per_rank": cores_per_rank,
+                        "native_so_loaded": [os.path.relpath(_lib.LIB_PATH, ROOT)]},
+                "clocks": clocks, "e2e": e2e, "e2e_full": e2e_full, "gpu_launches": KERNELS_PER_STEP * K,
                 "roofline": roofline, "cpu_baseline": cpu_base,
                 "kernel_ms": kernel_ms, "step_kernel_ms_sum": step_kernel_sum,
                 "serial": {"ms_per_step": serial_ms / K, "value": world * B * K / (serial_ms * 1e-3), "unit": UNIT,
                            "note": "same K steps with one step in flight (step latency); `value` has %d steps in flight" % L}}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        # Teardown: the CUDA graphs hold references to the lanes' NCCL communicators, and ncclCommDestroy blocks while a
+        # captured graph still uses the communicator - release the graphs first, then the communicators.
+        torch.cuda.synchronize()
+        dist.barrier()
+        graphs.clear()
+        for s in sets:
+            s["hp"] = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        for g in gathers:
+            g.close()
         dist.destroy_process_group()
     return 0
 
@@ -512,7 +615,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough for 3x L2)")
-    ap.add_argument("--inflight", type=int, default=3, help="steps in flight (each on its own stream and workspaces)")
+    ap.add_argument("--inflight", type=int, default=5, help="steps in flight (each on its own stream and workspaces)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run encode and postprocess on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")

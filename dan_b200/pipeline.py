@@ -92,9 +92,55 @@ def gather_slab_group(send, recv, group=None):
     return recv
 
 
+class DeviceGather(object):
+    """The detection exchange on the DEVICE timeline: one NCCL communicator owned by libdan_b200
+    (dan_comm_init) and one ncclAllGather per call, enqueued on torch's current stream by
+    dan_gather_detections.  It is captured like any kernel when the step is recorded as a CUDA graph,
+    so a replayed step costs no host time for the collective.  torch.distributed is only used once, to
+    ship the 128-byte NCCL id from rank 0 to the other ranks."""
+
+    def __init__(self, rank, world_size, device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib as L
+        self.rank, self.world_size, self.device = int(rank), int(world_size), device
+        self._lib = L
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            L.check(L.lib().dan_comm_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if self.world_size > 1:
+            backend = dist.get_backend(group)
+            t = ident.to(device) if backend == "nccl" else ident
+            dist.broadcast(t, src=0, group=group)
+            ident = t.cpu()
+        raw = (ctypes.c_ubyte * 128)(*[int(v) for v in ident.tolist()])
+        comm = ctypes.c_void_p(0)
+        with torch.cuda.device(device):
+            L.check(L.lib().dan_comm_init(raw, self.rank, self.world_size, ctypes.byref(comm)))
+        self._comm = comm
+
+    def gather(self, send, recv):
+        """recv [world, len(send)] <- send of every rank (rank order), on the current stream."""
+        L = self._lib
+        if recv.numel() != self.world_size * send.numel() or recv.dtype != send.dtype:
+            raise ValueError("recv must hold world_size slabs of the send buffer's size and dtype")
+        with torch.cuda.device(self.device):
+            L.check(L.lib().dan_gather_detections(self._comm, L.dev_ptr(send), L.dev_ptr(recv), send.numel() * send.element_size(),
+                                                  L.stream_ptr()))
+        return recv
+
+    def close(self):
+        if self._comm is not None and self._comm.value:
+            self._lib.lib().dan_comm_destroy(self._comm)
+        self._comm = None
+
+
 def flatten_detections(gathered, image_counts=None):
     """Ragged result for the host: list over images (global order) of dict(class -> (boxes [n,4], scores [n])).
-    `image_counts[r]` = number of real images of rank r (ranks may own fewer images than the slab capacity)."""
+    `image_counts[r]` = number of real images of rank r (ranks may own fewer images than the slab capacity; HotPath
+    zeroes the unused tail of its slab, so without image_counts those rows read as images without detections)."""
     result = []
     for r, (counts, scores, boxes) in enumerate(gathered):
         n_img = counts.shape[0] if image_counts is None else image_counts[r]
@@ -115,7 +161,7 @@ class HotPath(object):
     (inside a CUDA-graph capture this becomes two parallel branches); each half has its own workspace."""
 
     def __init__(self, anchors_train, inside_mask, encode_params, postprocess_params, anchors_eval=None,
-                 images_per_rank=None, workspaces=None, overlap=True, slab_buffer=None):
+                 images_per_rank=None, workspaces=None, overlap=True, slab_buffer=None, device_gather=None, recv_buffer=None):
         from . import _lib
         self.anchors_train = anchors_train          # (ymin, xmin, ymax, xmax)
         self.inside_mask = inside_mask
@@ -128,6 +174,8 @@ class HotPath(object):
         self.overlap = overlap
         self._side = None
         self._slab_buffer = slab_buffer             # optional caller-owned storage of the detection slab
+        self._gather = device_gather                # DeviceGather: the all-gather is enqueued right after the NMS kernel
+        self._recv = recv_buffer                    # [world, slab words] when device_gather is given
         self._slab = None
         self._enc_out = None
         self._aux = None
@@ -154,6 +202,12 @@ class HotPath(object):
         images = gt_offsets.numel() - 1
         self._buffers(images)
         counts, scores, boxes = self._slab.views()
+        if images < self._slab.images:
+            # a rank that owns fewer images than the slab holds: the tail travels in the collective, it must not carry
+            # stale detections
+            counts[images:].zero_()
+            scores[images:].zero_()
+            boxes[images:].zero_()
         det_out = (boxes[:images], scores[:images], counts[:images], self._aux[0][:images], self._aux[1][:images])
         if profile or not self.overlap:
             enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
@@ -163,6 +217,7 @@ class HotPath(object):
             if profile:
                 return enc[0], det[0], {"enc_pass1": enc[1][0], "enc_pass2": enc[1][1], "enc_pass3": enc[1][2],
                                         "pp_filter": det[1][0], "nms_greedy": det[1][1]}
+            self._enqueue_gather()
             return enc, det
         main = torch.cuda.current_stream()
         if self._side is None:
@@ -173,8 +228,22 @@ class HotPath(object):
                                  out=self._enc_out, workspace=self.ws_enc)
         det = F.postprocess_batch(self.pp_params, cls_pred, loc_pred=loc_pred, anchors=self.anchors_eval,
                                   out=det_out, workspace=self.ws_pp)
+        self._enqueue_gather()      # on the stream that just ran the NMS kernel; the encode branch is not waited for
         main.wait_stream(self._side)
         return enc, det
 
+    def _enqueue_gather(self):
+        """The only exchange of the path: all-gather of the detection slabs, enqueued behind the NMS kernel."""
+        if self._gather is None:
+            return
+        if self._recv is None:
+            self._recv = torch.empty(self._gather.world_size * self._slab.words, dtype=torch.float32, device=self.device)
+        self._gather.gather(self._slab.buf, self._recv)
+
     def gather(self, world_size, group=None):
         return gather_detections(self._slab, world_size, group)
+
+    def gathered(self):
+        """Views (rank order) of the slabs the in-graph all-gather delivered (device_gather mode)."""
+        w = self._slab.words
+        return [self._slab.views(self._recv[r * w:(r + 1) * w]) for r in range(self._gather.world_size)]
