@@ -121,12 +121,10 @@ DAN_D float cephes_expf(float x) {
   y = fadd(fmul(y, x), 5.0000001201e-1f);
   y = fadd(fmul(y, z), x);
   y = fadd(y, 1.f);
+  // 2^n built in ONE step, (n + 127) << 23, as Eigen's pexp does: n = -127 (x - max below about -87.7) gives the
+  // factor +0 and the result 0, not a denormal; n = 128 gives inf
   const int n = (int)fx;
-  const int n1 = n >> 1;
-  const int n2 = n - n1;
-  const float p1 = __int_as_float((n1 + 127) << 23);
-  const float p2 = __int_as_float((n2 + 127) << 23);
-  return fmul(fmul(y, p1), p2);
+  return fmul(y, __int_as_float((n + 127) << 23));
 }
 
 DAN_D float cephes_logf(float x) {

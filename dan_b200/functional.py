@@ -6,6 +6,7 @@ torch's current stream.  No arithmetic of the hot path is done in PyTorch."""
 from __future__ import annotations
 
 import ctypes
+import os
 from collections import namedtuple
 
 import torch
@@ -210,6 +211,11 @@ def encode_batch(params, ymin, xmin, ymax, xmax, inside_mask, gt_boxes, gt_offse
     else:
         targets, labels, scores, matched, match = out
     mask = _mask_u8(inside_mask)
+    if os.environ.get("DAN_B200_DEBUG"):
+        # the CSR contract of dan_encode_batch (costs a device synchronisation, hence debug only)
+        offs = gt_offsets.cpu()
+        if int(offs[0]) != 0 or int(offs[-1]) != total_gt or bool((offs[1:] < offs[:-1]).any()):
+            raise ValueError("gt_offsets must rise from 0 to len(gt_boxes) = %d, got %s ... %s" % (total_gt, int(offs[0]), int(offs[-1])))
     nbytes = L.lib().dan_encode_workspace_bytes(n, batch, total_gt)
     ws = (workspace or _ws).get(nbytes, dev)
     args = [ctypes.byref(params), *_anchor_ptrs(ymin, xmin, ymax, xmax), L.dev_ptr(mask), n,

@@ -63,14 +63,11 @@ def expf(x):
     y = y * z + x
     y = y + f32(1.0)
     n = fx.astype(i32)
-    # n in [-128, 128]; 2^n is applied as two normal factors 2^(n>>1) * 2^(n-(n>>1))
-    # (2^128 and 2^-128 are not representable as one fp32 factor)
-    n1 = n >> 1
-    n2 = n - n1
-    p1 = ((n1 + 127).astype(np.uint32) << np.uint32(23)).view(f32)
-    p2 = ((n2 + 127).astype(np.uint32) << np.uint32(23)).view(f32)
-    with np.errstate(over="ignore", under="ignore"):
-        return (y * p1) * p2
+    # n in [-127, 128]; 2^n is built in ONE step, (n + 127) << 23, like Eigen's pexp: n = -127 gives the factor +0 (the
+    # result flushes to 0 instead of a denormal), n = 128 gives inf
+    p = ((n + 127).astype(np.uint32) << np.uint32(23)).view(f32)
+    with np.errstate(over="ignore", under="ignore", invalid="ignore"):
+        return y * p
 
 
 def logf(x):

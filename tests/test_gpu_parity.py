@@ -810,3 +810,174 @@ def test_input_handoff_feeds_encode(cuda, oracle, s3fd_anchors_np):
     for k in range(len(r_idx)):
         ref = e_ref.encode_anchors(r_boxes[r_offs[k]:r_offs[k + 1]], *s3fd_anchors_np, match_mining=True)
         _check_encode(ref, [res.targets[k], res.labels[k], res.scores[k], res.matched_gt[k]], "kept image %d" % k)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: stress paths of the fused encode, full-size keep-lists, the sharded batch, numerics edges
+# ------------------------------------------------------------------------------------------------
+def _fused_mining_vs_matcher(cuda, oracle, anchors_np, gts, pos, ign, min_match, stop):
+    """dan_encode_batch with arbitrary mining attributes against the matcher run on the materialised overlaps."""
+    from dan_b200 import functional as F
+    anchors = [to_dev(v, cuda) for v in anchors_np]
+    cat, offs = synthetic.to_csr(gts)
+    params = F.encode_params(pos, ign, PS, match_mining=True, min_match=min_match, stop_positive_thres=stop)
+    res = F.encode_batch(params, *anchors[:4], anchors[4], to_dev(cat, cuda), to_dev(offs, cuda), want_match=True)
+    a4 = np.stack(anchors_np[:4], -1)
+    n_comp = 0
+    for b, gt in enumerate(gts):
+        g = gt if len(gt) else np.array([[0., 0., 1., 1.]], np.float32)
+        ov = oracle.iou_matrix(a4, g) * anchors_np[4].astype(np.float32)[:, None]
+        rm, rs = oracle.small_mining_match(ov, 0., ign, pos, min_match, stop, impl="reference" if _have_ref() else "port")
+        np.testing.assert_array_equal(_np(res.match[b]), rm, err_msg="image %d match" % b)
+        np.testing.assert_array_equal(_np(res.scores[b]), rs, err_msg="image %d scores" % b)
+        np.testing.assert_array_equal(_np(res.labels[b]), (rm > -1).astype(np.int64) - (rm < -1).astype(np.int64))
+        s1 = ov.max(1)                                     # anchors that stage 3 turned positive
+        n_comp += int(((rm >= 0) & (s1 < pos)).sum())
+    return n_comp
+
+
+def _have_ref():
+    from oracle import native
+    return native.have_reference()
+
+
+def test_fused_encode_bucket_overflow_and_large_min_match(cuda, oracle, s3fd_anchors_np):
+    """stop_positive_thres 0.01 puts hundreds of candidates into every GT's bucket (> kBucketCap = 64: the rescan path
+    of pass 3), min_match 40 / 3000 makes every GT needy and lets neighbouring GTs compete for the same anchors (the
+    windows and rounds of pass 3, its selection budget); the reference functor is the judge."""
+    gts = [synthetic.gen_faces(70 + i, 12, snap=(4.0 if i == 1 else 0.0)) for i in range(3)]
+    gts.append(synthetic.gen_adversarial("duplicate"))
+    gts.append(np.concatenate([synthetic.gen_faces(75, 6, smin=60.0, smax=90.0)] * 2) + np.float32(3.0))     # overlapping pairs
+    for min_match, stop in ((40, 0.01), (3000, 0.2), (6, 0.05)):
+        n = _fused_mining_vs_matcher(cuda, oracle, s3fd_anchors_np, gts, 0.4, 0.4, min_match, stop)
+        assert n > 0
+
+
+def test_fused_encode_many_needy_gts(cuda, oracle, s3fd_anchors_np):
+    """more needy GTs than one window of pass 3 holds (64) and more than one scan range (1024), dense tiny faces that
+    share candidate anchors: the serial dependence between the windows."""
+    gts = [synthetic.gen_dense_tiny(3, lo=1100, hi=1200), synthetic.gen_dense_tiny(4, lo=150, hi=200, snap=2.0)]
+    n = _fused_mining_vs_matcher(cuda, oracle, s3fd_anchors_np, gts, 0.4, 0.4, 6, 0.3)
+    assert n > 100
+
+
+@pytest.mark.parametrize("size,faces", [((1280, 1280), 200), ((1600, 1600), 300)])
+def test_parse_by_class_keep_lists_full_size(cuda, oracle, size, faces):
+    """config 4 at 1280^2 and 1600^2 (213 294 anchors): the keep-list itself against the oracle, one image each."""
+    from dan_b200.utility import bbox_util as bu
+    cfg = synthetic.pyramid_config("s3fd", size, border=0.)
+    a_np = synthetic.build_anchors(oracle.AnchorEncoder(None, None, PS), cfg)
+    an = np.stack(a_np[:4], -1)
+    anchors = [to_dev(v, cuda) for v in a_np[:4]]
+    cls, loc, _ = synthetic.gen_predictions(500 + size[0], an, size=size, max_faces=faces)
+    det = bu.parse_by_class_batch(list(size), to_dev(cls[None], cuda), 2, 0.01, 0, 5000, 750, 0.3, loc_pred=to_dev(loc[None], cuda),
+                                  anchors=anchors)
+    boxes, (sb, ss, idx) = _oracle_parse(oracle, size, cls, loc, a_np)
+    np.testing.assert_array_equal(_np(det.scores[0, 0]), ss[1])
+    np.testing.assert_array_equal(_np(det.boxes[0, 0]), sb[1])
+    top_idx, keep = idx[1]
+    k = int((ss[1] > 0).sum())
+    assert int(det.counts[0, 0]) == k and k > 50
+    np.testing.assert_array_equal(_np(det.keep_pos[0, 0])[:len(keep)], keep)
+    np.testing.assert_array_equal(_np(det.anchor_index[0, 0])[:k], top_idx[keep[:k]])
+
+
+def test_sharded_batch_256_matches_oracle(cuda, oracle, s3fd_anchors_np):
+    """config 5: B = 256 images through shard_range -> HotPath.step -> the detection exchange.  On one GPU the 8 ranks run
+    one after the other and their slabs are concatenated the way the all-gather lays them out (on a multi-GPU box the
+    driver's scaling run and bench.py's checksum test cover the NCCL path; tests/test_abi_and_host.py the gloo one);
+    sampled images of every shard are compared with the oracle."""
+    import torch
+    from dan_b200 import functional as F, pipeline
+    from dan_b200.utility import anchor_manipulator as am
+    B, world = 256, 8
+    enc = am.AnchorEncoder(0.4, 0.4, PS)
+    a_train = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd"))
+    a_eval = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", border=0.))
+    ev_np = synthetic.build_anchors(oracle.AnchorEncoder(None, None, PS), synthetic.pyramid_config("s3fd", border=0.))
+    an = np.stack(ev_np[:4], -1)
+    sample = {r: [pipeline.shard_range(B, r, world).lo, pipeline.shard_range(B, r, world).hi - 1] for r in range(world)}
+    gts = {i: synthetic.gen_faces(900 + i, 50) for i in range(B)}
+    enc_params = F.encode_params(0.4, 0.4, PS, match_mining=True)
+    pp_params = F.postprocess_params(2, (640, 640), 0.01, 0, 5000, 750, 0.3, prior_scaling=PS)
+    one = pipeline.DeviceGather(0, 1, cuda)              # world size 1: the C-ABI collective degenerates to a copy
+    slabs = []
+    e_ref = oracle.AnchorEncoder(0.4, 0.4, PS)
+    for r in range(world):
+        sh = pipeline.shard_range(B, r, world)
+        assert sh.hi - sh.lo == 32
+        preds = {i: synthetic.gen_predictions(900 + i, an, max_faces=40) for i in sample[r]}
+        cls = np.zeros((32, an.shape[0], 2), np.float32)
+        cls[:, :, 0] = 10.0                                   # images that are not sampled: nothing passes the threshold
+        loc = np.zeros((32, an.shape[0], 4), np.float32)
+        for i in sample[r]:
+            cls[i - sh.lo], loc[i - sh.lo] = preds[i][0], preds[i][1]
+        cat, offs = synthetic.to_csr([gts[i] for i in range(sh.lo, sh.hi)])
+        hp = pipeline.HotPath(a_train[:4], a_train[4], enc_params, pp_params, anchors_eval=a_eval[:4], device_gather=one)
+        res, det = hp.step(to_dev(cat, cuda), to_dev(offs, cuda), to_dev(cls, cuda), to_dev(loc, cuda))
+        torch.cuda.synchronize()
+        (counts, scores, boxes), = hp.gathered()
+        assert torch.equal(hp._recv, hp._slab.buf)
+        slabs.append((counts.clone(), scores.clone(), boxes.clone()))
+        for i in sample[r]:
+            ref = e_ref.encode_anchors(gts[i], *s3fd_anchors_np, match_mining=True)
+            _check_encode(ref, [res.targets[i - sh.lo], res.labels[i - sh.lo], res.scores[i - sh.lo], res.matched_gt[i - sh.lo]],
+                          "image %d" % i)
+            _, (sb, ss, _) = _oracle_parse(oracle, (640, 640), preds[i][0], preds[i][1], ev_np)
+            np.testing.assert_array_equal(_np(scores[i - sh.lo, 0]), ss[1], err_msg="image %d" % i)
+            np.testing.assert_array_equal(_np(boxes[i - sh.lo, 0]), sb[1], err_msg="image %d" % i)
+    flat = pipeline.flatten_detections(slabs)
+    assert len(flat) == B
+    for r in range(world):
+        for i in range(B // world):
+            n = int(slabs[r][0][i, 0])
+            assert flat[r * 32 + i][1][0].shape[0] == n
+            assert (n > 0) == ((r * 32 + i) in sample[r])
+    one.close()
+
+
+def test_softmax_logit_gaps_beyond_exp_range(cuda, oracle):
+    """logit gaps above ~87.7: exp(x - max) flushes to exactly 0 (2^n is built in one step, like Eigen's pexp), so the
+    probability is 0, not a denormal; the filter's quick reject must agree with the exact path there."""
+    from dan_b200 import functional as F
+    from dan_b200.utility import bbox_util as bu
+    gaps = np.array([86.0, 87.0, 87.3, 87.5, 87.7, 88.0, 88.4, 90.0, 120.0, 1e4, 3e5], np.float32)
+    logits = np.stack([np.concatenate([gaps, np.zeros_like(gaps)]), np.concatenate([np.zeros_like(gaps), gaps])], 1)
+    ref = oracle.softmax(logits)
+    np.testing.assert_array_equal(_np(F.softmax(to_dev(logits, cuda))), ref)
+    assert ref.min() == 0.0
+    n = logits.shape[0]
+    boxes = np.tile(np.array([[10., 10., 50., 50.]], np.float32), (n, 1)) + np.arange(n, dtype=np.float32)[:, None] * 60
+    sb, ss = bu.parse_by_class([4000, 4000], to_dev(logits, cuda), to_dev(boxes, cuda), 2, 0.0, 0, 100, 100, 0.5)
+    rb, rs = oracle.parse_by_class([4000, 4000], logits, boxes, 2, 0.0, 0, 100, 100, 0.5)
+    np.testing.assert_array_equal(_np(ss[1]), rs[1])
+    np.testing.assert_array_equal(_np(sb[1]), rb[1])
+
+
+def test_device_gather_single_rank(cuda):
+    """dan_gather_detections through the C ABI with a one-rank communicator (ncclAllGather of one slab), eagerly and
+    captured in a CUDA graph."""
+    import torch
+    from dan_b200 import pipeline
+    g = pipeline.DeviceGather(0, 1, cuda)
+    send = torch.arange(4096, dtype=torch.float32, device=cuda)
+    recv = torch.zeros_like(send)
+    g.gather(send, recv)
+    torch.cuda.synchronize()
+    assert torch.equal(send, recv)
+    recv.zero_()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            g.gather(send, recv)
+    torch.cuda.current_stream().wait_stream(side)
+    send.mul_(2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(send, recv)
+    del graph
+    with pytest.raises(ValueError):
+        g.gather(send, recv[:100])
+    g.close()
