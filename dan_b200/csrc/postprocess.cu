@@ -56,6 +56,7 @@ struct PpArgs {
   float nms_thr;
   // shared-memory plan of the NMS kernel (greedy_plan)
   int sort_bytes, kcap, wcap, cand_global, kept_global;
+  int kstride;                // per-list stride of the candidate arrays = min(keep_topk, n)
   // workspace
   unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
   int32_t* key_count;         // [L]
@@ -63,7 +64,8 @@ struct PpArgs {
   float* s_scores;            // sort_bboxes outputs [keep_topk]
   float4* s_boxes;
   int32_t* s_index;
-  unsigned long long* s_key;  // [L, keep_topk] sorted keys
+  unsigned long long* s_key;  // [L, kstride] sorted keys
+  unsigned long long* s_key2; // [L, kstride] merge buffer of lists longer than the in-shared-memory sort
   float4* s_box;              // [L, keep_topk] normalised corners (y0, x0, y1, x1), rank order (lists too long for shared memory)
   float* s_area;              // [L, keep_topk] (y1-y0)*(x1-x0)
   float4* g_kept_box;         // [L, keep_topk] kept list of the NMS when it does not fit shared memory
@@ -245,10 +247,16 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const PpArgs
   const int tid = threadIdx.x;
   const int cnt = min(A.key_count[0], A.n);
   const int k = min(A.keep_topk, cnt);
-  select_and_sort(A.keys, cnt, k, s_keys, sc);
+  const unsigned long long* sorted = s_keys;
+  if (k <= kSortCap) {
+    select_and_sort(A.keys, cnt, k, s_keys, sc);
+  } else {
+    select_and_sort_large(A.keys, cnt, k, A.s_key, A.s_key2, s_keys, sc);
+    sorted = A.s_key;
+  }
   for (int r = tid; r < A.keep_topk; r += kSortThreads) {
     if (r < k) {
-      const uint32_t idx = key_index(s_keys[r]);
+      const uint32_t idx = key_index(sorted[r]);
       A.s_scores[r] = src_scores[idx];
       A.s_boxes[r] = src_boxes[idx];
       if (A.s_index != nullptr) A.s_index[r] = (int32_t)idx;
@@ -359,7 +367,7 @@ static GreedyPlan greedy_plan(int64_t n, int keep_topk, int nms_cap) {
   GreedyPlan g;
   const int sort_n = (int)(n < kSortCap ? (n > 0 ? n : 1) : kSortCap);
   g.sort_bytes = next_pow2(sort_n) * 8;
-  g.kcap = keep_topk < sort_n ? keep_topk : sort_n;
+  g.kcap = (int)(keep_topk < n ? keep_topk : (n > 0 ? n : 1));      // candidate slots: no upper limit (the workspace holds them then)
   g.wcap = (nms_cap + 31) / 32;
   const size_t kept_bytes = align_up((size_t)nms_cap * 16, 16) + 2 * align_up((size_t)nms_cap * 4, 16) + (size_t)64 * g.wcap * 4;
   const size_t cand_box = align_up((size_t)g.kcap * 16, 16);
@@ -481,7 +489,7 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) nms_greedy_
   const int warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int b = list / max(A.num_classes - 1, 1);
-  const int64_t o = (int64_t)list * A.keep_topk;
+  const int64_t o = (int64_t)list * A.kstride;
   const float thr = A.nms_thr;
 
   // ---- carve
@@ -508,11 +516,11 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) nms_greedy_
   uint32_t* stripes;                                   // [2][32][wcap]: kept boxes touching x stripe s / y stripe s
   const int wcap = A.wcap;
   if (WHERE >= 2) {
-    const int64_t ok = (int64_t)list * A.keep_topk;
+    const int64_t ok = (int64_t)list * A.kstride;
     kbox = A.g_kept_box + ok;
     karea = A.g_kept_area + ok;
     krank = A.g_kept_rank + ok;
-    stripes = A.g_stripes + (int64_t)list * 64 * ((A.keep_topk + 31) / 32);
+    stripes = A.g_stripes + (int64_t)list * 64 * ((A.kstride + 31) / 32);
   } else {
     kbox = reinterpret_cast<float4*>(p); p += ((size_t)A.nms_cap * 16 + 15) / 16 * 16;
     karea = reinterpret_cast<float*>(p); p += ((size_t)A.nms_cap * 4 + 15) / 16 * 16;
@@ -598,7 +606,16 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) nms_greedy_
 
   // ---- 1. top-k + sort
   DAN_PHASE(8);
-  const int K = min(select_and_sort(gkeys, cnt, min(A.keep_topk, cnt), keys, sc, FILTER), A.keep_topk);
+  const int k_want = min(A.keep_topk, cnt);
+  int K;
+  const unsigned long long* sorted = keys;            // shared memory, or A.s_key for lists longer than kSortCap
+  if (k_want <= kSortCap) {
+    K = min(select_and_sort(gkeys, cnt, k_want, keys, sc, FILTER), A.keep_topk);
+  } else {
+    select_and_sort_large(gkeys, cnt, k_want, A.s_key + o, A.s_key2 + o, keys, sc);
+    sorted = A.s_key + o;
+    K = k_want;
+  }
   DAN_PHASE(1);
 
   // ---- 2. decode + clip + normalise.  The candidate boxes (16 B) reuse the shared memory of the keys (8 B): the ranks
@@ -606,7 +623,7 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) nms_greedy_
   // are already done (box r covers key slots 2r and 2r+1 >= r); the barrier protects the batch's own keys.
   for (int r0 = K > 0 ? ((K - 1) / kSortThreads) * kSortThreads : -1; r0 >= 0; r0 -= kSortThreads) {
     const int r = r0 + tid;
-    const unsigned long long key = (r < K) ? keys[r] : 0ull;
+    const unsigned long long key = (r < K) ? sorted[r] : 0ull;
     if (r < K) A.s_key[o + r] = key;
     __syncthreads();
     if (r < K) {
@@ -889,24 +906,26 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) nms_greedy_
 // ---------------------------------------------------------------------------
 
 struct PpLayout {
-  size_t key_count, keys, maybe, s_key, s_box, s_area, kept_box, kept_area, kept_rank, s_mask, stripes, total;
+  size_t key_count, keys, maybe, s_key, s_key2, s_box, s_area, kept_box, kept_area, kept_rank, s_mask, stripes, total;
 };
 
 static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms) {
   PpLayout w;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
+  const int64_t ks = keep_topk < n ? keep_topk : (n > 0 ? n : 1);      // kstride
   w.key_count = take(lists * 4);
   w.keys = take(lists * n * 8);
   w.maybe = take(nms ? lists * n * 4 : 0);
-  w.s_key = take(nms ? lists * keep_topk * 8 : 0);
-  w.s_box = take(nms ? lists * keep_topk * 16 : 0);
-  w.s_area = take(nms ? lists * keep_topk * 4 : 0);
-  w.kept_box = take(nms ? lists * keep_topk * 16 : 0);
-  w.kept_area = take(nms ? lists * keep_topk * 4 : 0);
-  w.kept_rank = take(nms ? lists * keep_topk * 4 : 0);
-  w.s_mask = take(nms ? lists * keep_topk * 8 : 0);
-  w.stripes = take(nms ? lists * 64 * ((keep_topk + 31) / 32) * 4 : 0);
+  w.s_key = take(lists * ks * 8);
+  w.s_key2 = take(lists * ks * 8);
+  w.s_box = take(nms ? lists * ks * 16 : 0);
+  w.s_area = take(nms ? lists * ks * 4 : 0);
+  w.kept_box = take(nms ? lists * ks * 16 : 0);
+  w.kept_area = take(nms ? lists * ks * 4 : 0);
+  w.kept_rank = take(nms ? lists * ks * 4 : 0);
+  w.s_mask = take(nms ? lists * ks * 8 : 0);
+  w.stripes = take(nms ? lists * 64 * ((ks + 31) / 32) * 4 : 0);
   w.total = off;
   return w;
 }
@@ -917,6 +936,7 @@ static void pp_bind(PpArgs& A, void* ws, const PpLayout& w) {
   A.keys = reinterpret_cast<unsigned long long*>(base + w.keys);
   A.maybe = reinterpret_cast<int32_t*>(base + w.maybe);
   A.s_key = reinterpret_cast<unsigned long long*>(base + w.s_key);
+  A.s_key2 = reinterpret_cast<unsigned long long*>(base + w.s_key2);
   A.s_box = reinterpret_cast<float4*>(base + w.s_box);
   A.s_area = reinterpret_cast<float*>(base + w.s_area);
   A.g_kept_box = reinterpret_cast<float4*>(base + w.kept_box);
@@ -944,6 +964,7 @@ static int run_sort_nms(const PpArgs& A_in, int lists, const float* src_scores, 
   A.sort_bytes = g.sort_bytes;
   A.kcap = g.kcap;
   A.wcap = g.wcap;
+  A.kstride = g.kcap;
   A.cand_global = g.cand_global;
   A.kept_global = g.kept_global;
   if (g.kept_global) return launch_greedy<DECODE, 2, FILTER>(A, lists, g.smem, src_scores, src_boxes, st);
@@ -968,7 +989,7 @@ size_t dan_postprocess_workspace_bytes(int32_t num_anchors, int32_t batch, int32
 
 size_t dan_sort_workspace_bytes(int64_t n, int32_t keep_topk) {
   if (n < 0 || keep_topk < 1) return 0;
-  return pp_layout(n, 1, 1, false).total;
+  return pp_layout(n, 1, keep_topk, false).total;
 }
 
 size_t dan_nms_workspace_bytes(int64_t n, int32_t nms_topk) {
@@ -987,8 +1008,6 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   DAN_REQUIRE(p->select_threshold >= 0.f, DAN_ERR_INVALID_ARGUMENT,
               "select_threshold must be >= 0 (a negative threshold would let zero-score rows carry boxes), got %g", p->select_threshold);
   DAN_REQUIRE(p->keep_topk >= 1 && p->nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "keep_topk and nms_topk must be >= 1");
-  DAN_REQUIRE(p->keep_topk <= kSortCap || num_anchors <= kSortCap, DAN_ERR_UNSUPPORTED,
-              "min(keep_topk, num_anchors) = %d exceeds the in-shared-memory sort capacity %d", p->keep_topk, kSortCap);
   DAN_REQUIRE((loc_pred != nullptr) != (boxes_pred != nullptr), DAN_ERR_INVALID_ARGUMENT, "exactly one of loc_pred / boxes_pred must be given");
   if (batch == 0) return DAN_OK;
   DAN_REQUIRE(cls_pred && out_boxes && out_scores, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
@@ -1074,10 +1093,9 @@ int dan_postprocess_batch_profile(const dan_postprocess_params* p, const float* 
 int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t keep_topk, float* out_scores, float* out_boxes,
                     int32_t* out_index, void* workspace, size_t workspace_bytes, void* stream) {
   DAN_REQUIRE(n >= 0 && n < 0x7fffffff && keep_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "bad size");
-  DAN_REQUIRE(keep_topk <= kSortCap || n <= kSortCap, DAN_ERR_UNSUPPORTED, "min(keep_topk, n) exceeds the sort capacity %d", kSortCap);
   DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");
   DAN_REQUIRE(n == 0 || (scores && boxes && aligned16(boxes)), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned input");
-  const PpLayout w = pp_layout(n, 1, 1, false);
+  const PpLayout w = pp_layout(n, 1, keep_topk, false);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   DAN_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortCap * 8)));
@@ -1100,7 +1118,7 @@ int dan_sort_bboxes(const float* scores, const float* boxes, int64_t n, int32_t 
 int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t nms_topk, float nms_threshold, float* out_scores,
                    float* out_boxes, int32_t* out_keep, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
   DAN_REQUIRE(n >= 0 && nms_topk >= 1, DAN_ERR_INVALID_ARGUMENT, "bad size");
-  DAN_REQUIRE(n <= kSortCap, DAN_ERR_UNSUPPORTED, "n %lld exceeds the sort capacity %d", (long long)n, kSortCap);
+  DAN_REQUIRE(n < 0x7fffffff, DAN_ERR_INVALID_ARGUMENT, "bad size");
   const int n_eff = n > 0 ? (int)n : 1;
   const int cap = nms_topk < n_eff ? nms_topk : n_eff;
   DAN_REQUIRE(out_scores && out_boxes && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "NULL / misaligned output");

@@ -146,6 +146,35 @@ DAN_D void sort_smem_keys(unsigned long long* s_keys, int m) {
   }
 }
 
+// k-th largest of the cnt keys in `keys` (HBM): block radix select, MSB first, 8 bits per pass
+DAN_D unsigned long long radix_select_kth(const unsigned long long* __restrict__ keys, int cnt, int k, SortScratch& sc) {
+  const int tid = threadIdx.x;
+  if (tid == 0) { sc.prefix = 0ull; sc.remaining = k; }
+  unsigned long long prefix_mask = 0ull;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += kSortThreads) sc.hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = sc.prefix;
+    for (int i = tid; i < cnt; i += kSortThreads) {
+      const unsigned long long key = keys[i];
+      if ((key & prefix_mask) == prefix) atomicAdd(&sc.hist[(int)((key >> shift) & 255ull)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int cum = 0, bin = 255;
+      for (; bin > 0; --bin) {
+        if (cum + sc.hist[bin] >= sc.remaining) break;
+        cum += sc.hist[bin];
+      }
+      sc.remaining -= cum;
+      sc.prefix = prefix | ((unsigned long long)bin << shift);
+    }
+    prefix_mask |= 255ull << shift;
+    __syncthreads();
+  }
+  return sc.prefix;
+}
+
 // staged = true: when cnt <= kSortCap the keys are already in s_keys[0, cnt) (the caller produced them there)
 DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, int k, unsigned long long* s_keys, SortScratch& sc,
                           bool staged = false) {
@@ -155,31 +184,7 @@ DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, 
     if (!staged)
       for (int i = tid; i < cnt; i += kSortThreads) s_keys[i] = keys[i];
   } else {
-    // block radix select, MSB first, 8 bits per pass: find the k-th largest key
-    if (tid == 0) { sc.prefix = 0ull; sc.remaining = k; }
-    unsigned long long prefix_mask = 0ull;
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      for (int i = tid; i < 256; i += kSortThreads) sc.hist[i] = 0;
-      __syncthreads();
-      const unsigned long long prefix = sc.prefix;
-      for (int i = tid; i < cnt; i += kSortThreads) {
-        const unsigned long long key = keys[i];
-        if ((key & prefix_mask) == prefix) atomicAdd(&sc.hist[(int)((key >> shift) & 255ull)], 1);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int cum = 0, bin = 255;
-        for (; bin > 0; --bin) {
-          if (cum + sc.hist[bin] >= sc.remaining) break;
-          cum += sc.hist[bin];
-        }
-        sc.remaining -= cum;
-        sc.prefix = prefix | ((unsigned long long)bin << shift);
-      }
-      prefix_mask |= 255ull << shift;
-      __syncthreads();
-    }
-    const unsigned long long kth = sc.prefix;
+    const unsigned long long kth = radix_select_kth(keys, cnt, k, sc);
     if (tid == 0) sc.fill = 0;
     __syncthreads();
     for (int i = tid; i < cnt; i += kSortThreads) {
@@ -193,5 +198,55 @@ DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, 
   return m;
 }
 
-
-
+// More than kSortCap keys to keep (no upper limit): the k largest of `keys` are compacted into buf_a (HBM), sorted in
+// runs of kSortCap in shared memory, and the runs are merged pairwise between buf_a and buf_b - every key finds its place
+// in the merged run by a binary search in the other run (keys are unique).  The sorted keys end in buf_a.  One CTA; meant
+// for the rare long lists (tf.nn.top_k / tf.image.non_max_suppression have no size limit, so neither does this path).
+DAN_D void select_and_sort_large(const unsigned long long* __restrict__ keys, int cnt, int k, unsigned long long* buf_a,
+                                 unsigned long long* buf_b, unsigned long long* s_keys, SortScratch& sc) {
+  const int tid = threadIdx.x;
+  if (cnt > k) {
+    const unsigned long long kth = radix_select_kth(keys, cnt, k, sc);
+    if (tid == 0) sc.fill = 0;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += kSortThreads) {
+      const unsigned long long key = keys[i];
+      if (key >= kth) buf_a[atomicAdd(&sc.fill, 1)] = key;
+    }
+  } else {
+    for (int i = tid; i < k; i += kSortThreads) buf_a[i] = keys[i];
+  }
+  __syncthreads();
+  for (int r0 = 0; r0 < k; r0 += kSortCap) {
+    const int m = min(kSortCap, k - r0);
+    for (int i = tid; i < m; i += kSortThreads) s_keys[i] = buf_a[r0 + i];
+    __syncthreads();
+    sort_smem_keys(s_keys, m);
+    for (int i = tid; i < m; i += kSortThreads) buf_a[r0 + i] = s_keys[i];
+    __syncthreads();
+  }
+  unsigned long long* src = buf_a;
+  unsigned long long* dst = buf_b;
+  for (long long run = kSortCap; run < k; run *= 2) {
+    for (int i = tid; i < k; i += kSortThreads) {
+      const long long base = (i / (2 * run)) * (2 * run);
+      const bool second = i - base >= run;
+      const long long x_lo = base + (second ? run : 0), y_lo = base + (second ? 0 : run);
+      const long long y_len = max(0ll, min(run, (long long)k - y_lo));
+      const unsigned long long key = src[i];
+      long long lo = 0, hi = y_len;                       // number of keys of the other run that precede `key`
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (src[y_lo + mid] > key) lo = mid + 1;
+        else hi = mid;
+      }
+      dst[base + (i - x_lo) + lo] = key;
+    }
+    __syncthreads();
+    unsigned long long* t = src; src = dst; dst = t;
+  }
+  if (src != buf_a) {
+    for (int i = tid; i < k; i += kSortThreads) buf_a[i] = src[i];
+    __syncthreads();
+  }
+}

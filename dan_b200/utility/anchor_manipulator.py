@@ -70,19 +70,17 @@ class AnchorEncoder(object):
 
     # ---- :134-161 ------------------------------------------------------------------
     def get_anchors_width_height(self, anchor_scale, extra_anchor_scale, anchor_ratio, name=None):
-        """Host constants (the reference builds tf.constant(float32) from python floats)."""
-        all_num_anchors_depth = len(anchor_scale) * len(anchor_ratio) + len(extra_anchor_scale)
-        list_h_on_image = []
-        list_w_on_image = []
-        for _, scale in enumerate(extra_anchor_scale):
-            list_h_on_image.append(scale)
-            list_w_on_image.append(scale)
-        for scale_index, scale in enumerate(anchor_scale):
-            for ratio_index, ratio in enumerate(anchor_ratio):
-                list_h_on_image.append(scale / math.sqrt(ratio))
-                list_w_on_image.append(scale * math.sqrt(ratio))
-        return (torch.tensor(list_h_on_image, dtype=torch.float32), torch.tensor(list_w_on_image, dtype=torch.float32),
-                all_num_anchors_depth)
+        """Heights / widths of the anchors of one layer, in depth order: first one square anchor per extra scale, then
+        for every scale each aspect ratio r as (s / sqrt(r), s * sqrt(r)).  Computed in python doubles and rounded to
+        fp32 once, which is what the reference's tf.constant(float32) of python floats does.
+
+        -> (heights [depth], widths [depth], depth)"""
+        squares = [(float(s), float(s)) for s in extra_anchor_scale]
+        shaped = [(float(s) / math.sqrt(r), float(s) * math.sqrt(r)) for s in anchor_scale for r in anchor_ratio]
+        sizes = squares + shaped
+        heights = torch.tensor([h for h, _ in sizes], dtype=torch.float32)
+        widths = torch.tensor([w for _, w in sizes], dtype=torch.float32)
+        return heights, widths, len(sizes)
 
     # ---- :163-198 ------------------------------------------------------------------
     def generate_anchors_by_offset(self, anchors_height, anchors_width, anchor_depth, image_shape, layer_shape,
@@ -95,9 +93,9 @@ class AnchorEncoder(object):
 
     # ---- :200-211 ------------------------------------------------------------------
     def get_anchors_count(self, anchors_depth, layer_shape, name=None):
-        all_num_anchors_spatial = layer_shape[0] * layer_shape[1]
-        all_num_anchors = all_num_anchors_spatial * anchors_depth
-        return all_num_anchors_spatial, all_num_anchors
+        """-> (cells of the layer, anchors of the layer = cells * depth)."""
+        cells = int(layer_shape[0]) * int(layer_shape[1])
+        return cells, cells * anchors_depth
 
     # ---- :213-273 ------------------------------------------------------------------
     def get_all_anchors(self, image_shape, anchors_height, anchors_width, anchors_depth, anchors_offsets, layer_shapes,

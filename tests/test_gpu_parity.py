@@ -382,7 +382,8 @@ def test_bbox_util_elementwise(cuda, oracle):
     np.testing.assert_array_equal(_np(bu.bbox_center2point(to_dev(boxes, cuda))), oracle.bbox_center2point(boxes))
 
 
-@pytest.mark.parametrize("n,k", [(34125, 5000), (213294, 5000), (3000, 5000), (9000, 100), (1, 4), (8192, 8192)])
+@pytest.mark.parametrize("n,k", [(34125, 5000), (213294, 5000), (3000, 5000), (9000, 100), (1, 4), (8192, 8192),
+                                 (20000, 15000), (70000, 70000)])       # beyond the in-shared-memory sort: runs + merges in HBM
 def test_sort_bboxes_vs_oracle(cuda, oracle, n, k):
     from dan_b200.utility import bbox_util as bu
     rng = np.random.default_rng(n + k)
@@ -398,7 +399,7 @@ def test_sort_bboxes_vs_oracle(cuda, oracle, n, k):
 
 
 @pytest.mark.parametrize("n,topk,thr", [(5000, 750, 0.3), (2000, 50, 0.5), (300, 750, 0.3), (64, 10, 0.0), (65, 100, 0.7),
-                                       (8192, 750, 0.3)])      # 8192: beyond the pair kernel's staging -> round-based NMS
+                                       (8192, 750, 0.3), (12000, 750, 0.3), (20000, 20000, 0.6)])   # > 8192: no size limit
 def test_nms_bboxes_vs_oracle(cuda, oracle, n, topk, thr):
     from dan_b200.utility import bbox_util as bu
     rng = np.random.default_rng(n + topk)
@@ -565,9 +566,8 @@ def test_postprocess_errors(cuda):
     box = torch.zeros((1, 100, 4), device=cuda)
     with pytest.raises(_lib.DanError):
         bu.parse_by_class_batch([64, 64], cls, 2, -0.5, 0, 100, 10, 0.3, bboxes_pred=box)
-    big = torch.zeros((1, 9000, 2), device=cuda)
-    with pytest.raises(_lib.DanError):      # more anchors AND a larger keep_topk than the in-shared-memory sort holds
-        bu.parse_by_class_batch([64, 64], big, 2, 0.1, 0, 100000, 10, 0.3, bboxes_pred=torch.zeros((1, 9000, 4), device=cuda))
+    with pytest.raises(_lib.DanError):
+        bu.parse_by_class_batch([64, 64], cls, 2, 0.1, 0, 0, 10, 0.3, bboxes_pred=box)           # keep_topk must be >= 1
     det = bu.parse_by_class_batch([64, 64], cls, 2, 0.1, 0, 100000, 10, 0.3, bboxes_pred=box)     # keep_topk > N is fine
     assert int(det.counts.sum()) == 0
     with pytest.raises(TypeError):
@@ -981,3 +981,21 @@ def test_device_gather_single_rank(cuda):
     with pytest.raises(ValueError):
         g.gather(send, recv[:100])
     g.close()
+
+
+def test_parse_by_class_beyond_shared_memory_limits(cuda, oracle):
+    """keep_topk and nms_topk far above what the kernels hold in shared memory (tf.nn.top_k and
+    tf.image.non_max_suppression have no limit): candidates, kept list and stripe index live in the workspace."""
+    from dan_b200.utility import bbox_util as bu
+    rng = np.random.default_rng(77)
+    n = 20000
+    cls = rng.normal(0, 2.0, (n, 2)).astype(np.float32)
+    c = rng.uniform(0, 2000, (n, 2))
+    wh = rng.uniform(4, 40, (n, 2))
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    for keep_topk, nms_topk in ((12000, 9500), (9000, 400)):
+        rb, rs = oracle.parse_by_class([2000, 2000], cls, boxes, 2, 0.05, 0, keep_topk, nms_topk, 0.5)
+        sb, ss = bu.parse_by_class([2000, 2000], to_dev(cls, cuda), to_dev(boxes, cuda), 2, 0.05, 0, keep_topk, nms_topk, 0.5)
+        np.testing.assert_array_equal(_np(ss[1]), rs[1])
+        np.testing.assert_array_equal(_np(sb[1]), rb[1])
+        assert int((rs[1] > 0).sum()) > 0.8 * min(nms_topk, 9000)
