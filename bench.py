@@ -364,14 +364,18 @@ def run_cuda(args):
         sampler.start()
         time.sleep(0.3)
 
+    host_enqueue_us = [0.0]
+
     def timed(serial):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         drain()
         barrier()
         e0.record()
         fork()
+        h0 = time.perf_counter()
         for k in range(K):
             step(W + k, serial=serial)
+        host_enqueue_us[0] = 1e6 * (time.perf_counter() - h0) / K      # host time to enqueue one step (not a GPU time)
         drain()
         e1.record()
         barrier()
@@ -579,7 +583,7 @@ def run_cuda(args):
                 "run": {"l2_policy": "%d rotating input/output buffer sets (%.0f MB) > 126 MB L2" % (R, R * per_set / 1e6),
                         "cuda_graph": not args.no_graph, "two_stream_overlap": not args.no_overlap, "steps_in_flight": L,
                         "inflight_outputs": "bit-identical to the serial run (checked on all sets)",
-                        "mean_gt_per_image": total_gt_mean / B,
+                        "mean_gt_per_image": total_gt_mean / B, "host_enqueue_us_per_step": host_enqueue_us[0],
                         "gather": "ncclAllGather inside each step's CUDA graph (dan_gather_detections)" if world > 1 else None,
                         "gather_check": gather_check, "host_cores_per_rank": cores_per_rank,
                         "native_so_loaded": [os.path.relpath(_lib.LIB_PATH, ROOT)]},
@@ -615,7 +619,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough for 3x L2)")
-    ap.add_argument("--inflight", type=int, default=5, help="steps in flight (each on its own stream and workspaces)")
+    ap.add_argument("--inflight", type=int, default=8, help="steps in flight (each on its own stream and workspaces)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run encode and postprocess on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")

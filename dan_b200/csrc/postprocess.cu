@@ -465,10 +465,15 @@ __device__ __noinline__ void resolve_chunk_serially(const uint32_t* T, uint32_t*
 // the indices of the few anchors the quick reject lets through, runs them through the exact path (softmax in
 // tf.nn.softmax's op order, threshold, decode, clip, min-size) on dense warps, and the surviving keys land directly in
 // the shared memory the sort works in: no filter launch, no key list in HBM, no global atomics.
+#ifndef DAN_NMS_REGS
+#define DAN_NMS_BOUNDS __launch_bounds__(kSortThreads, 1024 / kSortThreads)
+#else                                     // experiment: cap the registers so that CTAs of other kernels fit beside this one
+#define DAN_NMS_BOUNDS __maxnreg__(DAN_NMS_REGS)
+#endif
 constexpr int kMaybeCap = 4096;                        // indices kept in shared memory (the rest goes to the workspace)
 
 template <bool DECODE, int WHERE, bool FILTER>
-__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) nms_greedy_kernel(const PpArgs A, const float* __restrict__ src_scores,
+__global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __restrict__ src_scores,
                                                                      const float4* __restrict__ src_boxes) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ SortScratch sc;
