@@ -25,12 +25,22 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_committed_cuda_line_has_the_contract_keys():
-    line = json.load(open(os.path.join(ROOT, "profiles", "r01_final_bench.json")))
-    for k in COMMON + ["clocks", "gpu_launches", "roofline"]:
+    path = os.path.join(ROOT, "profiles", "r02_final_bench.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r02_mid_bench.json")
+    line = json.load(open(path))
+    for k in COMMON + ["clocks", "gpu_launches", "roofline", "e2e_full", "run", "serial"]:
         assert k in line, k
-    assert line["gpu_launches"] == 7 * line["steps"] and line["dtype"] == "f32" and line["data"] == "synthetic"
+    assert line["gpu_launches"] == 5 * line["steps"] and line["dtype"] == "f32" and line["data"] == "synthetic"
     r = line["roofline"]
-    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "GB/s"
+    # the roofline describes the step: per-stage max(hbm, fp32) times summed over the stages, against the step time
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and abs(r["frac"] - r["t_roofline_us"] / r["t_step_us"]) < 1e-9
+    assert set(r["stages"]) == {"encode", "decode_filter", "nms"}
+    assert abs(sum(st["t_roofline_us"] for st in r["stages"].values()) - r["t_roofline_us"]) < 1e-6
+    assert r["stages"]["decode_filter"]["bound"] == "hbm" and r["stages"]["encode"]["bound"] == "fp32"
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["e2e_full"]["d2h_bytes_per_step"] > line["e2e"]["d2h_bytes_per_step"]
     assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
     assert line["clocks"]["reasons"] == [] or "sw_power_cap" in "".join(line["clocks"]["reasons"])
+    ref = json.load(open(os.path.join(ROOT, "profiles", os.path.basename(path).replace("_bench.json", "_bench_reference_arm.json"))))
+    assert ref["config"] == line["config"]          # the driver compares the two arms' config objects
