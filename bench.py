@@ -267,9 +267,15 @@ def run_cuda(args):
     L = max(1, args.inflight)
     R = (R + L - 1) // L * L                  # a set always runs on the same lane
     ws_lanes = [(_lib.Workspace(), _lib.Workspace()) for _ in range(L)]
-    # one NCCL communicator per lane: collectives of one communicator must not run concurrently, the lanes do
-    gathers = [pipeline.DeviceGather(rank, world, dev) for _ in range(L)] if world > 1 else [None] * L
     slab_words = pipeline.DetectionSlab.words_for(B, pp_params.num_classes - 1, pp_params.nms_topk)
+    # the detection exchange (N > 1): "p2p" = the NMS kernel stores its slab rows into every rank's receive buffer over
+    # NVLink (CUDA IPC) and a one-warp kernel waits for the arrival flags; "nccl" = one ncclAllGather per step, one
+    # communicator per lane (collectives of one communicator must not run concurrently, the lanes do)
+    peers, gathers = None, [None] * L
+    if world > 1 and args.gather == "p2p":
+        peers = pipeline.PeerExchange(rank, world, dev, slab_words, num_sets=R)
+    elif world > 1:
+        gathers = [pipeline.DeviceGather(rank, world, dev) for _ in range(L)]
     sets = []
     for r in range(R):
         order = [(i + r) % B for i in range(B)]
@@ -278,13 +284,18 @@ def run_cuda(args):
              "cls": torch.from_numpy(np.stack([preds[i][0] for i in order])).pin_memory(),
              "loc": torch.from_numpy(np.stack([preds[i][1] for i in order])).pin_memory()}
         d = {k: v.to(dev) for k, v in h.items()}
-        recv = torch.zeros(world * slab_words, dtype=torch.float32, device=dev) if world > 1 else None
+        recv = None
+        if peers is not None:
+            recv = peers.recv(r)
+        elif world > 1:
+            recv = torch.zeros(world * slab_words, dtype=torch.float32, device=dev)
         hp = pipeline.HotPath(a_train[:4], a_train[4], enc_params, pp_params, anchors_eval=a_eval[:4],
-                              workspaces=ws_lanes[r % L], overlap=not args.no_overlap, device_gather=gathers[r % L], recv_buffer=recv)
+                              workspaces=ws_lanes[r % L], overlap=not args.no_overlap, device_gather=gathers[r % L],
+                              recv_buffer=None if peers is not None else recv, peer_exchange=peers, peer_set=r)
         sets.append({"host": h, "dev": d, "hp": hp, "recv": recv, "total_gt": int(offs[-1])})
     total_gt_mean = float(np.mean([s["total_gt"] for s in sets]))
 
-    log("inputs and %d communicators ready" % L)
+    log("inputs and exchange ready")
     def run_set(s, profile=False):
         return s["hp"].step(s["dev"]["gt"], s["dev"]["offs"], s["dev"]["cls"], s["dev"]["loc"], profile=profile)
 
@@ -584,7 +595,10 @@ def run_cuda(args):
                         "cuda_graph": not args.no_graph, "two_stream_overlap": not args.no_overlap, "steps_in_flight": L,
                         "inflight_outputs": "bit-identical to the serial run (checked on all sets)",
                         "mean_gt_per_image": total_gt_mean / B, "host_enqueue_us_per_step": host_enqueue_us[0],
-                        "gather": "ncclAllGather inside each step's CUDA graph (dan_gather_detections)" if world > 1 else None,
+                        "gather": None if world == 1 else (
+                            "peer stores: the NMS kernel writes its slab rows into every rank's receive buffer over NVLink "
+                            "(dan_postprocess_batch_peers) + a one-warp wait on the arrival flags, inside each step's CUDA graph"
+                            if peers is not None else "ncclAllGather inside each step's CUDA graph (dan_gather_detections)"),
                         "gather_check": gather_check, "host_cores_per_rank": cores_per_rank,
                         "native_so_loaded": [os.path.relpath(_lib.LIB_PATH, ROOT)]},
                 "clocks": clocks, "e2e": e2e, "e2e_full": e2e_full, "gpu_launches": KERNELS_PER_STEP * K,
@@ -606,7 +620,13 @@ def run_cuda(args):
         gc.collect()
         torch.cuda.synchronize()
         for g in gathers:
-            g.close()
+            if g is not None:
+                g.close()
+        if peers is not None:
+            for s in sets:
+                s["recv"] = None
+            dist.barrier()
+            peers.close()
         dist.destroy_process_group()
     return 0
 
@@ -620,6 +640,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough for 3x L2)")
     ap.add_argument("--inflight", type=int, default=8, help="steps in flight (each on its own stream and workspaces)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="detection exchange at N > 1")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run encode and postprocess on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -63,6 +63,14 @@ class PostprocessParams(ctypes.Structure):
     ]
 
 
+DAN_MAX_PEERS = 16
+
+
+class PeerExchangeArgs(ctypes.Structure):
+    """dan_peer_exchange of include/dan_b200.h."""
+    _fields_ = [("num_destinations", c_i32), ("delta_bytes", c_i64 * DAN_MAX_PEERS), ("flag", c_vp * DAN_MAX_PEERS), ("state", c_vp)]
+
+
 class RoutingLayers(ctypes.Structure):
     """dan_routing_layers of include/dan_b200.h."""
     _fields_ = [("num_layers", c_i32), ("feat_height", c_i32 * 16), ("feat_width", c_i32 * 16), ("anchor_depth", c_i32 * 16),
@@ -114,10 +122,19 @@ _SIGNATURES = {
     "dan_bbox_vote": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dan_gt_handoff": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp,
                                       c_vp]),
+    "dan_peer_alloc": (ctypes.c_int, [c_sz, ctypes.POINTER(c_vp), c_vp]),
+    "dan_peer_open": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "dan_peer_close": (ctypes.c_int, [c_vp]),
+    "dan_peer_free": (ctypes.c_int, [c_vp]),
+    "dan_postprocess_batch_peers": (ctypes.c_int, [ctypes.POINTER(PostprocessParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                                   c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
+                                                   ctypes.POINTER(PeerExchangeArgs), c_vp]),
+    "dan_wait_detections": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp]),
     "dan_nccl_load": (ctypes.c_int, [ctypes.c_char_p]),
     "dan_nccl_version": (ctypes.c_int, []),
     "dan_comm_unique_id": (ctypes.c_int, [c_vp]),
     "dan_comm_init": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp)]),
+    "dan_comm_init_ctas": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(c_vp)]),
     "dan_comm_destroy": (ctypes.c_int, [c_vp]),
     "dan_gather_detections": (ctypes.c_int, [c_vp, c_vp, c_vp, c_sz, c_vp]),
 }

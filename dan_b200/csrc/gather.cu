@@ -16,6 +16,20 @@ struct NcclUniqueId { char internal[128]; };
 typedef void* NcclComm;
 typedef int (*GetUniqueIdFn)(NcclUniqueId*);
 typedef int (*CommInitRankFn)(NcclComm*, int, NcclUniqueId, int);
+// ncclConfig_t as of NCCL 2.18 (size, magic, version first: NCCL copies `size` bytes over its own defaults, so an older,
+// shorter layout stays valid with newer libraries)
+struct NcclConfig218 {
+  size_t size;
+  unsigned int magic;
+  unsigned int version;
+  int blocking;
+  int cgaClusterSize;
+  int minCTAs;
+  int maxCTAs;
+  const char* netName;
+  int splitShare;
+};
+typedef int (*CommInitRankConfigFn)(NcclComm*, int, NcclUniqueId, int, NcclConfig218*);
 typedef int (*CommDestroyFn)(NcclComm);
 typedef int (*AllGatherFn)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
 typedef const char* (*GetErrorStringFn)(int);
@@ -25,6 +39,7 @@ struct NcclApi {
   void* handle;
   GetUniqueIdFn get_unique_id;
   CommInitRankFn comm_init_rank;
+  CommInitRankConfigFn comm_init_rank_config;
   CommDestroyFn comm_destroy;
   AllGatherFn all_gather;
   GetErrorStringFn error_string;
@@ -47,6 +62,7 @@ static int nccl_bind(const char* path) {
   a.handle = h;
   a.get_unique_id = (GetUniqueIdFn)dlsym(h, "ncclGetUniqueId");
   a.comm_init_rank = (CommInitRankFn)dlsym(h, "ncclCommInitRank");
+  a.comm_init_rank_config = (CommInitRankConfigFn)dlsym(h, "ncclCommInitRankConfig");     // NCCL >= 2.14 (optional)
   a.comm_destroy = (CommDestroyFn)dlsym(h, "ncclCommDestroy");
   a.all_gather = (AllGatherFn)dlsym(h, "ncclAllGather");
   a.error_string = (GetErrorStringFn)dlsym(h, "ncclGetErrorString");
@@ -87,7 +103,7 @@ int dan_comm_unique_id(void* out_id128) {
   return DAN_OK;
 }
 
-int dan_comm_init(const void* id128, int32_t rank, int32_t world_size, void** out_comm) {
+int dan_comm_init_ctas(const void* id128, int32_t rank, int32_t world_size, int32_t max_ctas, void** out_comm) {
   DAN_REQUIRE(id128 != nullptr && out_comm != nullptr, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
   DAN_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, DAN_ERR_INVALID_ARGUMENT, "rank %d of %d", rank, world_size);
   int rc = nccl_bind(nullptr);
@@ -95,10 +111,30 @@ int dan_comm_init(const void* id128, int32_t rank, int32_t world_size, void** ou
   NcclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   NcclComm comm = nullptr;
-  const int nrc = g_nccl.comm_init_rank(&comm, world_size, id, rank);
-  if (nrc != 0) return nccl_fail(nrc, "ncclCommInitRank");
+  if (max_ctas > 0 && g_nccl.comm_init_rank_config != nullptr) {
+    NcclConfig218 cfg;
+    cfg.size = sizeof(NcclConfig218);
+    cfg.magic = 0xcafebeefu;
+    cfg.version = 21800;                     // NCCL_VERSION(2, 18, 0)
+    cfg.blocking = cfg.cgaClusterSize = cfg.splitShare = (int)0x80000000;      // NCCL_CONFIG_UNDEF_INT
+    cfg.netName = nullptr;
+    cfg.minCTAs = 1;
+    cfg.maxCTAs = max_ctas;
+    const int nrc = g_nccl.comm_init_rank_config(&comm, world_size, id, rank, &cfg);
+    if (nrc != 0) return nccl_fail(nrc, "ncclCommInitRankConfig");
+  } else {
+    const int nrc = g_nccl.comm_init_rank(&comm, world_size, id, rank);
+    if (nrc != 0) return nccl_fail(nrc, "ncclCommInitRank");
+  }
   *out_comm = comm;
   return DAN_OK;
+}
+
+// NCCL's own choice of CTAs.  (Measured at 8 ranks x 8 steps in flight: with max_ctas = 1 a 480 KB all-gather takes ~570 us and
+// the step rate drops 3x; with NCCL's default the CTAs of the collectives hold SMs while they wait for the slowest rank,
+// 67 vs 47 us per step.  The peer exchange of dan_postprocess_batch_peers has neither cost.)
+int dan_comm_init(const void* id128, int32_t rank, int32_t world_size, void** out_comm) {
+  return dan_comm_init_ctas(id128, rank, world_size, 0, out_comm);
 }
 
 int dan_comm_destroy(void* comm) {

@@ -17,6 +17,7 @@
 //                      (bbox_util.py:80-90).  One launch, one CTA per list.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -80,6 +81,12 @@ struct PpArgs {
   int32_t* out_index;
   int32_t* out_keep;
   int filler;                 // fused parse_by_class: zero-score rows fill up the NMS selection
+  // peer exchange (dan_postprocess_batch_peers): every output row of the slab is also stored into the receive buffers of
+  // the other ranks over NVLink (mapped peer memory); the last CTA then raises this rank's flag in every peer
+  int npeers;                                   // destinations besides out_* (0: no exchange)
+  long long peer_delta[DAN_MAX_PEERS];          // byte offset from an address inside the own slab to its copy in destination q
+  int32_t* peer_flag[DAN_MAX_PEERS];            // this rank's arrival flag inside destination q
+  int32_t* peer_state;                          // [2] device words of this rank: CTAs done, step sequence number
 };
 
 // clip_bboxes, bbox_util.py:38-48
@@ -879,20 +886,28 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
   }
 #endif
 
-  // ---- 4. outputs, zero padded to nms_topk
+  // ---- 4. outputs, zero padded to nms_topk; with a peer exchange every slab row also goes to the other ranks
+  auto put_score = [&](int64_t oo, float v) {
+    A.out_scores[oo] = v;
+    for (int q = 0; q < A.npeers; ++q) *reinterpret_cast<float*>(reinterpret_cast<char*>(A.out_scores + oo) + A.peer_delta[q]) = v;
+  };
+  auto put_box = [&](int64_t oo, float4 v) {
+    A.out_boxes[oo] = v;
+    for (int q = 0; q < A.npeers; ++q) *reinterpret_cast<float4*>(reinterpret_cast<char*>(A.out_boxes + oo) + A.peer_delta[q]) = v;
+  };
   for (int t = tid; t < A.nms_topk; t += kSortThreads) {
     const int64_t oo = (int64_t)list * A.nms_topk + t;
     if (t < kept_n) {
       const int pos = krank[t];
       const unsigned long long key = A.s_key[o + pos];
       const uint32_t idx = key_index(key);
-      A.out_scores[oo] = DECODE ? key_to_score((uint32_t)(key >> 32)) : src_scores[idx];
-      A.out_boxes[oo] = DECODE ? kbox[t] : src_boxes[idx];     // clipped boxes are already min/max ordered
+      put_score(oo, DECODE ? key_to_score((uint32_t)(key >> 32)) : src_scores[idx]);
+      put_box(oo, DECODE ? kbox[t] : src_boxes[idx]);     // clipped boxes are already min/max ordered
       if (A.out_index != nullptr) A.out_index[oo] = (int32_t)idx;
       if (A.out_keep != nullptr) A.out_keep[oo] = A.filler ? pos : (int32_t)idx;
     } else {
-      A.out_scores[oo] = 0.f;
-      A.out_boxes[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
+      put_score(oo, 0.f);
+      put_box(oo, make_float4(0.f, 0.f, 0.f, 0.f));
       if (A.out_index != nullptr) A.out_index[oo] = -1;
       if (A.out_keep != nullptr) {
         // parse_by_class runs NMS on the zero padded top-k list: zero-area filler rows are never suppressed
@@ -902,8 +917,39 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
       }
     }
   }
-  if (tid == 0 && A.out_counts != nullptr) A.out_counts[list] = kept_n;
+  if (tid == 0 && A.out_counts != nullptr) {
+    A.out_counts[list] = kept_n;
+    for (int q = 0; q < A.npeers; ++q) *reinterpret_cast<int32_t*>(reinterpret_cast<char*>(A.out_counts + list) + A.peer_delta[q]) = kept_n;
+  }
+  if (A.npeers > 0) {
+    // release: this CTA's rows are visible system-wide before it counts itself done; the last CTA of the launch bumps the
+    // rank's step number and writes it into its flag slot in every destination (dan_wait_detections polls those)
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const int done = atomicAdd(A.peer_state, 1);
+      if (done == (int)gridDim.x - 1) {
+        A.peer_state[0] = 0;
+        const int seq = A.peer_state[1] + 1;
+        A.peer_state[1] = seq;
+        __threadfence_system();
+        for (int q = 0; q < A.npeers; ++q) *reinterpret_cast<volatile int32_t*>(A.peer_flag[q]) = seq;
+      }
+    }
+  }
   DAN_PHASE(4);
+}
+
+// One warp polls the arrival flags of the `world` ranks in this rank's receive buffer until all have reached the step
+// number this rank's own NMS kernel just produced (state[1]); it holds one warp of one SM, nothing else.
+__global__ void wait_detections_kernel(const int32_t* flags, const int32_t* state, int world) {
+  const int want = *reinterpret_cast<const volatile int32_t*>(state + 1);
+  const int q = threadIdx.x;
+  if (q < world) {
+    while (*reinterpret_cast<const volatile int32_t*>(flags + q) < want) __nanosleep(100);
+  }
+  __syncwarp();
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------
@@ -1005,7 +1051,8 @@ size_t dan_nms_workspace_bytes(int64_t n, int32_t nms_topk) {
 static int postprocess_core(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
                             const float* a_ymin, const float* a_xmin, const float* a_ymax, const float* a_xmax, int32_t num_anchors,
                             int32_t batch, float* out_boxes, float* out_scores, int32_t* out_counts, int32_t* out_anchor_index,
-                            int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, void* stream, cudaEvent_t* ev) {
+                            int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, void* stream, cudaEvent_t* ev,
+                            const dan_peer_exchange* peers = nullptr) {
   DAN_REQUIRE(p != nullptr, DAN_ERR_INVALID_ARGUMENT, "params is NULL");
   DAN_REQUIRE(p->num_classes >= 2, DAN_ERR_INVALID_ARGUMENT, "num_classes must be >= 2 (class 0 is background), got %d", p->num_classes);
   DAN_REQUIRE(num_anchors >= 0 && batch >= 0, DAN_ERR_INVALID_ARGUMENT, "negative size");
@@ -1050,6 +1097,18 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   A.out_index = out_anchor_index;
   A.out_keep = out_keep_pos;
   A.filler = 1;
+  if (peers != nullptr && peers->num_destinations > 0) {
+    DAN_REQUIRE(peers->num_destinations <= DAN_MAX_PEERS, DAN_ERR_UNSUPPORTED, "more than %d destinations", DAN_MAX_PEERS);
+    DAN_REQUIRE(peers->state != nullptr && out_counts != nullptr, DAN_ERR_INVALID_ARGUMENT, "peer exchange needs state words and out_counts");
+    A.npeers = peers->num_destinations;
+    for (int q = 0; q < A.npeers; ++q) {
+      DAN_REQUIRE(peers->flag[q] != nullptr && (peers->delta_bytes[q] & 15) == 0, DAN_ERR_INVALID_ARGUMENT,
+                  "destination %d: NULL flag or a slab offset that is not a multiple of 16 bytes", q);
+      A.peer_delta[q] = peers->delta_bytes[q];
+      A.peer_flag[q] = peers->flag[q];
+    }
+    A.peer_state = peers->state;
+  }
   pp_bind(A, workspace, w);
   // two classes: the NMS kernel filters its own image (one launch for the whole evaluation side)
   const bool fused = p->num_classes == 2 && (reinterpret_cast<uintptr_t>(cls_pred) & 7u) == 0;
@@ -1073,6 +1132,59 @@ int dan_postprocess_batch(const dan_postprocess_params* p, const float* cls_pred
                           int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, void* stream) {
   return postprocess_core(p, cls_pred, loc_pred, boxes_pred, a_ymin, a_xmin, a_ymax, a_xmax, num_anchors, batch, out_boxes, out_scores,
                           out_counts, out_anchor_index, out_keep_pos, workspace, workspace_bytes, stream, nullptr);
+}
+
+int dan_postprocess_batch_peers(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred, const float* boxes_pred,
+                                const float* a_ymin, const float* a_xmin, const float* a_ymax, const float* a_xmax, int32_t num_anchors,
+                                int32_t batch, float* out_boxes, float* out_scores, int32_t* out_counts, int32_t* out_anchor_index,
+                                int32_t* out_keep_pos, void* workspace, size_t workspace_bytes, const dan_peer_exchange* peers,
+                                void* stream) {
+  DAN_REQUIRE(batch > 0 || peers == nullptr || peers->num_destinations == 0, DAN_ERR_INVALID_ARGUMENT,
+              "a rank without images cannot take part in the peer exchange (its flag would never rise)");
+  return postprocess_core(p, cls_pred, loc_pred, boxes_pred, a_ymin, a_xmin, a_ymax, a_xmax, num_anchors, batch, out_boxes, out_scores,
+                          out_counts, out_anchor_index, out_keep_pos, workspace, workspace_bytes, stream, nullptr, peers);
+}
+
+int dan_wait_detections(const int32_t* flags, const int32_t* state, int32_t world_size, void* stream) {
+  DAN_REQUIRE(flags != nullptr && state != nullptr && world_size >= 1 && world_size <= 32, DAN_ERR_INVALID_ARGUMENT, "bad arguments");
+  wait_detections_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, state, world_size);
+  DAN_LAUNCH_CHECK("wait_detections_kernel");
+  return DAN_OK;
+}
+
+int dan_peer_alloc(size_t bytes, void** out_ptr, void* out_handle64) {
+  DAN_REQUIRE(bytes > 0 && out_ptr != nullptr && out_handle64 != nullptr, DAN_ERR_INVALID_ARGUMENT, "bad arguments");
+  void* ptr = nullptr;
+  DAN_CUDA(cudaMalloc(&ptr, bytes));
+  cudaError_t e = cudaMemset(ptr, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) {
+    cudaFree(ptr);
+    return cuda_fail(e, "cudaIpcGetMemHandle");
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(out_handle64, &h, 64);
+  *out_ptr = ptr;
+  return DAN_OK;
+}
+
+int dan_peer_open(const void* handle64, void** out_ptr) {
+  DAN_REQUIRE(handle64 != nullptr && out_ptr != nullptr, DAN_ERR_INVALID_ARGUMENT, "NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  DAN_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DAN_OK;
+}
+
+int dan_peer_close(void* ptr) {
+  if (ptr != nullptr) DAN_CUDA(cudaIpcCloseMemHandle(ptr));
+  return DAN_OK;
+}
+
+int dan_peer_free(void* ptr) {
+  if (ptr != nullptr) DAN_CUDA(cudaFree(ptr));
+  return DAN_OK;
 }
 
 int dan_postprocess_batch_profile(const dan_postprocess_params* p, const float* cls_pred, const float* loc_pred,

@@ -369,7 +369,7 @@ def postprocess_params(num_classes, image_shape, select_threshold, min_size, kee
 
 
 def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=None, out=None, want_index=True,
-                      workspace=None, profile=False):
+                      workspace=None, profile=False, peers=None):
     """Batched fused parse_by_class (bbox_util.py:103-119).  cls_pred [B,N,C]; give loc_pred [B,N,4]
     (+ anchors = (ymin,xmin,ymax,xmax)) or boxes_pred [B,N,4].  Returns Detections indexed [b, c-1]."""
     L.require_device()
@@ -408,6 +408,9 @@ def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=
             ms = (ctypes.c_float * 2)()
             L.check(L.lib().dan_postprocess_batch_profile(*args, ms))
             return Detections(boxes, scores, counts, aidx, kpos), list(ms)
+        if peers is not None:   # L.PeerExchangeArgs: the NMS kernel also stores the slab rows into the other ranks' buffers
+            L.check(L.lib().dan_postprocess_batch_peers(*args[:-1], ctypes.byref(peers), args[-1]))
+            return Detections(boxes, scores, counts, aidx, kpos)
         L.check(L.lib().dan_postprocess_batch(*args))
     return Detections(boxes, scores, counts, aidx, kpos)
 

@@ -10,6 +10,7 @@ all slabs -- the counts travel inside the slab, so there is no size exchange.
 """
 from __future__ import annotations
 
+import os
 from collections import namedtuple
 
 import torch
@@ -49,7 +50,8 @@ class DetectionSlab(object):
         self.n_boxes = self.n_scores * 4
         # counts region padded to 4 words so that the box region stays 16-byte aligned
         self.counts_words = (self.n_counts + 3) // 4 * 4
-        self.words = self.counts_words + self.n_scores + self.n_boxes
+        # (a multiple of 4 words, so that slabs laid end to end keep their box regions 16-byte aligned)
+        self.words = (self.counts_words + self.n_scores + self.n_boxes + 3) // 4 * 4
         if buf is None:
             buf = torch.zeros(self.words, dtype=torch.float32, device=device)
         if buf.numel() != self.words or buf.dtype != torch.float32 or not buf.is_contiguous():
@@ -59,7 +61,7 @@ class DetectionSlab(object):
     @staticmethod
     def words_for(images, lists, nms_topk):
         nc = images * lists
-        return (nc + 3) // 4 * 4 + nc * nms_topk * 5
+        return ((nc + 3) // 4 * 4 + nc * nms_topk * 5 + 3) // 4 * 4
 
     def views(self, buf=None):
         buf = self.buf if buf is None else buf
@@ -99,7 +101,7 @@ class DeviceGather(object):
     so a replayed step costs no host time for the collective.  torch.distributed is only used once, to
     ship the 128-byte NCCL id from rank 0 to the other ranks."""
 
-    def __init__(self, rank, world_size, device, group=None):
+    def __init__(self, rank, world_size, device, group=None, max_ctas=None):
         import ctypes
         import torch.distributed as dist
         from . import _lib as L
@@ -117,8 +119,10 @@ class DeviceGather(object):
             ident = t.cpu()
         raw = (ctypes.c_ubyte * 128)(*[int(v) for v in ident.tolist()])
         comm = ctypes.c_void_p(0)
+        if max_ctas is None:
+            max_ctas = int(os.environ.get("DAN_NCCL_MAX_CTAS", "0"))      # CTAs of the collective (0 = NCCL's default)
         with torch.cuda.device(device):
-            L.check(L.lib().dan_comm_init(raw, self.rank, self.world_size, ctypes.byref(comm)))
+            L.check(L.lib().dan_comm_init_ctas(raw, self.rank, self.world_size, int(max_ctas), ctypes.byref(comm)))
         self._comm = comm
 
     def gather(self, send, recv):
@@ -135,6 +139,103 @@ class DeviceGather(object):
         if self._comm is not None and self._comm.value:
             self._lib.lib().dan_comm_destroy(self._comm)
         self._comm = None
+
+
+class _DeviceMemory(object):
+    """A raw device allocation exposed through __cuda_array_interface__ so that torch can wrap it without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange(object):
+    """The detection exchange WITHOUT a collective kernel (ranks of one node): every rank allocates ONE receive buffer
+    per buffer set `[world slabs | world flags]` through the C ABI (cudaMalloc + CUDA IPC handle), the ranks map each
+    other's buffers, and the NMS kernel stores every slab row it writes into all of them over NVLink
+    (dan_postprocess_batch_peers).  `wait()` enqueues the one-warp kernel that returns when the slabs of all ranks of
+    this step have arrived.  torch.distributed is used once, to exchange the 64-byte IPC handles."""
+
+    def __init__(self, rank, world_size, device, slab_words, num_sets=1, group=None):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib as L
+        self._lib = L
+        self.rank, self.world_size, self.device = int(rank), int(world_size), device
+        self.slab_words, self.num_sets = int(slab_words), int(num_sets)
+        if self.world_size > L.DAN_MAX_PEERS:
+            raise ValueError("at most %d ranks" % L.DAN_MAX_PEERS)
+        slab_bytes = 4 * self.slab_words
+        self.set_bytes = (self.world_size * slab_bytes + 4 * 32 + 255) // 256 * 256      # slabs, then the arrival flags
+        self.flag_offset = self.world_size * slab_bytes
+        total = self.num_sets * self.set_bytes
+        ptr, handle = ctypes.c_void_p(0), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            L.check(L.lib().dan_peer_alloc(total, ctypes.byref(ptr), handle))
+        self._own = int(ptr.value)
+        self._mem = torch.as_tensor(_DeviceMemory(self._own, total), device=device)      # uint8 view of the allocation
+        mine = torch.tensor(list(handle), dtype=torch.uint8)
+        self._bases = [self._own] * self.world_size
+        self._opened = []
+        if self.world_size > 1:
+            backend = dist.get_backend(group)
+            t = mine.to(device) if backend == "nccl" else mine
+            allh = torch.empty((self.world_size, 64), dtype=torch.uint8, device=t.device)
+            dist.all_gather_into_tensor(allh, t, group=group)
+            allh = allh.cpu()
+            for q in range(self.world_size):
+                if q == self.rank:
+                    continue
+                raw = (ctypes.c_ubyte * 64)(*[int(v) for v in allh[q].tolist()])
+                p = ctypes.c_void_p(0)
+                with torch.cuda.device(device):
+                    L.check(L.lib().dan_peer_open(raw, ctypes.byref(p)))
+                self._bases[q] = int(p.value)
+                self._opened.append(p)
+        self._state = torch.zeros((self.num_sets, 2), dtype=torch.int32, device=device)
+
+    def recv(self, s):
+        """fp32 view [world * slab_words] of this rank's receive buffer of set s (rank-major, like an all-gather)."""
+        o = s * self.set_bytes
+        return self._mem[o:o + self.flag_offset].view(torch.float32)
+
+    def flags(self, s):
+        o = s * self.set_bytes + self.flag_offset
+        return self._mem[o:o + 4 * 32].view(torch.int32)
+
+    def args(self, s, slab_buf):
+        """dan_peer_exchange for a step of set s whose slab lives in `slab_buf` (every rank is a destination, the own
+        receive buffer included)."""
+        L = self._lib
+        a = L.PeerExchangeArgs()
+        a.num_destinations = self.world_size
+        slab_bytes = 4 * self.slab_words
+        for q in range(self.world_size):
+            dst = self._bases[q] + s * self.set_bytes
+            a.delta_bytes[q] = dst + self.rank * slab_bytes - int(slab_buf.data_ptr())
+            a.flag[q] = dst + self.flag_offset + 4 * self.rank
+        a.state = int(self._state[s].data_ptr())
+        return a
+
+    def wait(self, s):
+        """Returns (on the stream) when the slabs of all ranks for the latest step of set s are in recv(s)."""
+        L = self._lib
+        with torch.cuda.device(self.device):
+            L.check(L.lib().dan_wait_detections(L.dev_ptr(self.flags(s)), L.dev_ptr(self._state[s]), self.world_size, L.stream_ptr()))
+
+    def close(self):
+        L = self._lib
+        for p in self._opened:
+            L.lib().dan_peer_close(p)
+        self._opened = []
+        if self._own:
+            self._mem = None
+            L.lib().dan_peer_free(ctypes_void(self._own))
+            self._own = 0
+
+
+def ctypes_void(v):
+    import ctypes
+    return ctypes.c_void_p(v)
 
 
 def flatten_detections(gathered, image_counts=None):
@@ -161,7 +262,8 @@ class HotPath(object):
     (inside a CUDA-graph capture this becomes two parallel branches); each half has its own workspace."""
 
     def __init__(self, anchors_train, inside_mask, encode_params, postprocess_params, anchors_eval=None,
-                 images_per_rank=None, workspaces=None, overlap=True, slab_buffer=None, device_gather=None, recv_buffer=None):
+                 images_per_rank=None, workspaces=None, overlap=True, slab_buffer=None, device_gather=None, recv_buffer=None,
+                 peer_exchange=None, peer_set=0):
         from . import _lib
         self.anchors_train = anchors_train          # (ymin, xmin, ymax, xmax)
         self.inside_mask = inside_mask
@@ -176,6 +278,11 @@ class HotPath(object):
         self._slab_buffer = slab_buffer             # optional caller-owned storage of the detection slab
         self._gather = device_gather                # DeviceGather: the all-gather is enqueued right after the NMS kernel
         self._recv = recv_buffer                    # [world, slab words] when device_gather is given
+        self._peers = peer_exchange                 # PeerExchange: the NMS kernel stores the slab into every rank's buffer
+        self._peer_set = int(peer_set)
+        self._peer_args = None
+        if peer_exchange is not None:
+            self._recv = peer_exchange.recv(self._peer_set)
         self._slab = None
         self._enc_out = None
         self._aux = None
@@ -213,7 +320,8 @@ class HotPath(object):
             enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
                                  out=self._enc_out, workspace=self.ws_enc, profile=profile)
             det = F.postprocess_batch(self.pp_params, cls_pred, loc_pred=loc_pred, anchors=self.anchors_eval,
-                                      out=det_out, workspace=self.ws_pp, profile=profile)
+                                      out=det_out, workspace=self.ws_pp, profile=profile,
+                                      peers=None if profile else self._peer_arguments())
             if profile:
                 return enc[0], det[0], {"enc_pass1": enc[1][0], "enc_pass2": enc[1][1], "enc_pass3": enc[1][2],
                                         "pp_filter": det[1][0], "nms_greedy": det[1][1]}
@@ -227,13 +335,24 @@ class HotPath(object):
             enc = F.encode_batch(self.enc_params, *self.anchors_train, self.inside_mask, gt_boxes, gt_offsets,
                                  out=self._enc_out, workspace=self.ws_enc)
         det = F.postprocess_batch(self.pp_params, cls_pred, loc_pred=loc_pred, anchors=self.anchors_eval,
-                                  out=det_out, workspace=self.ws_pp)
+                                  out=det_out, workspace=self.ws_pp, peers=self._peer_arguments())
         self._enqueue_gather()      # on the stream that just ran the NMS kernel; the encode branch is not waited for
         main.wait_stream(self._side)
         return enc, det
 
+    def _peer_arguments(self):
+        if self._peers is None:
+            return None
+        if self._peer_args is None:
+            self._peer_args = self._peers.args(self._peer_set, self._slab.buf)
+        return self._peer_args
+
     def _enqueue_gather(self):
-        """The only exchange of the path: all-gather of the detection slabs, enqueued behind the NMS kernel."""
+        """The only exchange of the path: all-gather of the detection slabs, enqueued behind the NMS kernel (NCCL), or
+        the wait for the slabs the ranks' NMS kernels stored into each other's buffers (peer exchange)."""
+        if self._peers is not None:
+            self._peers.wait(self._peer_set)
+            return
         if self._gather is None:
             return
         if self._recv is None:
@@ -246,4 +365,5 @@ class HotPath(object):
     def gathered(self):
         """Views (rank order) of the slabs the in-graph all-gather delivered (device_gather mode)."""
         w = self._slab.words
-        return [self._slab.views(self._recv[r * w:(r + 1) * w]) for r in range(self._gather.world_size)]
+        world = self._peers.world_size if self._peers is not None else self._gather.world_size
+        return [self._slab.views(self._recv[r * w:(r + 1) * w]) for r in range(world)]

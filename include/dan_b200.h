@@ -366,14 +366,50 @@ int dan_gt_handoff(const float* gt_boxes, const int32_t* gt_offsets, const float
  *                       calls bind on first use.
  *   dan_comm_unique_id  ncclGetUniqueId -> 128 bytes (rank 0; ship them to the
  *                       other ranks by any means).
- *   dan_comm_init       ncclCommInitRank on the CURRENT device -> opaque comm.
+ *   dan_comm_init       ncclCommInitRank on the CURRENT device -> opaque comm
+ *                       (dan_comm_init_ctas: ncclCommInitRankConfig with maxCTAs = max_ctas,
+ *                       0 = NCCL's default).
  *   dan_gather_detections  recv_slabs [world, slab_bytes] <- send_slab [slab_bytes]
  *                       of every rank, rank order.
  * ------------------------------------------------------------------------- */
+/* The same exchange WITHOUT a collective kernel: the ranks of one node map each other's receive buffers (CUDA IPC over
+ * NVLink) and the NMS kernel stores every slab row it writes into all of them as well - the transfer is the tail of
+ * the compute kernel, no CTA waits for another rank.  The last CTA of the launch then writes the rank's step number into
+ * its flag slot of every destination; dan_wait_detections enqueues a one-warp kernel that returns when the flags of all
+ * ranks have reached this rank's own step number (one-sided: reusing a receive buffer before every reader is done
+ * with it is the caller's business, e.g. by rotating buffers).
+ *   dan_peer_alloc   cudaMalloc'ed, zeroed buffer + its 64-byte IPC handle; dan_peer_open maps a handle of ANOTHER
+ *                    process; dan_peer_close / dan_peer_free undo them.
+ *   dan_peer_exchange  num_destinations (<= DAN_MAX_PEERS); delta_bytes[q]: what to add to an address inside this rank's
+ *                    slab (out_counts / out_boxes / out_scores must all lie in it) to reach its copy in destination q
+ *                    (a multiple of 16); flag[q]: this rank's int32 flag inside destination q; state: two zeroed int32
+ *                    device words owned by this rank (CTAs done, step number). */
+#define DAN_MAX_PEERS 16
+typedef struct dan_peer_exchange {
+  int32_t num_destinations;
+  int64_t delta_bytes[DAN_MAX_PEERS];
+  int32_t* flag[DAN_MAX_PEERS];
+  int32_t* state;
+} dan_peer_exchange;
+int dan_peer_alloc(size_t bytes, void** out_ptr, void* out_handle64);
+int dan_peer_open(const void* handle64, void** out_ptr);
+int dan_peer_close(void* ptr);
+int dan_peer_free(void* ptr);
+int dan_postprocess_batch_peers(const dan_postprocess_params* h_params, const float* cls_pred,
+                                const float* loc_pred, const float* boxes_pred, const float* a_ymin,
+                                const float* a_xmin, const float* a_ymax, const float* a_xmax,
+                                int32_t num_anchors, int32_t batch, float* out_boxes, float* out_scores,
+                                int32_t* out_counts, int32_t* out_anchor_index, int32_t* out_keep_pos,
+                                void* workspace, size_t workspace_bytes,
+                                const dan_peer_exchange* h_peers, void* stream);
+int dan_wait_detections(const int32_t* flags, const int32_t* state, int32_t world_size, void* stream);
+
 int dan_nccl_load(const char* path);
 int dan_nccl_version(void);
 int dan_comm_unique_id(void* out_id128);
 int dan_comm_init(const void* id128, int32_t rank, int32_t world_size, void** out_comm);
+int dan_comm_init_ctas(const void* id128, int32_t rank, int32_t world_size, int32_t max_ctas,
+                       void** out_comm);
 int dan_comm_destroy(void* comm);
 int dan_gather_detections(void* comm, const void* send_slab, void* recv_slabs, size_t slab_bytes,
                           void* stream);

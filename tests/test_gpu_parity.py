@@ -999,3 +999,50 @@ def test_parse_by_class_beyond_shared_memory_limits(cuda, oracle):
         np.testing.assert_array_equal(_np(ss[1]), rs[1])
         np.testing.assert_array_equal(_np(sb[1]), rb[1])
         assert int((rs[1] > 0).sum()) > 0.8 * min(nms_topk, 9000)
+
+
+def test_peer_exchange_single_rank(cuda, oracle):
+    """dan_postprocess_batch_peers with one destination (this rank's own receive buffer, allocated through the C ABI):
+    the NMS kernel's peer stores, the arrival flag of the last CTA and dan_wait_detections, eagerly and in a CUDA graph."""
+    import torch
+    from dan_b200 import functional as F, pipeline
+    from dan_b200.utility import anchor_manipulator as am
+    enc = am.AnchorEncoder(0.4, 0.4, PS)
+    a_train = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd"))
+    a_eval = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", border=0.))
+    ev_np = synthetic.build_anchors(oracle.AnchorEncoder(None, None, PS), synthetic.pyramid_config("s3fd", border=0.))
+    an = np.stack(ev_np[:4], -1)
+    B = 3
+    gts = [synthetic.gen_faces(40 + i, 20) for i in range(B)]
+    preds = [synthetic.gen_predictions(40 + i, an, max_faces=30) for i in range(B)]
+    cat, offs = synthetic.to_csr(gts)
+    cls = to_dev(np.stack([p[0] for p in preds]), cuda)
+    loc = to_dev(np.stack([p[1] for p in preds]), cuda)
+    pp_params = F.postprocess_params(2, (640, 640), 0.01, 0, 5000, 750, 0.3, prior_scaling=PS)
+    words = pipeline.DetectionSlab.words_for(B, 1, 750)
+    px = pipeline.PeerExchange(0, 1, cuda, words, num_sets=2)
+    hp = pipeline.HotPath(a_train[:4], a_train[4], F.encode_params(0.4, 0.4, PS, match_mining=True), pp_params,
+                          anchors_eval=a_eval[:4], peer_exchange=px, peer_set=1)
+    gt_d, offs_d = to_dev(cat, cuda), to_dev(offs, cuda)
+    hp.step(gt_d, offs_d, cls, loc)
+    torch.cuda.synchronize()
+    assert torch.equal(px.recv(1), hp._slab.buf) and int(px.flags(1)[0]) == 1 and not px.recv(0).any()
+    (counts, scores, boxes), = hp.gathered()
+    for i in range(B):
+        _, (sb, ss, _) = _oracle_parse(oracle, (640, 640), preds[i][0], preds[i][1], ev_np)
+        np.testing.assert_array_equal(_np(scores[i, 0]), ss[1])
+        np.testing.assert_array_equal(_np(boxes[i, 0]), sb[1])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            hp.step(gt_d, offs_d, cls, loc)
+    torch.cuda.current_stream().wait_stream(side)
+    px.recv(1).zero_()
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(px.recv(1), hp._slab.buf) and int(px.flags(1)[0]) == 3
+    del graph
+    px.close()
