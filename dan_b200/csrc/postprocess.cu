@@ -58,6 +58,7 @@ struct PpArgs {
   // shared-memory plan of the NMS kernel (greedy_plan)
   int sort_bytes, kcap, wcap, cand_global, kept_global;
   int kstride;                // per-list stride of the candidate arrays = min(keep_topk, n)
+  int dyn_smem_bytes;         // dynamic shared memory of the launch
   // workspace
   unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
   int32_t* key_count;         // [L]
@@ -622,7 +623,10 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
   int K;
   const unsigned long long* sorted = keys;            // shared memory, or A.s_key for lists longer than kSortCap
   if (k_want <= kSortCap) {
-    K = min(select_and_sort(gkeys, cnt, k_want, keys, sc, FILTER), A.keep_topk);
+    // a second key buffer behind the first one when the CTA's shared memory holds it (nothing else lives there yet)
+    unsigned long long* spare = ((size_t)A.sort_bytes + (size_t)min(cnt, kSortCap) * 8 <= (size_t)A.dyn_smem_bytes)
+                                    ? reinterpret_cast<unsigned long long*>(dyn_smem + A.sort_bytes) : nullptr;
+    K = min(select_and_sort(gkeys, cnt, k_want, keys, sc, FILTER, spare), A.keep_topk);
   } else {
     select_and_sort_large(gkeys, cnt, k_want, A.s_key + o, A.s_key2 + o, keys, sc);
     sorted = A.s_key + o;
@@ -1016,6 +1020,7 @@ static int run_sort_nms(const PpArgs& A_in, int lists, const float* src_scores, 
   A.kcap = g.kcap;
   A.wcap = g.wcap;
   A.kstride = g.kcap;
+  A.dyn_smem_bytes = (int)g.smem;
   A.cand_global = g.cand_global;
   A.kept_global = g.kept_global;
   if (g.kept_global) return launch_greedy<DECODE, 2, FILTER>(A, lists, g.smem, src_scores, src_boxes, st);
