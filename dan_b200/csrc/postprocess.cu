@@ -351,9 +351,11 @@ DAN_D bool f2_maybe(const PpArgs& A, float x0, float x1) {
 //      suppression matrix.
 //   4. the first nms_topk kept boxes are written out in rank order, zero padded (bbox_util.py:80-90).
 // ---------------------------------------------------------------------------
-constexpr int kChunk = 256;
-constexpr int kChunkWords = kChunk / 32;
+constexpr int kWin = kSortThreads;                     // candidates in the window: one per thread
+constexpr int kSurv = 128;                             // survivors resolved per round
+constexpr int kSurvWords = kSurv / 32;
 constexpr int kMaxSweeps = 12;
+constexpr int kHintCells = 32 * 32;                    // one hint pair per (y stripe, x stripe) cell of a box centre
 constexpr size_t kGreedySmemMax = 186 * 1024;          // dynamic part (the kernel has ~38 KB of static shared memory)
 
 struct GreedyPlan {
@@ -426,10 +428,17 @@ struct Stripes {
     if (all) return make_uint2(0xffffffffu, 0xffffffffu);
     return make_uint2(axis(bx.y, bx.w, xlo, xinv), axis(bx.x, bx.z, ylo, yinv));
   }
+  // cell (y stripe * 32 + x stripe) of the box centre: the key of the suppressor hints (any cell is valid for any box)
+  DAN_D int cell(float4 bx) const {
+    const float fy = ((bx.x + bx.z) * 0.5f - ylo) * yinv, fx = ((bx.y + bx.w) * 0.5f - xlo) * xinv;
+    const int sy = (fabsf(fy) < 1e9f) ? min(max((int)fy, 0), 31) : 0;
+    const int sx = (fabsf(fx) < 1e9f) ? min(max((int)fx, 0), 31) : 0;
+    return sy * 32 + sx;
+  }
 };
 
-// barriers among the first kChunk threads of the CTA (hardware barrier 1); the other warps wait at the next __syncthreads
-DAN_D void bar_sync_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(kChunk) : "memory"); }
+// barriers among the first kSurv threads of the CTA (hardware barrier 1); the other warps wait at the next __syncthreads
+DAN_D void bar_sync_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(kSurv) : "memory"); }
 DAN_D bool bar_or_chunk(bool pred) {
   int r;
   asm volatile(
@@ -440,7 +449,7 @@ DAN_D bool bar_or_chunk(bool pred) {
       "  selp.s32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(r)
-      : "r"((int)pred), "n"(kChunk)
+      : "r"((int)pred), "n"(kSurv)
       : "memory");
   return r != 0;
 }
@@ -452,21 +461,21 @@ DAN_D bool bar_or_chunk(bool pred) {
 // undecided survivor every earlier one is decided); lane w holds word w of the masks.  Out of line (rare).
 __device__ __noinline__ void resolve_chunk_serially(const uint32_t* T, uint32_t* keptm, uint32_t* supm, int ns) {
   const int lane = threadIdx.x & 31;
-  uint32_t kw = (lane < kChunkWords) ? keptm[lane] : 0u;
-  uint32_t sw = (lane < kChunkWords) ? supm[lane] : 0u;
+  uint32_t kw = (lane < kSurvWords) ? keptm[lane] : 0u;
+  uint32_t sw = (lane < kSurvWords) ? supm[lane] : 0u;
   for (int v = 0; v < ns; ++v) {
     const int w = v >> 5;
     const uint32_t bit = 1u << (v & 31);
     const uint32_t known = __shfl_sync(0xffffffffu, kw | sw, w);
     if (known & bit) continue;                 // warp-uniform
-    const uint32_t t = (lane < kChunkWords && (lane << 5) < v) ? T[v * kChunkWords + lane] : 0u;
+    const uint32_t t = (lane < kSurvWords && (lane << 5) < v) ? T[v * kSurvWords + lane] : 0u;
     const bool hit = __any_sync(0xffffffffu, (t & kw) != 0u);
     if (lane == w) {
       if (hit) sw |= bit;
       else kw |= bit;
     }
   }
-  if (lane < kChunkWords) { keptm[lane] = kw; supm[lane] = sw; }
+  if (lane < kSurvWords) { keptm[lane] = kw; supm[lane] = sw; }
 }
 
 // FILTER (two classes, one list per image): the CTA also runs K3 for its image - it streams the image's logits, keeps
@@ -485,16 +494,18 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
                                                                      const float4* __restrict__ src_boxes) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ SortScratch sc;
-  __shared__ int s_flag[kChunk];                       // step a: candidate r of the chunk is suppressed by the kept list
-  __shared__ int s_surv[kChunk];                       // step b: chunk-local index of survivor u
-  __shared__ float4 s_sbox[kChunk];
-  __shared__ float s_sarea[kChunk];
-  __shared__ uint32_t s_T[kChunk][kChunkWords];
-  __shared__ uint32_t s_keptm[kChunkWords], s_supm[kChunkWords];
-  __shared__ uint2 s_smask[kChunk];
-  __shared__ int s_wcnt[kChunkWords];
-  __shared__ int s_next[2];                             // work counters of steps a and c
-  __shared__ int s_ns;
+  __shared__ unsigned char s_alive[kWin];              // ring over the window: candidate r lives in slot r % kWin
+  __shared__ unsigned short s_list[kWin];              // step a: window offsets of the candidates that need the full search
+  __shared__ int s_surv[kSurv];                        // step b: rank of survivor u
+  __shared__ float4 s_sbox[kSurv];
+  __shared__ float s_sarea[kSurv];
+  __shared__ uint32_t s_T[kSurv][kSurvWords];
+  __shared__ uint32_t s_keptm[kSurvWords], s_supm[kSurvWords];
+  __shared__ uint2 s_smask[kSurv];
+  __shared__ int s_hint[2][kHintCells];                // suppressor hints per cell: [0] first kept box centred there, [1] last suppressor found
+  __shared__ int s_wcnt[kSortThreads / 32];
+  __shared__ int s_next[2];                            // work counters of steps a and c
+  __shared__ int s_nlist, s_cnext;
 
   const int list = blockIdx.x;
   const int tid = threadIdx.x;
@@ -685,37 +696,80 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
   }
   for (int r = tid; r < K; r += kSortThreads) cmask[r] = sg.masks(cbox[r], carea[r]);
   for (int i = tid; i < 64 * wcap; i += kSortThreads) stripes[i] = 0u;
+  for (int i = tid; i < 2 * kHintCells; i += kSortThreads) (&s_hint[0][0])[i] = 0x7fffffff;
   if (tid < 2) s_next[tid] = 0;
+  if (tid == 0) s_nlist = 0;
   __syncthreads();
   int L = 0;                                           // kept boxes so far (CTA-uniform)
-  for (int c0 = 0; c0 < K && L < A.nms_topk; c0 += kChunk) {
-    const int nc = min(kChunk, K - c0);
+  int L_prev = 0;                                      // ... when the previous round tested its window
+  int w_end_prev = 0;                                  // end of the previous round's window: candidates below it carry state
+  for (int c0 = 0; c0 < K && L < A.nms_topk;) {
+    const int w_end = min(K, c0 + kWin);
     DAN_TICK();
-    // a. chunk vs kept list.  The kept list is indexed by stripe: bit j of xs[s] / ys[s] says that kept box j touches x / y
-    // stripe s.  The kept boxes a candidate can intersect are (OR of xs over its x stripes) AND (OR of ys over its y
-    // stripes): a group of G lanes owns one candidate, a lane one 32-bit word of the bitset, and only the set bits go
-    // through the exact test (the candidate leaves at the first suppressor).
-    if (L > 0) {
+    // a. window vs kept list.  Thread t owns candidate c0 + t.  A candidate that was in the previous window has met
+    // the first L_prev kept boxes already; a fresh one has met none.
+    const int my_r = c0 + tid;
+    const bool in_win = my_r < w_end;
+    {
+      bool alive = false, search = false;
+      int upto = 0;
+      if (in_win) {
+        const bool fresh = my_r >= w_end_prev;
+        alive = fresh ? true : (s_alive[my_r & (kWin - 1)] != 0);
+        upto = fresh ? 0 : L_prev;
+      }
+      if (alive && L > upto) {
+        const uint2 mm = cmask[my_r];
+        if (mm.x != 0u && mm.y != 0u) {                // (no area: no stripes, never suppressed)
+          // a1. the two hinted kept boxes of the cell of its centre: a member of a cluster of near duplicates dies here,
+          // after one or two exact tests by its own thread
+          const float4 me = cbox[my_r];
+          const float my_area = carea[my_r];
+          const int cl = sg.cell(me);
+          const int h0 = s_hint[0][cl], h1 = s_hint[1][cl];
+          bool dead = false;
+          if (h0 >= upto && h0 < L) dead = pair_suppresses(kbox[h0], karea[h0], me, my_area, thr);
+          if (!dead && h1 != h0 && h1 >= upto && h1 < L) dead = pair_suppresses(kbox[h1], karea[h1], me, my_area, thr);
+          alive = !dead;
+          search = !dead;
+        }
+      }
+      if (in_win) s_alive[my_r & (kWin - 1)] = alive ? 1 : 0;
+      const unsigned sm = __ballot_sync(0xffffffffu, search);
+      int base = 0;
+      if (lane == 0 && sm != 0u) base = atomicAdd(&s_nlist, __popc(sm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (search) s_list[base + __popc(sm & lt_mask)] = (unsigned short)tid;
+    }
+    __syncthreads();
+    // a2. the others against the kept list proper, which is indexed by stripe: bit j of xs[s] / ys[s] says that kept box j
+    // touches x / y stripe s.  The kept boxes a candidate can intersect are (OR of xs over its x stripes) AND (OR of ys
+    // over its y stripes): a group of G lanes owns one candidate, a lane one 32-bit word of the bitset, and only the set
+    // bits (beyond the boxes the candidate has met already) go through the exact test; the candidate leaves at the
+    // first suppressor, which becomes the cell's second hint.
+    const int nlist = s_nlist;
+    if (nlist > 0) {
       const int W = (L + 31) >> 5;
       const int G = W <= 8 ? 8 : (W <= 16 ? 16 : 32);        // lanes per candidate
       const int cpw = 32 / G;                                // candidates per warp pass
       const int gl = lane & (G - 1), sub = lane / G;
       const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (sub * G);
       while (true) {                                         // candidates are handed out dynamically: their cost varies a lot
-        int r0 = 0;
-        if (lane == 0) r0 = atomicAdd(&s_next[0], cpw);
-        r0 = __shfl_sync(0xffffffffu, r0, 0);
-        if (r0 >= nc) break;
-        const int r = r0 + sub;
-        const bool have = r < nc;
-        const float4 me = have ? cbox[c0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float my_area = have ? carea[c0 + r] : 0.f;
-        const uint2 mm = have ? cmask[c0 + r] : make_uint2(0u, 0u);      // (no area: no stripes, never suppressed)
+        int i0 = 0;
+        if (lane == 0) i0 = atomicAdd(&s_next[0], cpw);
+        i0 = __shfl_sync(0xffffffffu, i0, 0);
+        if (i0 >= nlist) break;
+        const bool have = i0 + sub < nlist;
+        const int r = c0 + (have ? (int)s_list[i0 + sub] : 0);
+        const float4 me = have ? cbox[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float my_area = have ? carea[r] : 0.f;
+        const uint2 mm = have ? cmask[r] : make_uint2(0u, 0u);
+        const int upto = (r >= w_end_prev) ? 0 : L_prev;
         bool sup = false;
         for (int wb = 0; wb < W; wb += G) {                  // one block of words unless the kept list is very long
           const int w = wb + gl;
           uint32_t poss = 0u;
-          if (w < W && mm.x != 0u && mm.y != 0u) {
+          if (w < W && w >= (upto >> 5) && mm.x != 0u && mm.y != 0u) {
             // (the stripes of a box are a contiguous range: independent loads, no address chain)
             uint32_t ax = 0u, ay = 0u;
             const int xe = 31 - __clz(mm.x), ye = 31 - __clz(mm.y);
@@ -724,6 +778,7 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
 #pragma unroll 2
             for (int st = __ffs(mm.y) - 1; st <= ye; ++st) ay |= ys[st * wcap + w];
             poss = ax & ay;
+            if (w == (upto >> 5)) poss &= ~((1u << (upto & 31)) - 1u);
           }
           while (__any_sync(0xffffffffu, poss != 0u && !sup)) {
             bool t = false;
@@ -731,51 +786,49 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
               const int j = (w << 5) + __ffs(poss) - 1;
               poss &= poss - 1u;
               t = pair_suppresses(kbox[j], karea[j], me, my_area, thr);
+              if (t) atomicExch(&s_hint[1][sg.cell(me)], j);
             }
             if ((__ballot_sync(0xffffffffu, t) & gmask) != 0u) sup = true;
           }
         }
-        if (have && gl == 0) s_flag[r] = sup ? 1 : 0;
+        if (have && gl == 0 && sup) s_alive[r & (kWin - 1)] = 0;
       }
-    } else {
-      if (tid < nc) s_flag[tid] = 0;
     }
     __syncthreads();
     DAN_TOCK(0);
     DAN_TICK();
-    // b. survivors in rank order (the first kChunk threads, named barrier 1)
-    if (tid < kChunk) {
-#ifdef DAN_PHASE_TIMING
-      t_b = clock64();
-#endif
-      const bool f = (tid < nc) && (s_flag[tid] == 0);
-      const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (lane == 0) s_wcnt[warp] = __popc(m);
-      if (tid < kChunkWords) { s_keptm[tid] = 0u; s_supm[tid] = 0u; }
-      DAN_LAP(5);
-      bar_sync_chunk();
-      DAN_LAP(6);
-      int base = 0, total = 0;
+    // b. the first kSurv candidates of the window that are still alive, in rank order; the window of the next round
+    // starts behind the last of them
+    const bool f = in_win && s_alive[my_r & (kWin - 1)] != 0;
+    const unsigned fm = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_wcnt[warp] = __popc(fm);
+    if (tid < kSurvWords) { s_keptm[tid] = 0u; s_supm[tid] = 0u; }
+    __syncthreads();
+    int total, ubase;
+    {
+      const int cw = (lane < kSortThreads / 32) ? s_wcnt[lane] : 0;
+      int incl = cw;
 #pragma unroll
-      for (int w = 0; w < kChunkWords; ++w) {
-        const int c = s_wcnt[w];
-        if (w < warp) base += c;
-        total += c;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
       }
-      if (f) {
-        const int u = base + __popc(m & lt_mask);
-        const float4 bx = cbox[c0 + tid];
-        const float ar = carea[c0 + tid];
-        s_surv[u] = tid;
-        s_sbox[u] = bx;
-        s_sarea[u] = ar;
-        s_smask[u] = cmask[c0 + tid];
+      total = __shfl_sync(0xffffffffu, incl, 31);
+      ubase = __shfl_sync(0xffffffffu, incl - cw, warp & 31);
+    }
+    if (f) {
+      const int u = ubase + __popc(fm & lt_mask);
+      if (u < kSurv) {
+        s_surv[u] = my_r;
+        s_sbox[u] = cbox[my_r];
+        s_sarea[u] = carea[my_r];
+        s_smask[u] = cmask[my_r];
+        if (u == kSurv - 1) s_cnext = my_r + 1;
       }
-      if (tid == 0) s_ns = total;
-      DAN_LAP(7);
     }
     __syncthreads();
-    const int ns = s_ns;
+    const int ns = min(total, kSurv);
+    const int c_next = (total >= kSurv) ? s_cnext : w_end;
     DAN_TOCK(1);
     DAN_TICK();
     // c. suppression bits among the survivors: warp -> row v, lanes -> 32 earlier survivors per step
@@ -804,40 +857,33 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
     __syncthreads();
     DAN_TOCK(2);
     DAN_TICK();
-    // d. relaxation: thread v owns survivor v (the first kChunk threads)
+    // d. relaxation: thread v owns survivor v (the first kSurv threads)
     int sweeps = 0;
-    if (tid < kChunk) {
-      uint32_t T[kChunkWords];
+    if (tid < kSurv) {
+      uint32_t T[kSurvWords];
       const int vw = tid >> 5;
       const uint32_t vbit = 1u << (tid & 31);
       const bool mine = tid < ns;
 #pragma unroll
-      for (int w = 0; w < kChunkWords; ++w) T[w] = (mine && (w << 5) < tid) ? s_T[tid][w] : 0u;
+      for (int w = 0; w < kSurvWords; ++w) T[w] = (mine && (w << 5) < tid) ? s_T[tid][w] : 0u;
       bool decided = !mine;
       bool open = true;
-#ifdef DAN_PHASE_TIMING
-      t_b = clock64();
-#endif
       while (open && sweeps < kMaxSweeps) {
         uint32_t hitm = 0u, pendm = 0u;
         if (!decided) {
 #pragma unroll
-          for (int w = 0; w < kChunkWords; ++w) {
+          for (int w = 0; w < kSurvWords; ++w) {
             const uint32_t kw = s_keptm[w], sw = s_supm[w];
             hitm |= T[w] & kw;
             pendm |= T[w] & ~(kw | sw);
           }
         }
-        DAN_LAP(8);
         bar_sync_chunk();                              // every thread has read the masks of the previous sweep
-        DAN_LAP(9);
         if (!decided) {
           if (hitm != 0u) { atomicOr(&s_supm[vw], vbit); decided = true; }
           else if (pendm == 0u) { atomicOr(&s_keptm[vw], vbit); decided = true; }
         }
-        DAN_LAP(10);
         open = bar_or_chunk(!decided);
-        DAN_LAP(11);
         ++sweeps;
       }
       if (open) {
@@ -846,25 +892,28 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
       }
       DAN_TOCK(3);
       DAN_TICK();
-      // e. append the kept survivors in rank order
-      int before = 0, nk = 0;
+      // e. append the kept survivors in rank order; a kept box becomes the first hint of its cell unless an earlier
+      // (higher scoring) one is centred there
+      int before = 0;
 #pragma unroll
-      for (int w = 0; w < kChunkWords; ++w) {
+      for (int w = 0; w < kSurvWords; ++w) {
         const int c = __popc(s_keptm[w]);
         if (w < vw) before += c;
-        nk += c;
       }
       if (tid < 2) s_next[tid] = 0;
+      if (tid == 2) s_nlist = 0;
       if (mine && (s_keptm[vw] & vbit)) {
         const int pos = L + before + __popc(s_keptm[vw] & (vbit - 1u));
         if (pos < A.nms_topk) {
-          kbox[pos] = s_sbox[tid];
+          const float4 bx = s_sbox[tid];
+          kbox[pos] = bx;
           karea[pos] = s_sarea[tid];
-          krank[pos] = c0 + s_surv[tid];
+          krank[pos] = s_surv[tid];
           const uint2 sm = s_smask[tid];
           const uint32_t bit = 1u << (pos & 31);
           for (uint32_t m = sm.x; m != 0u; m &= m - 1u) atomicOr(&xs[(__ffs(m) - 1) * wcap + (pos >> 5)], bit);
           for (uint32_t m = sm.y; m != 0u; m &= m - 1u) atomicOr(&ys[(__ffs(m) - 1) * wcap + (pos >> 5)], bit);
+          if (sm.x != 0u) atomicMin(&s_hint[0][sg.cell(bx)], pos);
         }
       }
     }
@@ -872,9 +921,12 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
     {
       int nk = 0;
 #pragma unroll
-      for (int w = 0; w < kChunkWords; ++w) nk += __popc(s_keptm[w]);
+      for (int w = 0; w < kSurvWords; ++w) nk += __popc(s_keptm[w]);
+      L_prev = L;
       L = min(L + nk, A.nms_topk);
     }
+    w_end_prev = w_end;
+    c0 = c_next;
 #ifdef DAN_PHASE_TIMING
     DAN_TOCK(4);
     n_sweeps += sweeps; n_surv += ns; ++n_chunks;

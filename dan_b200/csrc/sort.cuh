@@ -267,6 +267,9 @@ DAN_D int select_and_sort(const unsigned long long* __restrict__ keys, int cnt, 
     m = k;
   }
   DAN_PHASE(8);
+#ifdef DAN_NO_MERGE_SORT
+  s_spare = nullptr;
+#endif
   if (s_spare != nullptr && m > 128) {
     __syncthreads();
     merge_sort_smem_keys(s_keys, s_spare, m);

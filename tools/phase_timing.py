@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dan_b200 import build
 lib_dbg = "/tmp/libdan_b200_phase.so"
-cmd = ["nvcc"] + build.NVCC_FLAGS + ["-shared", "-DDAN_PHASE_TIMING"] + [os.path.join(build.CSRC, s) for s in build.SOURCES] + ["-o", lib_dbg]
+cmd = ["nvcc"] + build.NVCC_FLAGS + ["-shared", "-DDAN_PHASE_TIMING"] + os.environ.get("DAN_EXTRA_NVCC_FLAGS", "").split() + [os.path.join(build.CSRC, s) for s in build.SOURCES] + ["-o", lib_dbg]
 subprocess.run(cmd, check=True)
 from dan_b200 import _lib
 if "--prod" not in sys.argv:
