@@ -176,12 +176,13 @@ def require_device():
         raise RuntimeError("dan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
 
 
-def dev_ptr(t, dtype=None, name="tensor"):
-    """data_ptr() of a contiguous CUDA tensor (None -> NULL)."""
+def dev_ptr(t, dtype=None, name="tensor", allow_pinned=False):
+    """data_ptr() of a contiguous CUDA tensor (None -> NULL).  allow_pinned: a page-locked HOST tensor is accepted too
+    (arguments the kernels may read in place over PCIe, see dan_postprocess_batch in include/dan_b200.h)."""
     if t is None:
         return ctypes.c_void_p(0)
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
-        raise TypeError("%s must be a CUDA torch.Tensor (no CPU fallback)" % name)
+    if not isinstance(t, torch.Tensor) or not (t.is_cuda or (allow_pinned and t.is_pinned())):
+        raise TypeError("%s must be a CUDA torch.Tensor%s (no CPU fallback)" % (name, " or a pinned host tensor" if allow_pinned else ""))
     if dtype is not None and t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():

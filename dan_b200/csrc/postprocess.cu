@@ -63,6 +63,8 @@ struct PpArgs {
   unsigned long long* keys;   // [L, n]  L = batch * (C-1) lists
   int32_t* key_count;         // [L]
   int32_t* maybe;             // [L, n] anchors that pass the quick reject (fused filter; beyond shared memory)
+  float4* stash;              // [B, n] decoded + clipped box of every anchor that passed the filter, or NULL.  Used when
+                              // loc / boxes live in mapped HOST memory: a row then crosses PCIe once, not twice
   float* s_scores;            // sort_bboxes outputs [keep_topk]
   float4* s_boxes;
   int32_t* s_index;
@@ -161,7 +163,11 @@ DAN_D void filter_one(const PpArgs& A, int b, int a, bool live, int lane, unsign
     if (live) {
       p = fmul(cephes_expf(fsub(x[c], mx)), inv);
       if (p > A.select_thr) {                       // select_bboxes :24-36
-        if (!have_box) { box = pp_box(A, b, a); have_box = true; }
+        if (!have_box) {
+          box = pp_box(A, b, a);
+          have_box = true;
+          if (A.stash != nullptr) A.stash[(int64_t)b * A.n + a] = box;
+        }
         const float w = fadd(fsub(box.w, box.y), 1.f);   // filter_bboxes :50-59
         const float h = fadd(fsub(box.z, box.x), 1.f);
         pass = (w > A.min_size_p1) && (h > A.min_size_p1);
@@ -607,6 +613,7 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
         const float pr = fmul(e1, fdiv(1.f, fadd(e0, e1)));
         if (pr > A.select_thr) {                            // select_bboxes :24-36
           const float4 box = pp_box(A, b, a);
+          if (A.stash != nullptr) A.stash[(int64_t)b * A.n + a] = box;
           const float w = fadd(fsub(box.w, box.y), 1.f);    // filter_bboxes :50-59
           const float h = fadd(fsub(box.z, box.x), 1.f);
           if ((w > A.min_size_p1) && (h > A.min_size_p1)) {
@@ -655,7 +662,7 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
     __syncthreads();
     if (r < K) {
       const uint32_t idx = key_index(key);
-      const NmsBox nb = nms_norm(DECODE ? pp_box(A, b, (int)idx) : src_boxes[idx]);
+      const NmsBox nb = nms_norm(DECODE ? (A.stash != nullptr ? A.stash[(int64_t)b * A.n + idx] : pp_box(A, b, (int)idx)) : src_boxes[idx]);
       cbox[r] = make_float4(nb.y0, nb.x0, nb.y1, nb.x1);
       carea[r] = nb.area;
     }
@@ -1013,10 +1020,10 @@ __global__ void wait_detections_kernel(const int32_t* flags, const int32_t* stat
 // ---------------------------------------------------------------------------
 
 struct PpLayout {
-  size_t key_count, keys, maybe, s_key, s_key2, s_box, s_area, kept_box, kept_area, kept_rank, s_mask, stripes, total;
+  size_t key_count, keys, maybe, stash, s_key, s_key2, s_box, s_area, kept_box, kept_area, kept_rank, s_mask, stripes, total;
 };
 
-static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms) {
+static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms, int64_t stash_rows = 0) {
   PpLayout w;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
@@ -1024,6 +1031,7 @@ static PpLayout pp_layout(int64_t n, int64_t lists, int64_t keep_topk, bool nms)
   w.key_count = take(lists * 4);
   w.keys = take(lists * n * 8);
   w.maybe = take(nms ? lists * n * 4 : 0);
+  w.stash = take(stash_rows * 16);
   w.s_key = take(lists * ks * 8);
   w.s_key2 = take(lists * ks * 8);
   w.s_box = take(nms ? lists * ks * 16 : 0);
@@ -1092,7 +1100,7 @@ int dan_debug_phases(long long* h_out32) { return cudaMemcpyFromSymbol(h_out32, 
 
 size_t dan_postprocess_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t num_classes, int32_t keep_topk) {
   if (num_anchors < 0 || batch < 0 || num_classes < 2 || keep_topk < 1) return 0;
-  return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1), keep_topk, true).total;
+  return pp_layout(num_anchors, (int64_t)batch * (num_classes - 1), keep_topk, true, (int64_t)batch * num_anchors).total;
 }
 
 size_t dan_sort_workspace_bytes(int64_t n, int32_t keep_topk) {
@@ -1123,7 +1131,7 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
   DAN_REQUIRE(loc_pred == nullptr || (a_ymin && a_xmin && a_ymax && a_xmax), DAN_ERR_INVALID_ARGUMENT, "anchors needed to decode loc_pred");
   DAN_REQUIRE(aligned16(loc_pred) && aligned16(boxes_pred) && aligned16(out_boxes), DAN_ERR_INVALID_ARGUMENT, "box tensors must be 16-byte aligned");
   const int lists = batch * (p->num_classes - 1);
-  const PpLayout w = pp_layout(num_anchors, lists, p->keep_topk, true);
+  const PpLayout w = pp_layout(num_anchors, lists, p->keep_topk, true, (int64_t)batch * num_anchors);
   DAN_REQUIRE(workspace != nullptr && workspace_bytes >= w.total, DAN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
               workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1167,6 +1175,25 @@ static int postprocess_core(const dan_postprocess_params* p, const float* cls_pr
     A.peer_state = peers->state;
   }
   pp_bind(A, workspace, w);
+  // loc_pred / boxes_pred in page-locked HOST memory (cudaHostAlloc / cudaHostRegister; mapped under unified addressing):
+  // the kernels read only the rows of the anchors that pass the score threshold (~3 %), straight over PCIe, and keep
+  // the decoded box of such a row in the workspace so that the row is fetched once.  Pageable memory is refused.
+  {
+    const void* geo = loc_pred != nullptr ? static_cast<const void*>(loc_pred) : static_cast<const void*>(boxes_pred);
+    cudaPointerAttributes pa;
+    const cudaError_t e = cudaPointerGetAttributes(&pa, geo);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+    } else if (pa.type == cudaMemoryTypeHost) {
+      DAN_REQUIRE(pa.devicePointer != nullptr, DAN_ERR_INVALID_ARGUMENT, "loc_pred / boxes_pred: host memory that is not mapped for the device");
+      if (loc_pred != nullptr) A.loc = reinterpret_cast<const float4*>(pa.devicePointer);
+      else A.boxes = reinterpret_cast<const float4*>(pa.devicePointer);
+      A.stash = reinterpret_cast<float4*>(static_cast<char*>(workspace) + w.stash);
+    } else {
+      DAN_REQUIRE(pa.type != cudaMemoryTypeUnregistered, DAN_ERR_INVALID_ARGUMENT,
+                  "loc_pred / boxes_pred is pageable host memory: pass device memory or page-locked (pinned) host memory");
+    }
+  }
   // two classes: the NMS kernel filters its own image (one launch for the whole evaluation side)
   const bool fused = p->num_classes == 2 && (reinterpret_cast<uintptr_t>(cls_pred) & 7u) == 0;
   if (ev) DAN_CUDA(cudaEventRecord(ev[0], st));

@@ -371,7 +371,9 @@ def postprocess_params(num_classes, image_shape, select_threshold, min_size, kee
 def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=None, out=None, want_index=True,
                       workspace=None, profile=False, peers=None):
     """Batched fused parse_by_class (bbox_util.py:103-119).  cls_pred [B,N,C]; give loc_pred [B,N,4]
-    (+ anchors = (ymin,xmin,ymax,xmax)) or boxes_pred [B,N,4].  Returns Detections indexed [b, c-1]."""
+    (+ anchors = (ymin,xmin,ymax,xmax)) or boxes_pred [B,N,4].  Returns Detections indexed [b, c-1].
+    loc_pred / boxes_pred may be PINNED HOST tensors: the kernels then read only the rows of the anchors that pass the
+    score threshold, in place over PCIe (host-resident geometry, include/dan_b200.h)."""
     L.require_device()
     cls_pred = cls_pred.contiguous()
     if cls_pred.dim() != 3:
@@ -400,7 +402,8 @@ def postprocess_batch(params, cls_pred, loc_pred=None, boxes_pred=None, anchors=
     nbytes = L.lib().dan_postprocess_workspace_bytes(n, batch, c, params.keep_topk)
     ws = (workspace or _ws).get(nbytes, dev)
     args = [ctypes.byref(params), L.dev_ptr(cls_pred, torch.float32, "cls_pred"),
-            L.dev_ptr(loc_pred, torch.float32, "loc_pred"), L.dev_ptr(boxes_pred, torch.float32, "boxes_pred"), *aptr, n, batch,
+            L.dev_ptr(loc_pred, torch.float32, "loc_pred", allow_pinned=True),
+            L.dev_ptr(boxes_pred, torch.float32, "boxes_pred", allow_pinned=True), *aptr, n, batch,
             L.dev_ptr(boxes), L.dev_ptr(scores), L.dev_ptr(counts), L.dev_ptr(aidx), L.dev_ptr(kpos), L.dev_ptr(ws), nbytes,
             L.stream_ptr()]
     with torch.cuda.device(dev):

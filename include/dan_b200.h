@@ -213,6 +213,15 @@ int dan_nms_bboxes(const float* scores, const float* boxes, int64_t n, int32_t n
  * cls_pred [B,N,C] logits.  Exactly one of `loc_pred` ([B,N,4] offsets, decoded
  * in-kernel against the anchors like decode_anchors) or `boxes_pred` ([B,N,4]
  * already decoded boxes, what parse_by_class literally takes) must be non-NULL.
+ * HOST-RESIDENT GEOMETRY: `loc_pred` / `boxes_pred` may also point to page-locked
+ * host memory that is mapped for the device (cudaHostAlloc, cudaHostRegister; with
+ * unified addressing that is every pinned allocation).  Only the rows of anchors
+ * whose score passes `select_threshold` are ever read (~3 % for a detector's
+ * output), so the kernels fetch exactly those rows over PCIe, once (the decoded box
+ * is kept in the workspace), and the other rows never leave the host: 16 of the
+ * 24 bytes per anchor of a host-side caller's input are not transferred at all.
+ * `cls_pred` is read in full and must be device memory.  Pageable host memory is
+ * refused with DAN_ERR_INVALID_ARGUMENT.
  * ------------------------------------------------------------------------- */
 typedef struct dan_postprocess_params {
   int32_t num_classes;

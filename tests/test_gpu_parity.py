@@ -528,6 +528,80 @@ def test_parse_by_class_variants(cuda, oracle):
             np.testing.assert_array_equal(_np(det.keep_pos[0, c - 1])[:len(keep)], keep)
 
 
+def test_parse_by_class_host_resident_geometry(cuda, oracle):
+    """loc_pred / bboxes_pred in PINNED HOST memory (include/dan_b200.h, host-resident geometry): the kernels fetch only the
+    rows that pass the threshold, in place; results equal the oracle's and the device-resident run's bit for bit - two
+    classes (fused filter), three classes (separate filter kernel), decoded boxes, eagerly and replayed from a CUDA graph.
+    Pageable host memory is refused."""
+    import ctypes
+    import torch
+    from dan_b200 import _lib as L, functional as F
+    from dan_b200.utility import bbox_util as bu
+    size = (640, 640)
+    cfg = synthetic.pyramid_config("s3fd", size, border=0.)
+    a_np = synthetic.build_anchors(oracle.AnchorEncoder(None, None, PS), cfg)
+    an = np.stack(a_np[:4], -1)
+    anchors = [to_dev(v, cuda) for v in a_np[:4]]
+    preds = [synthetic.gen_predictions(520 + i, an, size=size, max_faces=80) for i in range(3)]
+    cls = np.stack([p[0] for p in preds])
+    loc = np.stack([p[1] for p in preds])
+    loc_host = torch.from_numpy(loc).pin_memory()
+    args = (list(size), to_dev(cls, cuda), 2, 0.01, 0, 5000, 750, 0.3)
+    ref = bu.parse_by_class_batch(*args, loc_pred=to_dev(loc, cuda), anchors=anchors)
+    det = bu.parse_by_class_batch(*args, loc_pred=loc_host, anchors=anchors)
+    for name in ("boxes", "scores", "counts", "anchor_index", "keep_pos"):
+        assert torch.equal(getattr(ref, name), getattr(det, name)), name
+    _, (sb, ss, _) = _oracle_parse(oracle, size, cls[1], loc[1], a_np)
+    np.testing.assert_array_equal(_np(det.scores[1, 0]), ss[1])
+    np.testing.assert_array_equal(_np(det.boxes[1, 0]), sb[1])
+    # decoded boxes on the host
+    boxes = np.stack([_oracle_parse(oracle, size, cls[b], loc[b], a_np)[0] for b in range(3)]).astype(np.float32)
+    det_b = bu.parse_by_class_batch(*args, bboxes_pred=torch.from_numpy(boxes).pin_memory())
+    assert torch.equal(det_b.scores, ref.scores) and torch.equal(det_b.boxes, ref.boxes)
+    # CUDA graph: the host pointer is baked into the graph; new rows written by the host between replays are picked up
+    params = F.postprocess_params(2, size, 0.01, 0, 5000, 750, 0.3, prior_scaling=PS)
+    cls_d = to_dev(cls, cuda)
+    ws = L.Workspace()
+    out = F.postprocess_batch(params, cls_d, loc_pred=loc_host, anchors=anchors, workspace=ws)      # sizes the workspace
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            out = F.postprocess_batch(params, cls_d, loc_pred=loc_host, anchors=anchors, workspace=ws,
+                                      out=(out.boxes, out.scores, out.counts, out.anchor_index, out.keep_pos))
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out.boxes, ref.boxes) and torch.equal(out.scores, ref.scores)
+    loc_host.copy_(torch.from_numpy(loc[::-1].copy()))                     # other offsets, same buffer
+    ref2 = bu.parse_by_class_batch(*args, loc_pred=to_dev(loc[::-1].copy(), cuda), anchors=anchors)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out.boxes, ref2.boxes) and torch.equal(out.scores, ref2.scores) and torch.equal(out.counts, ref2.counts)
+    # three classes: the separate filter kernel stashes, the NMS kernel reads the stash
+    rng = np.random.default_rng(31)
+    n = a_np[0].shape[0]
+    cls3 = rng.normal(0, 2.0, (1, n, 3)).astype(np.float32)
+    loc3 = rng.normal(0, 0.5, (1, n, 4)).astype(np.float32)
+    a3 = ([640, 640], to_dev(cls3, cuda), 3, 0.2, 10, 400, 100, 0.45)
+    r3 = bu.parse_by_class_batch(*a3, loc_pred=to_dev(loc3, cuda), anchors=anchors)
+    d3 = bu.parse_by_class_batch(*a3, loc_pred=torch.from_numpy(loc3).pin_memory(), anchors=anchors)
+    assert torch.equal(r3.boxes, d3.boxes) and torch.equal(r3.scores, d3.scores) and torch.equal(r3.keep_pos, d3.keep_pos)
+    # pageable host memory: python mirror and the C ABI both refuse
+    with pytest.raises(TypeError):
+        bu.parse_by_class_batch(*args, loc_pred=torch.from_numpy(loc), anchors=anchors)
+    pageable = np.ascontiguousarray(loc)
+    nb = L.lib().dan_postprocess_workspace_bytes(n, 3, 2, 5000)
+    w = ws.get(nb, cls_d.device)
+    rc = L.lib().dan_postprocess_batch(ctypes.byref(params), L.dev_ptr(cls_d), ctypes.c_void_p(pageable.ctypes.data), ctypes.c_void_p(0),
+                                       *[L.dev_ptr(a) for a in anchors], n, 3, L.dev_ptr(out.boxes), L.dev_ptr(out.scores),
+                                       L.dev_ptr(out.counts), ctypes.c_void_p(0), ctypes.c_void_p(0), L.dev_ptr(w), nb, L.stream_ptr())
+    assert rc == -1            # DAN_ERR_INVALID_ARGUMENT
+    torch.cuda.synchronize()
+
+
 def test_postprocess_properties_full_size(cuda):
     """size-independent properties at 1600^2 (213 294 anchors), batch 4: sorted scores, counts consistent, kept boxes
     mutually below the NMS threshold (no +1 IoU), idempotence of NMS on its own output."""
