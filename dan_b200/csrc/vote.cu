@@ -51,19 +51,52 @@ DAN_D bool vote_overlaps(const float4& h, float area_h, const float4& b, float t
   return o >= thr;                      // false for NaN, like numpy
 }
 
-// walks the members of one group in score order
+// Broad phase of the head search: the extent of the detections (+1 pixel on the far sides, the overlap convention above)
+// is cut into 32 stripes per axis.  A detection touches a contiguous range of stripes per axis, packed into 20 bits
+// (xlo | xhi << 5 | ylo << 10 | yhi << 15); kEverywhere marks a box that must meet every head in the exact test
+// (non-finite coordinates, a threshold <= 0 for which disjoint boxes "overlap" too).  vote_overlaps() can only be true
+// for thr > 0 when the intersection has positive width and height, i.e. when [x1, x2 + 1] and [y1, y2 + 1] of the two
+// boxes intersect - and intervals that intersect share a stripe, because the stripe of a coordinate is a monotone
+// function of it.
+constexpr uint32_t kEverywhere = 1u << 20;
+
+struct VoteStripes {
+  float xlo, xinv, ylo, yinv;
+  bool all;
+  DAN_D int stripe(float v, float lo, float inv) const { return min(max((int)fmul(fsub(v, lo), inv), 0), 31); }
+  DAN_D uint32_t range(const float4& b) const {
+    if (all || !(fabsf(b.x) < 1e30f && fabsf(b.y) < 1e30f && fabsf(b.z) < 1e30f && fabsf(b.w) < 1e30f)) return kEverywhere;
+    return (uint32_t)stripe(b.x, xlo, xinv) | ((uint32_t)stripe(fadd(b.z, 1.f), xlo, xinv) << 5) |
+           ((uint32_t)stripe(b.y, ylo, yinv) << 10) | ((uint32_t)stripe(fadd(b.w, 1.f), ylo, yinv) << 15);
+  }
+};
+
+// bit s set for every stripe s in [lo, hi]
+DAN_D uint32_t stripe_span(uint32_t lo, uint32_t hi) { return ((2u << hi) - 1u) & ~((1u << lo) - 1u); }
+
+// walks the members of one group in score order.  One WARP walks one group, all lanes in lock step (every lane holds
+// the same sums): the search for the next member looks at 32 positions at a time (one ballot) instead of one.
 struct MemberIter {
   const uint16_t* assign;
   const float4* box;
   const float* score;
-  int pos, n;
+  int pos, n;                           // next window of 32 positions to look at
+  int base;                             // first position of the window `pending` describes
+  unsigned pending;                     // members of the current window that have not been consumed
   uint16_t head;
   float sx, sy, sz, sw, mx;             // sequential sums of box * score (np.sum(axis=0)), running max score
-  DAN_D float next() {                  // score of the next member; accumulates its weighted box
-    while (assign[pos] != head) ++pos;
-    const float4 b = box[pos];
-    const float s = score[pos];
-    ++pos;
+  DAN_D float next() {                  // score of the next member; accumulates its weighted box (warp-uniform)
+    const int lane = threadIdx.x & 31;
+    while (pending == 0u) {             // (the caller asks for exactly count[head] members, so one more always exists)
+      const int p = pos + lane;
+      pending = __ballot_sync(0xffffffffu, p < n && assign[p] == head);
+      base = pos;
+      pos += 32;
+    }
+    const int i = base + __ffs(pending) - 1;
+    pending &= pending - 1u;
+    const float4 b = box[i];
+    const float s = score[i];
     sx = fadd(sx, fmul(b.x, s));
     sy = fadd(sy, fmul(b.y, s));
     sz = fadd(sz, fmul(b.z, s));
@@ -188,20 +221,56 @@ __global__ void __launch_bounds__(kSortThreads, 1) bbox_vote_kernel(const VoteAr
   __syncthreads();
 
   // ---- 2. heads in score order (:173-190), 32 candidate heads per round.
-  // Every thread keeps its 8 boxes in registers (rb[e], score rank rr[e]) with an `alive` bit each.
+  // Thread t owns the score ranks t, t + 1024, ...: an `alive` bit and the packed stripe ranges of each in registers.
   //   a. warp 0 lists the next (up to) 32 unassigned positions = the candidates of this round
   //   b. thread (k = warp, m = lane) tests candidate k against the earlier candidate m  -> 32 row masks
   //   c. every thread resolves the 32 candidates from the masks (bit operations): candidate k is a head unless an earlier
-  //      HEAD of the round overlaps it (then it joins the first such head)
-  //   d. every thread tests its own alive boxes behind the last candidate against the round's heads, in head order
-  // Three barriers per 32 heads.
+  //      HEAD of the round overlaps it (then it joins the first such head); warp s publishes which of the round's heads
+  //      touch x / y stripe s (two ballots)
+  //   d. every thread looks its own alive boxes behind the last candidate up in that index - (OR over the box's x
+  //      stripes) AND (OR over its y stripes) = the round's heads it can overlap - and runs the exact test on those
+  //      only, in head order (the first hit is the head it joins)
+  // Four barriers per 32 heads.
   __shared__ int s_cand[32];
   __shared__ unsigned s_mask[32];
   __shared__ unsigned s_selfok;
   __shared__ int s_ncand;
+  __shared__ unsigned s_xs[32], s_ys[32];
+  __shared__ float s_ext[kSortThreads / 32][4];
+  VoteStripes sg;
+  {
+    float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const float4 bx = rb[e];
+      if (rr[e] >= 0 && fabsf(bx.x) < 1e30f && fabsf(bx.y) < 1e30f && fabsf(bx.z) < 1e30f && fabsf(bx.w) < 1e30f) {
+        x0 = fminf(x0, bx.x); x1 = fmaxf(x1, fadd(bx.z, 1.f));
+        y0 = fminf(y0, bx.y); y1 = fmaxf(y1, fadd(bx.w, 1.f));
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, d)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, d));
+      y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, d)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, d));
+    }
+    if (lane == 0) { s_ext[warp][0] = x0; s_ext[warp][1] = x1; s_ext[warp][2] = y0; s_ext[warp][3] = y1; }
+    __syncthreads();
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      x0 = fminf(x0, s_ext[w][0]); x1 = fmaxf(x1, s_ext[w][1]);
+      y0 = fminf(y0, s_ext[w][2]); y1 = fmaxf(y1, s_ext[w][3]);
+    }
+    sg.xlo = x0; sg.ylo = y0;
+    sg.xinv = (x1 > x0) ? fdiv(32.f, fsub(x1, x0)) : 0.f;
+    sg.yinv = (y1 > y0) ? fdiv(32.f, fsub(y1, y0)) : 0.f;
+    sg.all = !(A.thr > 0.f);
+  }
+  uint32_t rq[kPer];                                       // packed stripe ranges of the thread's boxes
   unsigned alive = 0;
 #pragma unroll
-  for (int e = 0; e < kPer; ++e) alive |= (rr[e] >= 0) ? (1u << e) : 0u;
+  for (int e = 0; e < kPer; ++e) {
+    alive |= (rr[e] >= 0) ? (1u << e) : 0u;
+    rq[e] = (rr[e] >= 0) ? sg.range(rb[e]) : 0u;
+  }
   auto add_count = [&](int head, unsigned k) {
     atomicAdd(reinterpret_cast<unsigned int*>(count) + (head >> 1), k << ((head & 1) * 16));
   };
@@ -259,27 +328,44 @@ __global__ void __launch_bounds__(kSortThreads, 1) bbox_vote_kernel(const VoteAr
         assign[pos] = kGone;                               // NaN self IoU: deleted alone (:189-190)
       }
     }
+    {                                                      // warp s: the round's heads that touch x / y stripe s
+      uint32_t q = 0u;
+      const bool is_head = lane < ncand && ((heads >> lane) & 1u);
+      if (is_head) q = sg.range(box[s_cand[lane]]);
+      const bool every = (q & kEverywhere) != 0u;
+      const unsigned hx = __ballot_sync(0xffffffffu, is_head && (every || ((stripe_span(q & 31u, (q >> 5) & 31u) >> warp) & 1u)));
+      const unsigned hy = __ballot_sync(0xffffffffu, is_head && (every || ((stripe_span((q >> 10) & 31u, (q >> 15) & 31u) >> warp) & 1u)));
+      if (lane == 0) { s_xs[warp] = hx; s_ys[warp] = hy; }
+    }
 #pragma unroll
     for (int e = 0; e < kPer; ++e)                         // the candidates themselves are settled
-      if (rr[e] <= last) alive &= ~(1u << e);
-    {                                                      // d. (warp-uniform loop: no per-lane exits)
-      unsigned hm = heads;
-      while (hm) {
-        const int m = __ffs(hm) - 1;
-        hm &= hm - 1u;
-        const int hp = s_cand[m];
-        const float4 h = box[hp];
-        const float area_h = vote_area(h);
-        unsigned got = 0u;
+      if (tid + e * kSortThreads <= last) alive &= ~(1u << e);
+    __syncthreads();
 #pragma unroll
-        for (int e = 0; e < kPer; ++e) {
-          if (((alive >> e) & 1u) && vote_overlaps(h, area_h, rb[e], A.thr)) {
-            assign[rr[e]] = (uint16_t)hp;
+    for (int e = 0; e < kPer; ++e) {                       // d.
+      if ((alive >> e) & 1u) {
+        const uint32_t q = rq[e];
+        unsigned poss = heads;
+        if (!(q & kEverywhere)) {
+          unsigned ax = 0u, ay = 0u;
+          for (uint32_t st = q & 31u; st <= ((q >> 5) & 31u); ++st) ax |= s_xs[st];
+          for (uint32_t st = (q >> 10) & 31u; st <= ((q >> 15) & 31u); ++st) ay |= s_ys[st];
+          poss = ax & ay;
+        }
+        const int r = tid + e * kSortThreads;              // (the box itself stays in shared memory: it is needed rarely)
+        const float4 me = poss ? box[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+        while (poss) {                                     // ascending = head order: the first hit is the head it joins
+          const int m = __ffs(poss) - 1;
+          poss &= poss - 1u;
+          const int hp = s_cand[m];
+          const float4 h = box[hp];
+          if (vote_overlaps(h, vote_area(h), me, A.thr)) {
+            assign[r] = (uint16_t)hp;
             alive &= ~(1u << e);
-            ++got;
+            add_count(hp, 1u);
+            break;
           }
         }
-        if (got) add_count(hp, got);
       }
     }
     cur = last + 1;
@@ -319,20 +405,22 @@ __global__ void __launch_bounds__(kSortThreads, 1) bbox_vote_kernel(const VoteAr
   __syncthreads();
   const int groups = s_total;
   float* out = A.out + (int64_t)b * A.max_out * 5;
-  for (int g = tid; g < A.max_out; g += kSortThreads) {
+  for (int g = warp; g < A.max_out; g += kSortThreads / 32) {          // one warp per group (warp-uniform control flow)
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, o4 = 0.f;
     if (g < groups) {
       MemberIter it;
       it.assign = assign; it.box = box; it.score = score; it.n = n;
       it.head = qlist[g];
       it.pos = it.head;                 // the head is the first member of its own group (a deleted head has count 0)
+      it.base = 0;
+      it.pending = 0u;
       it.sx = it.sy = it.sz = it.sw = 0.f;
       it.mx = __int_as_float(0xff800000);
       const float ssum = numpy_pairwise(it, (int)count[it.head]);       // :199-201
       o0 = fdiv(it.sx, ssum); o1 = fdiv(it.sy, ssum); o2 = fdiv(it.sz, ssum); o3 = fdiv(it.sw, ssum);
       o4 = it.mx;                                                       // :200,202
     }
-    out[g * 5] = o0; out[g * 5 + 1] = o1; out[g * 5 + 2] = o2; out[g * 5 + 3] = o3; out[g * 5 + 4] = o4;
+    if (lane == 0) { out[g * 5] = o0; out[g * 5 + 1] = o1; out[g * 5 + 2] = o2; out[g * 5 + 3] = o3; out[g * 5 + 4] = o4; }
   }
   if (tid == 0) A.out_count[b] = groups;
   if (A.out_assign) {
