@@ -295,7 +295,8 @@ def run_cuda(args):
     a_train = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", IMAGE))
     a_eval = synthetic.build_anchors(enc, synthetic.pyramid_config("s3fd", IMAGE, border=0.))
     N = a_train[0].numel()
-    enc_params = F.encode_params(0.4, 0.4, ps, match_mining=True)
+    # (layout hint: the 160^2 / 80^2 / 40^2 levels are one-anchor-per-cell grids; results do not depend on it)
+    enc_params = F.encode_params(0.4, 0.4, ps, match_mining=True, pyramid=None if args.no_layout_hint else enc.pyramid)
     pp_params = F.postprocess_params(2, IMAGE, *PP, prior_scaling=ps)
 
     # ---- synthetic inputs: B distinct images per rank; buffer set r holds them rolled by r ----------------------
@@ -725,6 +726,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run encode and postprocess on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-layout-hint", action="store_true", help="encode without the pyramid layout hint (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -46,12 +46,17 @@ class Pyramid(ctypes.Structure):
     ]
 
 
+DAN_MAX_GRIDS = 8
+
+
 class EncodeParams(ctypes.Structure):
     _fields_ = [
         ("matcher", c_i32), ("ignore_threshold", c_f32), ("positive_threshold", c_f32),
         ("prior_scaling", c_f32 * 4), ("pa_scale", c_f32), ("debug", c_i32),
         ("negative_low_thres", c_f32), ("min_match", c_i32), ("stop_positive_thres", c_f32),
         ("ignore_between", c_i32), ("gt_max_first", c_i32),
+        ("num_grids", c_i32), ("grid_start", c_i32 * DAN_MAX_GRIDS), ("grid_w", c_i32 * DAN_MAX_GRIDS),
+        ("grid_h", c_i32 * DAN_MAX_GRIDS),
     ]
 
 

@@ -171,8 +171,17 @@ def dual_max_match(overlaps, low_thres, high_thres, ignore_between=True, gt_max_
 # ----------------------------------------------------------------------------------
 def encode_params(positive_threshold, ignore_threshold, prior_scaling, match_mining, pa_scale=0.0, debug=False,
                   negative_low_thres=0.0, min_match=6, stop_positive_thres=0.3, ignore_between=True,
-                  gt_max_first=True):
+                  gt_max_first=True, pyramid=None):
+    """dan_encode_params.  pyramid (optional, the dan_pyramid POD of make_pyramid / AnchorEncoder.get_all_anchors): fills
+    the LAYOUT HINT of the params - which stretches of the flat anchor arrays are row-major grids with one anchor per
+    cell - so that the encode kernels can give every warp a compact tile of cells.  Performance only: the results do
+    not depend on it.  The anchors passed to encode_batch must then be the ones that pyramid generates."""
     p = L.EncodeParams()
+    if pyramid is not None:
+        for start, w, h in grid_hint(pyramid):
+            if p.num_grids < L.DAN_MAX_GRIDS:
+                p.grid_start[p.num_grids], p.grid_w[p.num_grids], p.grid_h[p.num_grids] = start, w, h
+                p.num_grids += 1
     p.matcher = L.DAN_MATCH_MINING if match_mining else L.DAN_MATCH_DUAL
     p.ignore_threshold = float(ignore_threshold)
     p.positive_threshold = float(positive_threshold)
@@ -186,6 +195,18 @@ def encode_params(positive_threshold, ignore_threshold, prior_scaling, match_min
     p.ignore_between = 1 if ignore_between else 0
     p.gt_max_first = 1 if gt_max_first else 0
     return p
+
+
+def grid_hint(pyramid):
+    """[(first anchor, cells per row, rows)] of the pyramid levels the layout hint can describe: one anchor per cell,
+    level start a multiple of 32, width a multiple of 8, height a multiple of 4 (include/dan_b200.h)."""
+    out, start = [], 0
+    for i in range(pyramid.num_layers):
+        h, w, d = int(pyramid.layer_h[i]), int(pyramid.layer_w[i]), int(pyramid.depth[i])
+        if d == 1 and start % 32 == 0 and w > 0 and h > 0 and w % 8 == 0 and h % 4 == 0:
+            out.append((start, w, h))
+        start += h * w * d
+    return out
 
 
 def encode_batch(params, ymin, xmin, ymax, xmax, inside_mask, gt_boxes, gt_offsets, out=None, want_match=False,

@@ -102,12 +102,28 @@ class AnchorEncoder(object):
                         feat_strides, allowed_borders, should_clips, name=None):
         self._pyramid = F.make_pyramid(image_shape, anchors_height, anchors_width, anchors_depth, anchors_offsets,
                                        layer_shapes, feat_strides, allowed_borders, should_clips)
-        return F.generate_anchors(self._pyramid)
+        self._generated = F.generate_anchors(self._pyramid)
+        return self._generated
+
+    @property
+    def pyramid(self):
+        """dan_pyramid POD of the last get_all_anchors call (None before): functional.encode_params(pyramid=...) turns
+        it into the layout hint of the encode kernels."""
+        return getattr(self, "_pyramid", None)
+
+    def _hint_for(self, anchors):
+        """The layout hint is only used for the very tensors get_all_anchors returned (any other anchor set is encoded
+        without it: same results, strips instead of tiles)."""
+        gen = getattr(self, "_generated", None)
+        if gen is None or any(a is not g for a, g in zip(anchors, gen[:4])):
+            return None
+        return self._pyramid
 
     # ---- :275-387 ------------------------------------------------------------------
-    def _params(self, ignore_threshold, positive_threshold, match_mining, pa_scale, debug):
+    def _params(self, ignore_threshold, positive_threshold, match_mining, pa_scale, debug, anchors=None):
         return F.encode_params(positive_threshold, ignore_threshold, self._prior_scaling, match_mining,
-                               pa_scale=pa_scale, debug=debug)
+                               pa_scale=pa_scale, debug=debug,
+                               pyramid=self._hint_for(anchors) if anchors is not None else None)
 
     def _encode_one(self, bboxes, anchors, inside_mask, params):
         bboxes = L.as_f32(bboxes).view(-1, 4)
@@ -120,16 +136,18 @@ class AnchorEncoder(object):
         """encode anchors with ground truth on the fly (one image), anchor_manipulator.py:275-326.
 
         -> (gt_targets [N,4], gt_labels int64 [N], gt_scores [N], matched_gt_bbox*pos [N,4])"""
-        params = self._params(self._ignore_threshold, self._positive_threshold, match_mining, 0.0, debug)
-        return self._encode_one(bboxes, (anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax), inside_mask, params)
+        anchors = (anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax)
+        params = self._params(self._ignore_threshold, self._positive_threshold, match_mining, 0.0, debug, anchors)
+        return self._encode_one(bboxes, anchors, inside_mask, params)
 
     def encode_pa_anchors(self, bboxes, anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax, inside_mask,
                           ignore_threshold, positive_threshold, match_mining=True, scale=1., debug=False):
         """PyramidBox face/head/body encode, anchor_manipulator.py:328-387."""
         if not scale > 0:
             raise L.DanError(-1, "scale must be > 0")
-        params = self._params(ignore_threshold, positive_threshold, match_mining, float(scale), debug)
-        return self._encode_one(bboxes, (anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax), inside_mask, params)
+        anchors = (anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax)
+        params = self._params(ignore_threshold, positive_threshold, match_mining, float(scale), debug, anchors)
+        return self._encode_one(bboxes, anchors, inside_mask, params)
 
     # ---- batched additions (no analogue in the reference) ---------------------------
     def encode_anchors_batch(self, gt_boxes, gt_offsets, anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax,
@@ -137,14 +155,16 @@ class AnchorEncoder(object):
         """All images of a batch in one launch sequence.  gt_boxes [sum M,4], gt_offsets int32 [B+1] (CSR).
 
         -> EncodeResult(targets [B,N,4], labels [B,N], scores [B,N], matched_gt [B,N,4], match [B,N]|None)"""
-        params = self._params(self._ignore_threshold, self._positive_threshold, match_mining, 0.0, debug)
+        params = self._params(self._ignore_threshold, self._positive_threshold, match_mining, 0.0, debug,
+                              (anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax))
         return F.encode_batch(params, anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax, inside_mask, gt_boxes,
                               gt_offsets, out=out, want_match=want_match)
 
     def encode_pa_anchors_batch(self, gt_boxes, gt_offsets, anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax,
                                 inside_mask, ignore_threshold, positive_threshold, match_mining=True, scale=1.,
                                 debug=False, want_match=False, out=None):
-        params = self._params(ignore_threshold, positive_threshold, match_mining, float(scale), debug)
+        params = self._params(ignore_threshold, positive_threshold, match_mining, float(scale), debug,
+                              (anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax))
         return F.encode_batch(params, anchors_ymin, anchors_xmin, anchors_ymax, anchors_xmax, inside_mask, gt_boxes,
                               gt_offsets, out=out, want_match=want_match)
 

@@ -45,7 +45,7 @@ def test_struct_layouts_match_header(lib):
     """ctypes mirrors of the PODs have the C sizes (4-byte fields only, no padding)."""
     from dan_b200 import _lib
     assert ctypes.sizeof(_lib.Pyramid) == 4 * (3 + 4 * 16 + 4 * 16 + 2 * 128)
-    assert ctypes.sizeof(_lib.EncodeParams) == 4 * 14
+    assert ctypes.sizeof(_lib.EncodeParams) == 4 * (14 + 1 + 3 * 8)        # + layout hint: num_grids, 3 x DAN_MAX_GRIDS
     assert ctypes.sizeof(_lib.PostprocessParams) == 4 * 12
 
 

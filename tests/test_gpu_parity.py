@@ -927,6 +927,61 @@ def test_fused_encode_bucket_overflow_and_large_min_match(cuda, oracle, s3fd_anc
         assert n > 0
 
 
+@pytest.mark.parametrize("size", [(640, 640), (1024, 1024)])
+def test_fused_encode_layout_hint_is_neutral(cuda, oracle, size):
+    """dan_encode_params' layout hint (8 x 4 tiles of cells per warp instead of 32 x 1 strips) changes which warp holds
+    which anchor and nothing else: every output of the fused encode is bit-identical with and without it - mining
+    (with stage-2 patches and stage-3 compensation), dual matcher with both claim orders, encode_pa_anchors - and the
+    mining result equals the reference functor's.  Invalid hints are refused."""
+    import torch
+    from dan_b200 import functional as F, _lib as L
+    from dan_b200.utility import anchor_manipulator as am
+    cfg = synthetic.pyramid_config("s3fd", size)
+    enc = am.AnchorEncoder(0.4, 0.4, PS)
+    anchors = synthetic.build_anchors(enc, cfg)
+    grids = F.grid_hint(enc.pyramid)
+    assert len(grids) >= 3 and grids[0][0] == 0
+    gts = [synthetic.gen_faces(40 + i, 50) for i in range(4)] + [synthetic.gen_dense_tiny(5, lo=150, hi=200, snap=2.0),
+                                                                  np.zeros((0, 4), np.float32), synthetic.gen_adversarial("duplicate")]
+    scale = np.float32(size[0] / 640.0)
+    gts = [g * scale for g in gts]
+    cat, offs = synthetic.to_csr(gts)
+    cat_d, offs_d = to_dev(cat, cuda), to_dev(offs, cuda)
+    variants = [dict(match_mining=True), dict(match_mining=True, min_match=40, stop_positive_thres=0.05),
+                dict(match_mining=False, gt_max_first=True), dict(match_mining=False, gt_max_first=False, ignore_between=False),
+                dict(match_mining=True, pa_scale=0.5)]
+    for kw in variants:
+        plain = F.encode_batch(F.encode_params(0.4, 0.4, PS, **kw), *anchors[:4], anchors[4], cat_d, offs_d, want_match=True)
+        p_hint = F.encode_params(0.4, 0.4, PS, pyramid=enc.pyramid, **kw)
+        assert p_hint.num_grids == len(grids)
+        hinted = F.encode_batch(p_hint, *anchors[:4], anchors[4], cat_d, offs_d, want_match=True)
+        for name in ("targets", "labels", "scores", "matched_gt", "match"):
+            a, b = getattr(plain, name), getattr(hinted, name)
+            if a.dtype == torch.float32:
+                a, b = a.view(torch.int32), b.view(torch.int32)              # bit patterns (sign of zero included)
+            assert torch.equal(a, b), "%s differs with the layout hint (%s)" % (name, kw)
+    # the mirror uses the hint for the anchors it generated itself: against the reference functor
+    a_np = [_np(a) for a in anchors]
+    res = enc.encode_anchors_batch(cat_d, offs_d, *anchors[:4], anchors[4], match_mining=True, want_match=True)
+    a4 = np.stack(a_np[:4], -1)
+    for b in (0, 4, 5):
+        g = gts[b] if len(gts[b]) else np.array([[0., 0., 1., 1.]], np.float32)
+        ov = oracle.iou_matrix(a4, g) * a_np[4].astype(np.float32)[:, None]
+        rm, rs = oracle.small_mining_match(ov, 0., 0.4, 0.4, 6, 0.3, impl="reference" if _have_ref() else "port")
+        np.testing.assert_array_equal(_np(res.match[b]), rm)
+        np.testing.assert_array_equal(_np(res.scores[b]), rs)
+    # invalid hints
+    for start, w, h in ((16, 8, 4), (0, 12, 4), (0, 8, 6), (0, 8, 4 * (anchors[0].numel() // 32 + 1))):
+        bad = F.encode_params(0.4, 0.4, PS, match_mining=True)
+        bad.num_grids, bad.grid_start[0], bad.grid_w[0], bad.grid_h[0] = 1, start, w, h
+        with pytest.raises(L.DanError):
+            F.encode_batch(bad, *anchors[:4], anchors[4], cat_d, offs_d)
+    bad = F.encode_params(0.4, 0.4, PS, match_mining=True, pyramid=enc.pyramid)
+    bad.grid_start[1] = 0                                                  # overlaps grid 0
+    with pytest.raises(L.DanError):
+        F.encode_batch(bad, *anchors[:4], anchors[4], cat_d, offs_d)
+
+
 def test_fused_encode_many_needy_gts(cuda, oracle, s3fd_anchors_np):
     """more needy GTs than one window of pass 3 holds (64) and more than one scan range (1024), dense tiny faces that
     share candidate anchors: the serial dependence between the windows."""
