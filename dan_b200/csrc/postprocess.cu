@@ -571,11 +571,11 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
     const int key_cap = A.sort_bytes / 8;              // keys that fit the sort's shared memory
     if (tid == 0) { s_nmaybe = 0; s_nkeys = 0; }
     __syncthreads();
-    auto push = [&](int a) {
-      const int pos = atomicAdd(&s_nmaybe, 1);
+    auto put = [&](int pos, int a) {
       if (pos < kMaybeCap) s_maybe[pos] = a;
       else gmaybe[pos] = a;
     };
+    auto push = [&](int a) { put(atomicAdd(&s_nmaybe, 1), a); };
     // the image's logits as 16-byte vectors (two anchors); the row of an image starts 8-byte aligned only
     const float* x = A.cls + (int64_t)b * A.n * 2;
     const int head = (reinterpret_cast<uintptr_t>(x) & 15u) ? 1 : 0;
@@ -590,10 +590,20 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        // A warp looks at 64 consecutive anchors here.  Its survivors enter the list in ANCHOR order with one atomic per
+        // warp: the exact pass below then reads neighbouring box rows from neighbouring lanes, i.e. whole sectors - which
+        // matters when the rows live in host memory and every sector is a PCIe read.
         const int v = v0 + u * kSortThreads + tid;
-        if (v < nvec) {
-          if (f2_maybe(A, q[u].x, q[u].y)) push(head + 2 * v);
-          if (f2_maybe(A, q[u].z, q[u].w)) push(head + 2 * v + 1);
+        const bool p0 = v < nvec && f2_maybe(A, q[u].x, q[u].y);
+        const bool p1 = v < nvec && f2_maybe(A, q[u].z, q[u].w);
+        const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+        if ((m0 | m1) != 0u) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_nmaybe, __popc(m0) + __popc(m1));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          int pos = base + __popc(m0 & lt_mask) + __popc(m1 & lt_mask);
+          if (p0) put(pos++, head + 2 * v);
+          if (p1) put(pos, head + 2 * v + 1);
         }
       }
     }
