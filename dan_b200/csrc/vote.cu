@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) bbox_vote_kernel(const VoteAr
             assign[r] = (uint16_t)hp;
             alive &= ~(1u << e);
             add_count(hp, 1u);
-            break;
+            poss = 0u;                                     // (no `break`: the lanes of the warp leave the loop together,
+                                                           // racecheck saw them reach the barrier apart otherwise)
           }
         }
       }
