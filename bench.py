@@ -340,6 +340,9 @@ def run_cuda(args):
         sets.append({"host": h, "dev": d, "hp": hp, "recv": recv, "total_gt": int(offs[-1])})
     total_gt_mean = float(np.mean([s["total_gt"] for s in sets]))
 
+    # kernels of this library per step: enc_pass1, enc_pass2_find, enc_pass2_apply, enc_pass3, nms_greedy (+ the warp table of
+    # the layout hint, + the one-warp wait of the peer exchange at N > 1; the NCCL gather's kernel is not ours)
+    launches_per_step = KERNELS_PER_STEP + (1 if enc_params.num_grids > 0 else 0) + (1 if peers is not None else 0)
     log("inputs and exchange ready")
     def run_set(s, profile=False, host_loc=False):
         """host_loc: the box offsets stay in the pinned host buffer and the NMS kernel reads the rows it needs in place"""
@@ -683,7 +686,7 @@ def run_cuda(args):
                             if peers is not None else "ncclAllGather inside each step's CUDA graph (dan_gather_detections)"),
                         "gather_check": gather_check, "host_cores_per_rank": cores_per_rank, "numa_node_rank0": numa_node,
                         "native_so_loaded": [os.path.relpath(_lib.LIB_PATH, ROOT)]},
-                "clocks": clocks, "e2e": e2e, "e2e_copy_all": e2e_copy_all, "e2e_full": e2e_full, "gpu_launches": KERNELS_PER_STEP * K,
+                "clocks": clocks, "e2e": e2e, "e2e_copy_all": e2e_copy_all, "e2e_full": e2e_full, "gpu_launches": launches_per_step * K,
                 "roofline": roofline, "cpu_baseline": cpu_base,
                 "kernel_ms": kernel_ms, "step_kernel_ms_sum": step_kernel_sum,
                 "serial": {"ms_per_step": serial_ms / K, "value": world * B * K / (serial_ms * 1e-3), "unit": UNIT,

@@ -70,6 +70,32 @@ def test_anchor_count_and_pyramid_validation(lib):
     assert lib.dan_anchor_count(ctypes.byref(bad)) < 0
 
 
+def test_layout_hint_from_pyramid(lib):
+    """functional.grid_hint / encode_params(pyramid=...): only levels with one anchor per cell, a start that is a multiple of
+    32, a width that is a multiple of 8 and a height that is a multiple of 4 are described (include/dan_b200.h)."""
+    from dan_b200 import functional as F, synthetic
+    from dan_b200.utility.anchor_manipulator import AnchorEncoder
+    enc = AnchorEncoder(0.4, 0.4, [0.1, 0.1, 0.2, 0.2])
+
+    def pyramid(cfg):
+        hs, ws, ds = zip(*[enc.get_anchors_width_height(cfg["anchor_scales"][i], cfg["extra_scales"][i], cfg["anchor_ratios"][i])
+                           for i in range(len(cfg["layer_shapes"]))])
+        return F.make_pyramid(cfg["image_shape"], hs, ws, ds, cfg["offsets"], cfg["layer_shapes"], cfg["layer_strides"],
+                              cfg["allowed_borders"], cfg["should_clips"])
+    # 640^2: 160^2, 80^2, 40^2 qualify; 20^2 (width 20), 10^2, 5^2 do not
+    assert F.grid_hint(pyramid(synthetic.pyramid_config("s3fd", (640, 640)))) == [(0, 160, 160), (25600, 80, 80), (32000, 40, 40)]
+    # 1024^2: all six levels (256 ... 8 cells per side)
+    g = F.grid_hint(pyramid(synthetic.pyramid_config("s3fd", (1024, 1024))))
+    assert [w for _, w, _ in g] == [256, 128, 64, 32, 16, 8] and g[-1][0] == 256 ** 2 + 128 ** 2 + 64 ** 2 + 32 ** 2 + 16 ** 2
+    # two anchors per cell on the first level: that level is skipped, the others keep their (shifted) starts
+    cfg = synthetic.pyramid_config("s3fd", (640, 640))
+    cfg["extra_scales"] = [(24.,)] + [()] * 5
+    assert F.grid_hint(pyramid(cfg)) == [(51200, 80, 80), (57600, 40, 40)]
+    p = F.encode_params(0.4, 0.4, [0.1, 0.1, 0.2, 0.2], True, pyramid=pyramid(synthetic.pyramid_config("s3fd", (640, 640))))
+    assert p.num_grids == 3 and list(p.grid_start)[:3] == [0, 25600, 32000] and list(p.grid_w)[:3] == [160, 80, 40]
+    assert F.encode_params(0.4, 0.4, [0.1, 0.1, 0.2, 0.2], True).num_grids == 0
+
+
 def test_attr_validation_before_device(lib):
     """the op constructor's InvalidArgument conditions (small_mining_match.cc:292-305) are enforced at the C ABI."""
     null = ctypes.c_void_p(0)
