@@ -358,7 +358,10 @@ DAN_D bool f2_maybe(const PpArgs& A, float x0, float x1) {
 //   4. the first nms_topk kept boxes are written out in rank order, zero padded (bbox_util.py:80-90).
 // ---------------------------------------------------------------------------
 constexpr int kWin = kSortThreads;                     // candidates in the window: one per thread
-constexpr int kSurv = 128;                             // survivors resolved per round
+#ifndef DAN_NMS_SURV
+#define DAN_NMS_SURV 128
+#endif
+constexpr int kSurv = DAN_NMS_SURV;                    // survivors resolved per round
 constexpr int kSurvWords = kSurv / 32;
 constexpr int kMaxSweeps = 12;
 constexpr int kHintCells = 32 * 32;                    // one hint pair per (y stripe, x stripe) cell of a box centre
