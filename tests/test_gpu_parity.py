@@ -1174,4 +1174,16 @@ def test_peer_exchange_single_rank(cuda, oracle):
     torch.cuda.synchronize()
     assert torch.equal(px.recv(1), hp._slab.buf) and int(px.flags(1)[0]) == 3
     del graph
+    # the same step with the box offsets left in PINNED HOST memory (host-resident geometry through HotPath.step, with
+    # the peer stores): identical slab and identical encode outputs
+    ref_det = [t.clone() for t in hp._slab.views()]
+    ref_enc = [t.clone() for t in hp._enc_out[:4]]
+    for t in hp._slab.views():
+        t.fill_(-3)
+    loc_host = torch.from_numpy(np.stack([p[1] for p in preds])).pin_memory()
+    hp.step(gt_d, offs_d, cls, loc_host)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(ref_det, hp._slab.views()))
+    assert all(torch.equal(a, b) for a, b in zip(ref_det, hp.gathered()[0]))
+    assert all(torch.equal(a, b) for a, b in zip(ref_enc, hp._enc_out[:4]))
     px.close()
