@@ -960,6 +960,19 @@ def test_fused_encode_layout_hint_is_neutral(cuda, oracle, size):
             if a.dtype == torch.float32:
                 a, b = a.view(torch.int32), b.view(torch.int32)              # bit patterns (sign of zero included)
             assert torch.equal(a, b), "%s differs with the layout hint (%s)" % (name, kw)
+    # anchors outside the image masked out (border 0): the mask is read through the same warp -> anchor table
+    enc0 = am.AnchorEncoder(0.4, 0.4, PS)
+    anchors0 = synthetic.build_anchors(enc0, synthetic.pyramid_config("s3fd", size, border=0.))
+    assert 0 < int(anchors0[4].sum()) < anchors0[4].numel()
+    for kw in (dict(match_mining=True), dict(match_mining=False)):
+        plain = F.encode_batch(F.encode_params(0.4, 0.4, PS, **kw), *anchors0[:4], anchors0[4], cat_d, offs_d, want_match=True)
+        hinted = F.encode_batch(F.encode_params(0.4, 0.4, PS, pyramid=enc0.pyramid, **kw), *anchors0[:4], anchors0[4], cat_d, offs_d,
+                                want_match=True)
+        for name in ("targets", "labels", "scores", "matched_gt", "match"):
+            a, b = getattr(plain, name), getattr(hinted, name)
+            if a.dtype == torch.float32:
+                a, b = a.view(torch.int32), b.view(torch.int32)
+            assert torch.equal(a, b), "%s differs with the layout hint and an inside mask (%s)" % (name, kw)
     # the mirror uses the hint for the anchors it generated itself: against the reference functor
     a_np = [_np(a) for a in anchors]
     res = enc.encode_anchors_batch(cat_d, offs_d, *anchors[:4], anchors[4], match_mining=True, want_match=True)
