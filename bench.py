@@ -317,9 +317,24 @@ def run_cuda(args):
     # NVLink (CUDA IPC) and a one-warp kernel waits for the arrival flags; "nccl" = one ncclAllGather per step, one
     # communicator per lane (collectives of one communicator must not run concurrently, the lanes do)
     peers, gathers = None, [None] * L
+    gather_fallback = None
     if world > 1 and args.gather == "p2p":
-        peers = pipeline.PeerExchange(rank, world, dev, slab_words, num_sets=R)
-    elif world > 1:
+        # CUDA IPC can be unavailable (some container / vGPU set-ups): every rank then falls back to the NCCL gather.  The
+        # ranks agree on the outcome so that none of them is left waiting in the other path.
+        try:
+            peers = pipeline.PeerExchange(rank, world, dev, slab_words, num_sets=R)
+            ok, why = 1, ""
+        except Exception as e:      # noqa: BLE001 (reported in the JSON line)
+            peers, ok, why = None, 0, "%s: %s" % (type(e).__name__, e)
+        agreed = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if int(agreed.item()) == 0:
+            if peers is not None:
+                peers.close()
+                peers = None
+            gather_fallback = why or "another rank could not map the peer buffers"
+            log("peer exchange unavailable (%s): falling back to ncclAllGather" % gather_fallback)
+    if world > 1 and peers is None:
         gathers = [pipeline.DeviceGather(rank, world, dev) for _ in range(L)]
     sets = []
     for r in range(R):
@@ -684,7 +699,7 @@ def run_cuda(args):
                             "peer stores: the NMS kernel writes its slab rows into every rank's receive buffer over NVLink "
                             "(dan_postprocess_batch_peers) + a one-warp wait on the arrival flags, inside each step's CUDA graph"
                             if peers is not None else "ncclAllGather inside each step's CUDA graph (dan_gather_detections)"),
-                        "gather_check": gather_check, "host_cores_per_rank": cores_per_rank, "numa_node_rank0": numa_node,
+                        "gather_fallback": gather_fallback, "gather_check": gather_check, "host_cores_per_rank": cores_per_rank, "numa_node_rank0": numa_node,
                         "native_so_loaded": [os.path.relpath(_lib.LIB_PATH, ROOT)]},
                 "clocks": clocks, "e2e": e2e, "e2e_copy_all": e2e_copy_all, "e2e_full": e2e_full, "gpu_launches": launches_per_step * K,
                 "roofline": roofline, "cpu_baseline": cpu_base,
