@@ -739,7 +739,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough for 3x L2)")
-    ap.add_argument("--inflight", type=int, default=8, help="steps in flight (each on its own stream and workspaces)")
+    ap.add_argument("--inflight", type=int, default=10, help="steps in flight (each on its own stream and workspaces)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="detection exchange at N > 1")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run encode and postprocess on one stream")
