@@ -2,7 +2,7 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.
 tail -c 600 gpurun_out/r2b_n8.err
 python - <<'PY'
 import json
-d = json.load(open("gpurun_out/r2b_n8.json"))
+d = json.loads(open("gpurun_out/r2b_n8.json").read().splitlines()[-1])      # (NCCL prints its version on stdout first)
 print(round(d["value"]), d["ms_per_step"], d["serial"]["ms_per_step"], d["run"].get("host_cores_per_rank"), d["run"].get("numa_node_rank0"))
 for k in ("e2e", "e2e_copy_all", "e2e_full"):
     print(k, round(d[k]["value"]), d[k]["ms_per_step"], d[k].get("h2d_gbs_per_gpu"))
