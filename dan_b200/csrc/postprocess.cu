@@ -911,29 +911,40 @@ __global__ void DAN_NMS_BOUNDS nms_greedy_kernel(const PpArgs A, const float* __
         bar_sync_chunk();
       }
       DAN_TOCK(3);
-      DAN_TICK();
-      // e. append the kept survivors in rank order; a kept box becomes the first hint of its cell unless an earlier
-      // (higher scoring) one is centred there
-      int before = 0;
-#pragma unroll
-      for (int w = 0; w < kSurvWords; ++w) {
-        const int c = __popc(s_keptm[w]);
-        if (w < vw) before += c;
-      }
+    }
+    __syncthreads();
+    DAN_TICK();
+    // e. append the kept survivors in rank order; a kept box becomes the first hint of its cell unless an earlier
+    // (higher scoring) one is centred there.  ALL threads take part: kEntryThreads threads share one survivor, each
+    // enters the kept box into every kEntryThreads-th stripe of both axes (a big box touches 2 x 20 stripes: in the hands
+    // of the survivor's own thread alone this was the longest serial piece of a round).
+    {
+      constexpr int kEntryThreads = kSortThreads / kSurv;
+      const int v = tid / kEntryThreads, part = tid % kEntryThreads;
+      const int vw = v >> 5;
+      const uint32_t vbit = 1u << (v & 31);
       if (tid < 2) s_next[tid] = 0;
       if (tid == 2) s_nlist = 0;
-      if (mine && (s_keptm[vw] & vbit)) {
+      if (v < ns && (s_keptm[vw] & vbit)) {
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < kSurvWords; ++w)
+          if (w < vw) before += __popc(s_keptm[w]);
         const int pos = L + before + __popc(s_keptm[vw] & (vbit - 1u));
         if (pos < A.nms_topk) {
-          const float4 bx = s_sbox[tid];
-          kbox[pos] = bx;
-          karea[pos] = s_sarea[tid];
-          krank[pos] = s_surv[tid];
-          const uint2 sm = s_smask[tid];
+          const uint2 sm = s_smask[v];
           const uint32_t bit = 1u << (pos & 31);
-          for (uint32_t m = sm.x; m != 0u; m &= m - 1u) atomicOr(&xs[(__ffs(m) - 1) * wcap + (pos >> 5)], bit);
-          for (uint32_t m = sm.y; m != 0u; m &= m - 1u) atomicOr(&ys[(__ffs(m) - 1) * wcap + (pos >> 5)], bit);
-          if (sm.x != 0u) atomicMin(&s_hint[0][sg.cell(bx)], pos);
+          if (part == 0) {
+            const float4 bx = s_sbox[v];
+            kbox[pos] = bx;
+            karea[pos] = s_sarea[v];
+            krank[pos] = s_surv[v];
+            if (sm.x != 0u) atomicMin(&s_hint[0][sg.cell(bx)], pos);
+          }
+          for (int st = part; st < 32; st += kEntryThreads) {
+            if ((sm.x >> st) & 1u) atomicOr(&xs[st * wcap + (pos >> 5)], bit);
+            if ((sm.y >> st) & 1u) atomicOr(&ys[st * wcap + (pos >> 5)], bit);
+          }
         }
       }
     }
