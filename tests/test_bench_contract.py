@@ -44,3 +44,25 @@ def test_committed_cuda_line_has_the_contract_keys():
     assert line["clocks"]["reasons"] == [] or "sw_power_cap" in "".join(line["clocks"]["reasons"])
     ref = json.load(open(os.path.join(ROOT, "profiles", os.path.basename(path).replace("_bench.json", "_bench_reference_arm.json"))))
     assert ref["config"] == line["config"]          # the driver compares the two arms' config objects
+
+
+def test_rank_pinning_helpers():
+    """bench.py's host-side helpers for N > 1: cpulist parsing and the per-rank core slices (no GPU, no NVML needed: without
+    NUMA information every rank gets its own slice of the allowed cores, and the affinity is restored afterwards)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench._cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and bench._cpulist("") == []
+    assert bench.gpu_numa_nodes(2) in ([None, None], ) or all(v is None or v >= 0 for v in bench.gpu_numa_nodes(2))
+    if hasattr(os, "sched_getaffinity"):
+        before = os.sched_getaffinity(0)
+        try:
+            n0, node0 = bench.pin_rank_to_cores(0, 2)
+            mine0 = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, before)
+            n1, node1 = bench.pin_rank_to_cores(1, 2)
+            mine1 = os.sched_getaffinity(0)
+            assert n0 == len(mine0) >= 1 and n1 == len(mine1) >= 1 and mine0 <= before and mine1 <= before
+            if len(before) >= 2 and node0 is None and node1 is None:
+                assert not (mine0 & mine1)
+        finally:
+            os.sched_setaffinity(0, before)
